@@ -1,0 +1,703 @@
+// ProbabilisticMap::insertPointCloud on the device.
+//
+// Reference: bonxai_map/include/bonxai_map/probabilistic_map.hpp:141-203 (insertPointCloud, RayIterator),
+//            bonxai_map/src/probabilistic_map.cpp:30-54,77-106 (addHitPoint, addMissPoint, updateFreeCells).
+//
+// The reference walks points, then rays, sequentially and lets the per-cell update_id decide who updates a
+// cell. The same result is produced here by five data-parallel phases:
+//   1 classify   fp64 range clip + posToCoord per point; a scan-local hash finds, per endpoint voxel, the
+//                LOWEST point index (the point the reference would have processed first: it decides hit/miss)
+//   2 resolve    one thread per winning point: find-or-create the leaf, stale test (update_id == c against the
+//                PRE-scan state), emit an endpoint record and — if the voxel differs from the origin's — a ray
+//                with its range in the flat space of 8-cell ray chunks
+//   3 mark       the flat chunk space is walked by all threads: exact integer DDA restarted from the closed form
+//                at cell k0 = 8*chunk, setting bits in a per-leaf 512-bit "touched" mask (test before atomicOr)
+//   4 endpoints  hit/miss update + stamp of the endpoint cells
+//   5 apply      one warp per touched leaf: every touched cell whose update_id != c gets the clamped miss
+//                update and the stamp; endpoint cells were stamped in 4 and are skipped exactly like the
+//                reference's clearPoint skips them.
+// Phases 1-3 never change a cell value, so a scan that runs out of pool space is simply repeated after the
+// pools have grown; phases 4-5 cannot fail.
+#include "map.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace bnx {
+
+namespace {
+
+constexpr int TPB = 256;
+constexpr u32 CHUNK = 8;  // ray cells per work item
+constexpr unsigned long long CHUNK_FIELD = (1ull << 40) - 1ull;
+constexpr u32 OVF_TILES = 1u, OVF_CHUNKS = 2u;
+
+inline int blocks_for(i64 n, int tpb = TPB) { return (int)std::max<i64>(1, ceil_div(n, tpb)); }
+
+// ------------------------------------------------------------------------------------------------
+// phase 1: classify + endpoint dedupe
+// ------------------------------------------------------------------------------------------------
+// The per-point body of insertPointCloud (probabilistic_map.hpp:146-158) followed by posToCoord
+// (bonxai.hpp:404-410). Every fp64 operation is an explicitly rounded intrinsic: no FMA contraction, and
+// squaredNorm associates as (x*x + y*y) + z*z like the oracle's Eigen stand-in.
+__device__ __forceinline__ int4 classify_point(double px, double py, double pz, const ScanParams& p) {
+  const double vx = __dsub_rn(px, p.ox), vy = __dsub_rn(py, p.oy), vz = __dsub_rn(pz, p.oz);
+  const double sq = __dadd_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)), __dmul_rn(vz, vz));
+  int type = 0;
+  double ex = px, ey = py, ez = pz;
+  if (sq >= p.max_range_sqr) {
+    const double nrm = __dsqrt_rn(sq);
+    ex = __dadd_rn(p.ox, __dmul_rn(__ddiv_rn(vx, nrm), p.max_range));
+    ey = __dadd_rn(p.oy, __dmul_rn(__ddiv_rn(vy, nrm), p.max_range));
+    ez = __dadd_rn(p.oz, __dmul_rn(__ddiv_rn(vz, nrm), p.max_range));
+    type = 1;
+  }
+  return make_int4(__double2int_rd(__dmul_rn(ex, p.inv_res)), __double2int_rd(__dmul_rn(ey, p.inv_res)),
+                   __double2int_rd(__dmul_rn(ez, p.inv_res)), type);
+}
+
+template <bool F64, bool VEC4>
+__global__ void __launch_bounds__(TPB) k_classify(const unsigned char* __restrict__ pts, u32 stride, ScanParams p, ScanBuffers b) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n) return;
+  double px, py, pz;
+  if (F64) {
+    const double* q = reinterpret_cast<const double*>(pts + (size_t)i * stride);
+    px = q[0];
+    py = q[1];
+    pz = q[2];
+  } else if (VEC4) {
+    const float4 q = *reinterpret_cast<const float4*>(pts + (size_t)i * 16);  // pcl::PointXYZ
+    px = (double)q.x;
+    py = (double)q.y;
+    pz = (double)q.z;
+  } else {
+    const float* q = reinterpret_cast<const float*>(pts + (size_t)i * stride);
+    px = (double)q[0];
+    py = (double)q[1];
+    pz = (double)q[2];
+  }
+  const int4 e = classify_point(px, py, pz, p);
+  b.ep[i] = e;
+  __threadfence();  // ep[i] must be visible before a table slot can name i
+  // scan-local hash with indirect keys: a slot holds a point index, its key is ep[index].xyz
+  u32 slot = (u32)hash3(e.x, e.y, e.z) & p.hash_mask;
+  for (;;) {
+    u32 v = b.table[slot];
+    if (v == NONE) {
+      v = atomicCAS(&b.table[slot], NONE, i);
+      if (v == NONE) break;  // claimed an empty slot
+    }
+    const int4 o = __ldcg(&b.ep[v]);
+    if (o.x == e.x && o.y == e.y && o.z == e.z) {
+      if (i < v) atomicMin(&b.table[slot], i);
+      break;
+    }
+    slot = (slot + 1) & p.hash_mask;
+  }
+  b.slot_of[i] = slot;
+}
+
+// ------------------------------------------------------------------------------------------------
+// phase 2: resolve winners -> endpoint records + rays
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long warp_incl_scan(unsigned long long v, u32 lane) {
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= (u32)o) v += t;
+  }
+  return v;
+}
+
+// PENDING = false: one thread per point of the scan. PENDING = true: one thread per queued addHitPoint /
+// addMissPoint endpoint (already updated and stamped when it was queued; it only needs its ray).
+template <bool PENDING>
+__global__ void __launch_bounds__(TPB) k_resolve(GridDev g, ScanParams p, ScanBuffers b, u32 count) {
+  __shared__ unsigned long long s_warp[TPB / 32];
+  __shared__ u32 s_warp_e[TPB / 32];
+  __shared__ unsigned long long s_base, s_m;
+  __shared__ u32 s_base_e;
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_m = 0;
+
+  bool is_end = false;
+  int4 e = make_int4(0, 0, 0, 0);
+  u32 leaf = NONE, ci = 0, m = 0;
+  if (i < count) {
+    bool winner;
+    if (PENDING) {
+      e = b.pending[i];
+      winner = true;
+    } else {
+      winner = b.table[b.slot_of[i]] == i;
+      if (winner) e = b.ep[i];
+    }
+    if (winner) {
+      bool stale = false;
+      if (!PENDING) {
+        leaf = leaf_find_or_create(g, e.x, e.y, e.z);  // Accessor::value(coord, true), bonxai.hpp:469-494
+        if (leaf != NONE) {
+          ci = ((u32)e.x & 7u) | (((u32)e.y & 7u) << 3) | (((u32)e.z & 7u) << 6);
+          const bool on = (leaf_active(g, leaf)[ci >> 6] >> (ci & 63)) & 1ull;
+          const u32 word = on ? reinterpret_cast<const u32*>(leaf_cells(g, leaf))[ci] : 0u;
+          stale = (word & 0xFu) == p.c;  // probabilistic_map.cpp:34 / :47 — skipped AND no ray is cast
+        } else {
+          stale = true;  // pool exhausted: the scan will be repeated
+        }
+      }
+      if (!stale) {
+        is_end = true;
+        const i64 dx = (i64)e.x - p.Ox, dy = (i64)e.y - p.Oy, dz = (i64)e.z - p.Oz;
+        const u64 ax = dx < 0 ? -dx : dx, ay = dy < 0 ? -dy : dy, az = dz < 0 ? -dz : dz;
+        m = (u32)max(max(ax, ay), az);  // probabilistic_map.hpp:180; the ray has exactly m cells (end excluded)
+      }
+    }
+  }
+  u32 chunks = m / CHUNK + (m % CHUNK != 0);
+  if (chunks > p.max_chunks) {  // would overflow the packed counter: refuse the scan (BNX_ERR_UNSUPPORTED)
+    atomicOr(&b.sc->overflow, OVF_CHUNKS);
+    chunks = 0;
+    m = 0;
+  }
+  const unsigned long long mine = is_end && m ? ((1ull << 40) | chunks) : 0ull;
+  // block-wide exclusive scans: packed (rays, chunks) and endpoint count
+  unsigned long long incl = warp_incl_scan(mine, lane);
+  const u32 eballot = __ballot_sync(0xffffffffu, is_end && !PENDING);
+  const u32 e_excl_w = __popc(eballot & ((1u << lane) - 1u));
+  if (lane == 31) s_warp[warp] = incl;
+  if (lane == 0) s_warp_e[warp] = __popc(eballot);
+  unsigned long long msum = m;
+  for (int o = 16; o; o >>= 1) msum += __shfl_xor_sync(0xffffffffu, msum, o);
+  __syncthreads();
+  if (lane == 0 && msum) atomicAdd(&s_m, msum);
+  if (threadIdx.x == 0) {
+    unsigned long long tot = 0;
+    u32 tot_e = 0;
+    for (int k = 0; k < TPB / 32; ++k) {
+      const unsigned long long c = s_warp[k];
+      s_warp[k] = tot;
+      tot += c;
+      const u32 ce = s_warp_e[k];
+      s_warp_e[k] = tot_e;
+      tot_e += ce;
+    }
+    s_base = tot ? atomicAdd(&b.sc->ray_chunk, tot) : 0ull;
+    s_base_e = tot_e ? atomicAdd(&b.sc->n_endpoints, tot_e) : 0u;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && s_m) atomicAdd(&b.sc->sum_m, s_m);
+  if (is_end && !PENDING) b.ends[s_base_e + s_warp_e[warp] + e_excl_w] = make_uint2(leaf, ci | ((u32)e.w << 16));
+  if (mine) {
+    const unsigned long long at = s_base + s_warp[warp] + (incl - mine);
+    const u32 ray = (u32)(at >> 40);
+    const unsigned long long cb = at & CHUNK_FIELD;
+    if (cb + chunks > 0xFFFFFFF0ull) {
+      atomicOr(&b.sc->overflow, OVF_CHUNKS);
+    } else {
+      b.rays[ray] = make_int4(e.x, e.y, e.z, (int)(u32)cb);
+      // every 32-chunk tile whose first chunk lies inside this ray learns its owner
+      const u32 t0 = ((u32)cb + 31u) >> 5, t1 = ((u32)cb + chunks - 1u) >> 5;
+      for (u32 t = t0; t <= t1; ++t) {
+        if (t < p.tile_cap) {
+          b.tile_first[t] = ray;
+        } else {
+          atomicOr(&b.sc->overflow, OVF_TILES);
+          break;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// phase 3: mark ray cells
+// ------------------------------------------------------------------------------------------------
+struct LeafCursor {
+  int bx, by, bz;  // current leaf key = coord >> 3
+  int rx, ry, rz;  // current root key = coord >> 5
+  u32 inner, leaf;
+  u32 word;  // current 64-bit word of the touched mask (= z & 7)
+  unsigned long long bits;
+  bool valid;
+};
+
+__device__ __forceinline__ void cursor_flush(const GridDev& g, LeafCursor& c) {
+  if (c.bits && c.leaf != NONE) {
+    unsigned long long* t = reinterpret_cast<unsigned long long*>(leaf_touched(g, c.leaf)) + c.word;
+    if ((*t & c.bits) != c.bits) atomicOr(t, c.bits);  // test first: the leaves around the sensor are hit by every ray
+  }
+  c.bits = 0;
+}
+
+__device__ __forceinline__ void cursor_visit(const GridDev& g, const ScanParams& p, const ScanBuffers& b, LeafCursor& c, int x, int y, int z) {
+  const int bx = x >> 3, by = y >> 3, bz = z >> 3;
+  if (!c.valid || bx != c.bx || by != c.by || bz != c.bz) {
+    cursor_flush(g, c);
+    const int rx = x >> 5, ry = y >> 5, rz = z >> 5;
+    if (!c.valid || rx != c.rx || ry != c.ry || rz != c.rz) {
+      const int kx = x & ~31, ky = y & ~31, kz = z & ~31;
+      c.inner = root_find(g, kx, ky, kz);
+      if (c.inner == NONE) c.inner = root_find_or_insert(g, kx, ky, kz);
+      c.rx = rx;
+      c.ry = ry;
+      c.rz = rz;
+    }
+    c.leaf = c.inner == NONE ? NONE : leaf_in_inner_or_create(g, c.inner, x, y, z);
+    c.bx = bx;
+    c.by = by;
+    c.bz = bz;
+    c.valid = true;
+    c.word = (u32)z & 7u;
+    if (c.leaf != NONE) {
+      u32* st = leaf_stamp(g, c.leaf);
+      if (*st != p.seq && atomicExch(st, p.seq) != p.seq) {
+        const u32 at = atomicAdd(&b.sc->n_touched, 1u);
+        if (at < p.touched_cap) b.touched[at] = c.leaf;
+      }
+    }
+  } else if (((u32)z & 7u) != c.word) {
+    cursor_flush(g, c);
+    c.word = (u32)z & 7u;
+  }
+  c.bits |= 1ull << (((u32)x & 7u) | (((u32)y & 7u) << 3));
+}
+
+// Cells k0 .. min(k0+8, m)-1 of the ray origin -> end. Cell k of RayIterator (probabilistic_map.hpp:162-203)
+// is origin + sign * floor((2*k*|d| + m) / (2*m)) per axis, with residual error k*|d| - pos*m: the walk is
+// restarted from that closed form and then advanced with the reference's own error accumulator.
+template <typename E>
+__device__ __forceinline__ void walk_chunk(const GridDev& g, const ScanParams& p, const ScanBuffers& b, const int4 ray, u32 k0) {
+  const i64 dx = (i64)ray.x - p.Ox, dy = (i64)ray.y - p.Oy, dz = (i64)ray.z - p.Oz;
+  const u32 ax = (u32)(dx < 0 ? -dx : dx), ay = (u32)(dy < 0 ? -dy : dy), az = (u32)(dz < 0 ? -dz : dz);
+  const int sx = dx < 0 ? -1 : 1, sy = dy < 0 ? -1 : 1, sz = dz < 0 ? -1 : 1;
+  const u32 m = max(max(ax, ay), az);
+  const u32 k1 = min(k0 + CHUNK, m);
+  u32 px, py, pz;
+  if (m < 32768u) {
+    px = (2u * k0 * ax + m) / (2u * m);
+    py = (2u * k0 * ay + m) / (2u * m);
+    pz = (2u * k0 * az + m) / (2u * m);
+  } else {
+    px = (u32)((2ull * k0 * ax + m) / (2ull * m));
+    py = (u32)((2ull * k0 * ay + m) / (2ull * m));
+    pz = (u32)((2ull * k0 * az + m) / (2ull * m));
+  }
+  E ex = (E)((i64)k0 * ax - (i64)px * m), ey = (E)((i64)k0 * ay - (i64)py * m), ez = (E)((i64)k0 * az - (i64)pz * m);
+  int x = p.Ox + sx * (int)px, y = p.Oy + sy * (int)py, z = p.Oz + sz * (int)pz;
+  LeafCursor c;
+  c.valid = false;
+  c.bits = 0;
+  c.leaf = NONE;
+  c.inner = NONE;
+  for (u32 k = k0; k < k1; ++k) {
+    cursor_visit(g, p, b, c, x, y, z);
+    ex += (E)ax;
+    ey += (E)ay;
+    ez += (E)az;
+    if ((ex << 1) >= (E)m) {
+      x += sx;
+      ex -= (E)m;
+    }
+    if ((ey << 1) >= (E)m) {
+      y += sy;
+      ey -= (E)m;
+    }
+    if ((ez << 1) >= (E)m) {
+      z += sz;
+      ez -= (E)m;
+    }
+  }
+  cursor_flush(g, c);
+}
+
+__global__ void __launch_bounds__(TPB) k_mark(GridDev g, ScanParams p, ScanBuffers b) {
+  const unsigned long long rc = b.sc->ray_chunk;
+  const u32 n_rays = (u32)(rc >> 40);
+  const u32 total = (u32)(rc & CHUNK_FIELD);
+  if (b.sc->overflow) return;
+  const u32 lane = threadIdx.x & 31;
+  const u32 warps = gridDim.x * (TPB / 32);
+  for (u32 tile = blockIdx.x * (TPB / 32) + (threadIdx.x >> 5); (u64)tile * 32 < total; tile += warps) {
+    const u32 c0 = tile * 32;
+    const u32 r_first = b.tile_first[tile];
+    // which of the next 32 rays start inside this tile? bit j = a ray starts at chunk c0 + j
+    const u32 rb = r_first + 1 + lane;
+    u32 bit = 0;
+    if (rb < n_rays) {
+      const u32 base = (u32)b.rays[rb].w;
+      if (base - c0 < 32u) bit = 1u << (base - c0);
+    }
+    const u32 starts = __reduce_or_sync(0xffffffffu, bit);
+    const u32 chunk = c0 + lane;
+    if (chunk < total) {
+      const u32 r = r_first + __popc(starts & ((2u << lane) - 1u));
+      const int4 ray = b.rays[r];
+      const u32 k0 = (chunk - (u32)ray.w) * CHUNK;
+      const i64 dx = (i64)ray.x - p.Ox, dy = (i64)ray.y - p.Oy, dz = (i64)ray.z - p.Oz;
+      const u64 mm = max(max(dx < 0 ? -dx : dx, dy < 0 ? -dy : dy), dz < 0 ? -dz : dz);
+      if (mm < (1u << 29)) {
+        walk_chunk<int>(g, p, b, ray, k0);
+      } else {
+        walk_chunk<i64>(g, p, b, ray, k0);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// phase 4 / 5: apply
+// ------------------------------------------------------------------------------------------------
+// addHitPoint / addMissPoint on the winning endpoint voxels, probabilistic_map.cpp:30-54
+__global__ void __launch_bounds__(TPB) k_apply_endpoints(GridDev g, ScanParams p, ScanBuffers b) {
+  if (g.ctr->error | b.sc->overflow) return;
+  const u32 n = b.sc->n_endpoints;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint2 rec = b.ends[i];
+    const u32 leaf = rec.x, ci = rec.y & 0xFFFFu, type = rec.y >> 16;
+    u32* cell = reinterpret_cast<u32*>(leaf_cells(g, leaf)) + ci;
+    unsigned long long* act = reinterpret_cast<unsigned long long*>(leaf_active(g, leaf)) + (ci >> 6);
+    const unsigned long long bit = 1ull << (ci & 63);
+    const bool on = (*act & bit) != 0;
+    const u32 word = on ? *cell : 0u;  // a missing cell is created as CellT{}: id 0, probability 0
+    i32 prob = (i32)word >> 4;
+    prob = type ? max(prob + p.miss, p.cmin) : min(prob + p.hit, p.cmax);
+    *cell = ((u32)prob << 4) | p.c;
+    if (!on) atomicOr(act, bit);
+  }
+}
+
+// clearPoint over the union of all rays, probabilistic_map.cpp:81-89: one warp per touched leaf
+__global__ void __launch_bounds__(TPB) k_apply_leaves(GridDev g, ScanParams p, ScanBuffers b) {
+  if (g.ctr->error | b.sc->overflow) return;
+  const u32 n = min(b.sc->n_touched, p.touched_cap);
+  const u32 lane = threadIdx.x & 31;
+  const u32 warps = gridDim.x * (TPB / 32);
+  u32 changed = 0;
+  for (u32 t = blockIdx.x * (TPB / 32) + (threadIdx.x >> 5); t < n; t += warps) {
+    const u32 leaf = b.touched[t];
+    unsigned long long* touched = reinterpret_cast<unsigned long long*>(leaf_touched(g, leaf));
+    unsigned long long* active = reinterpret_cast<unsigned long long*>(leaf_active(g, leaf));
+    u32* cells = reinterpret_cast<u32*>(leaf_cells(g, leaf));
+    unsigned long long tw = 0, aw = 0;
+    if (lane < 8) {
+      tw = touched[lane];
+      aw = active[lane];
+    }
+#pragma unroll
+    for (u32 w = 0; w < 8; ++w) {
+      const unsigned long long t64 = __shfl_sync(0xffffffffu, tw, w);
+      if (t64 == 0) continue;
+      const unsigned long long a64 = __shfl_sync(0xffffffffu, aw, w);
+#pragma unroll
+      for (u32 half = 0; half < 2; ++half) {
+        const u32 bit = half * 32 + lane;
+        if ((t64 >> bit) & 1ull) {
+          u32* cell = cells + w * 64 + bit;
+          const u32 word = ((a64 >> bit) & 1ull) ? *cell : 0u;
+          if ((word & 0xFu) != p.c) {
+            const i32 prob = max(((i32)word >> 4) + p.miss, p.cmin);
+            *cell = ((u32)prob << 4) | p.c;
+            ++changed;
+          }
+        }
+      }
+    }
+    if (lane < 8 && tw) {
+      active[lane] = aw | tw;
+      touched[lane] = 0ull;
+    }
+  }
+  for (int o = 16; o; o >>= 1) changed += __shfl_xor_sync(0xffffffffu, changed, o);
+  if (lane == 0 && changed) atomicAdd(&b.sc->n_changed, changed);
+}
+
+// public addHitPoint / addMissPoint (probabilistic_map.cpp:30-54): update now, queue the ray
+__global__ void k_add_point(GridDev g, ScanParams p, ScanBuffers b, int4 e, u32 at, u32* queued) {
+  const u32 leaf = leaf_find_or_create(g, e.x, e.y, e.z);
+  *queued = 0;
+  if (leaf == NONE) return;
+  const u32 ci = ((u32)e.x & 7u) | (((u32)e.y & 7u) << 3) | (((u32)e.z & 7u) << 6);
+  u32* cell = reinterpret_cast<u32*>(leaf_cells(g, leaf)) + ci;
+  unsigned long long* act = reinterpret_cast<unsigned long long*>(leaf_active(g, leaf)) + (ci >> 6);
+  const unsigned long long bit = 1ull << (ci & 63);
+  const bool on = (*act & bit) != 0;
+  const u32 word = on ? *cell : 0u;
+  if (!on) {
+    *act |= bit;
+    *cell = 0u;
+  }
+  if ((word & 0xFu) != p.c) {
+    i32 prob = (i32)word >> 4;
+    prob = e.w ? max(prob + p.miss, p.cmin) : min(prob + p.hit, p.cmax);
+    *cell = ((u32)prob << 4) | p.c;
+    b.pending[at] = e;
+    *queued = 1;
+  }
+}
+
+// isOccupied / isUnknown / isFree, probabilistic_map.cpp:56-75
+__global__ void __launch_bounds__(TPB) k_query(GridDev g, const i32* __restrict__ xyz, i64 n, int kind, i32 thr, u8* __restrict__ out) {
+  for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+    const int x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+    const u32 leaf = leaf_find(g, x, y, z);
+    bool r = kind == BNX_UNKNOWN;  // missing cell: unknown, neither occupied nor free
+    if (leaf != NONE) {
+      const u32 ci = ((u32)x & 7u) | (((u32)y & 7u) << 3) | (((u32)z & 7u) << 6);
+      if ((leaf_active(g, leaf)[ci >> 6] >> (ci & 63)) & 1ull) {
+        const i32 prob = (i32) reinterpret_cast<const u32*>(leaf_cells(g, leaf))[ci] >> 4;
+        r = kind == BNX_OCCUPIED ? prob > thr : kind == BNX_UNKNOWN ? prob == thr : prob < thr;
+      }
+    }
+    out[i] = r;
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+Map::~Map() {
+  if (grid.stream()) cudaStreamSynchronize(grid.stream());
+  if (d_sc_) cudaFree(d_sc_);
+  if (h_status_) cudaFreeHost(h_status_);
+  for (auto& e : ev_)
+    if (e) cudaEventDestroy(e);
+}
+
+static i32 logods_host(float prob) {  // probabilistic_map.hpp:34-36
+  return (i32)(1e6 * std::log(prob / (1.0 - prob)));
+}
+
+int Map::init(double resolution) {
+  BNX_TRY(grid.init(resolution, 2, 3, 4));  // probabilistic_map.cpp:14-16
+  options[0] = logods_host(0.4f);
+  options[1] = logods_host(0.7f);
+  options[2] = logods_host(0.12f);
+  options[3] = logods_host(0.97f);
+  options[4] = logods_host(0.5f);
+  BNX_CUDA(cudaMalloc(&d_sc_, sizeof(ScanCounters)));
+  BNX_CUDA(cudaMallocHost(&h_status_, sizeof(Status)));
+  for (auto& e : ev_) BNX_CUDA(cudaEventCreate(&e));
+  buf_.sc = d_sc_;
+  BNX_TRY(b_pending_.reserve(1024 * sizeof(int4)));
+  buf_.pending = b_pending_.as<int4>();
+  return BNX_OK;
+}
+
+int Map::reserve_scan(i64 n, i64 stride_bytes, double max_range) {
+  (void)stride_bytes;
+  const size_t np = (size_t)n + n_pending_ + 32;
+  BNX_TRY(b_ep_.reserve(np * sizeof(int4)));
+  BNX_TRY(b_slot_.reserve(np * 4));
+  BNX_TRY(b_ends_.reserve(np * sizeof(uint2)));
+  BNX_TRY(b_rays_.reserve(np * sizeof(int4)));
+  u64 slots = 1024;
+  while (slots < (u64)n * 2) slots <<= 1;
+  BNX_TRY(b_table_.reserve(slots * 4));
+  // 32-chunk tiles: estimated from the longest possible ray, grown on overflow
+  double cells = std::isfinite(max_range) ? std::ceil(max_range * grid.inv_resolution) + 2.0 : 512.0;
+  cells = std::min(cells, 4096.0);
+  const size_t tiles = (size_t)((double)np * (cells / CHUNK + 1.0) / 32.0) + np / 32 + 64;
+  BNX_TRY(b_tiles_.reserve(tiles * 4));
+  BNX_TRY(b_touched_.reserve((size_t)grid.dev().leaf_cap * 4));
+  buf_.ep = b_ep_.as<int4>();
+  buf_.slot_of = b_slot_.as<u32>();
+  buf_.table = b_table_.as<u32>();
+  buf_.ends = b_ends_.as<uint2>();
+  buf_.rays = b_rays_.as<int4>();
+  buf_.tile_first = b_tiles_.as<u32>();
+  buf_.touched = b_touched_.as<u32>();
+  return BNX_OK;
+}
+
+int Map::insert(const void* points, i64 stride_bytes, i64 n, bool f64, const double origin[3], double max_range, int where) {
+  BNX_REQUIRE(n >= 0 && n + (i64)n_pending_ < (1ll << 24), "insert: at most 2^24-1 points per scan");
+  BNX_REQUIRE(n == 0 || points != nullptr, "insert: null points");
+  BNX_REQUIRE(origin != nullptr, "insert: null origin");
+  if (f64) {
+    BNX_REQUIRE(stride_bytes >= 24 && stride_bytes % 8 == 0, "insert_f64: stride must be a multiple of 8, >= 24");
+  } else {
+    BNX_REQUIRE(stride_bytes >= 12 && stride_bytes % 4 == 0, "insert_f32: stride must be a multiple of 4, >= 12");
+  }
+  cudaStream_t s = grid.stream();
+  if (profiling) cudaEventRecord(ev_[0], s);
+  BNX_TRY(reserve_scan(n, stride_bytes, max_range));
+  const void* d_points = points;
+  if (where == BNX_HOST && n > 0) {
+    BNX_TRY(b_pts_.reserve((size_t)n * stride_bytes));
+    BNX_CUDA(cudaMemcpyAsync(b_pts_.p, points, (size_t)n * stride_bytes, cudaMemcpyHostToDevice, s));
+    d_points = b_pts_.p;
+  }
+  ScanParams p = {};
+  p.ox = origin[0];
+  p.oy = origin[1];
+  p.oz = origin[2];
+  p.max_range = max_range;
+  p.max_range_sqr = max_range * max_range;  // probabilistic_map.hpp:145
+  p.inv_res = grid.inv_resolution;
+  // posToCoord(origin), probabilistic_map.cpp:91 — one fp64 multiply then floor, identical on host and device
+  p.Ox = (i32)std::floor(origin[0] * grid.inv_resolution);
+  p.Oy = (i32)std::floor(origin[1] * grid.inv_resolution);
+  p.Oz = (i32)std::floor(origin[2] * grid.inv_resolution);
+  p.miss = options[0];
+  p.hit = options[1];
+  p.cmin = options[2];
+  p.cmax = options[3];
+  p.c = update_count;
+  p.n = (u32)n;
+  p.max_chunks = (u32)std::min<u64>(((1ull << 40) - 1) / (u64)std::max<i64>(n + n_pending_, 1), 1ull << 28);
+  return run_scan(d_points, stride_bytes, f64, p, false);
+}
+
+int Map::run_scan(const void* d_points, i64 stride_bytes, bool f64, const ScanParams& base, bool) {
+  cudaStream_t s = grid.stream();
+  ScanParams p = base;
+  const i64 n = p.n;
+  u64 slots = 1024;
+  while (slots < (u64)n * 2) slots <<= 1;
+  p.hash_mask = (u32)(slots - 1);
+  if (profiling) cudaEventRecord(ev_[1], s);
+  if (n > 0) {
+    BNX_CUDA(cudaMemsetAsync(buf_.table, 0xFF, slots * 4, s));
+    const unsigned char* pts = static_cast<const unsigned char*>(d_points);
+    const int blocks = blocks_for(n);
+    if (f64) {
+      k_classify<true, false><<<blocks, TPB, 0, s>>>(pts, (u32)stride_bytes, p, buf_);
+    } else if (stride_bytes == 16 && (reinterpret_cast<uintptr_t>(pts) & 15u) == 0) {
+      k_classify<false, true><<<blocks, TPB, 0, s>>>(pts, 16u, p, buf_);
+    } else {
+      k_classify<false, false><<<blocks, TPB, 0, s>>>(pts, (u32)stride_bytes, p, buf_);
+    }
+    BNX_CUDA(cudaGetLastError());
+  }
+  if (profiling) cudaEventRecord(ev_[2], s);
+
+  const int persistent = sm_count() * 8;
+  i64 retries = 0;
+  for (;; ++retries) {
+    if (retries > 48) {
+      set_error("insert: node pools could not be grown enough for this scan");
+      return BNX_ERR_NOMEM;
+    }
+    p.seq = ++seq_;
+    p.tile_cap = (u32)std::min<size_t>(b_tiles_.bytes / 4, 0xFFFFFFFFull);
+    p.touched_cap = (u32)std::min<size_t>(b_touched_.bytes / 4, 0xFFFFFFFFull);
+    const GridDev g = grid.dev();
+    BNX_CUDA(cudaMemsetAsync(d_sc_, 0, sizeof(ScanCounters), s));
+    if (n_pending_) k_resolve<true><<<blocks_for(n_pending_), TPB, 0, s>>>(g, p, buf_, n_pending_);
+    if (n > 0) k_resolve<false><<<blocks_for(n), TPB, 0, s>>>(g, p, buf_, (u32)n);
+    if (profiling && retries == 0) cudaEventRecord(ev_[3], s);
+    k_mark<<<persistent, TPB, 0, s>>>(g, p, buf_);
+    if (profiling && retries == 0) cudaEventRecord(ev_[4], s);
+    k_apply_endpoints<<<std::min(persistent, blocks_for(n + 1)), TPB, 0, s>>>(g, p, buf_);
+    k_apply_leaves<<<persistent, TPB, 0, s>>>(g, p, buf_);
+    BNX_CUDA(cudaGetLastError());
+    if (profiling && retries == 0) cudaEventRecord(ev_[5], s);
+    BNX_CUDA(cudaMemcpyAsync(&h_status_->sc, d_sc_, sizeof(ScanCounters), cudaMemcpyDeviceToHost, s));
+    BNX_CUDA(cudaMemcpyAsync(&h_status_->gc, g.ctr, sizeof(GridCounters), cudaMemcpyDeviceToHost, s));
+    BNX_CUDA(cudaStreamSynchronize(s));
+    const Status st = *h_status_;
+    if (st.gc.error == 0 && st.sc.overflow == 0) break;
+    // phases 4/5 skipped themselves: nothing was applied. Grow what was short and repeat from phase 2.
+    if (st.sc.overflow & OVF_CHUNKS) {
+      set_error("insert: more than 2^32 ray chunks in one scan");
+      return BNX_ERR_UNSUPPORTED;
+    }
+    if (st.gc.error) BNX_TRY(grid.recover(st.gc));
+    if (st.sc.overflow & OVF_TILES) {
+      const u64 chunks = st.sc.ray_chunk & CHUNK_FIELD;
+      BNX_TRY(b_tiles_.reserve((size_t)(chunks / 32 + 64) * 4));
+      buf_.tile_first = b_tiles_.as<u32>();
+    }
+    BNX_TRY(b_touched_.reserve((size_t)grid.dev().leaf_cap * 4));
+    buf_.touched = b_touched_.as<u32>();
+  }
+  const Status st = *h_status_;
+  counters[0] = n;
+  counters[1] = (i64)st.sc.n_endpoints + n_pending_;
+  counters[2] = (i64)st.sc.sum_m + n;
+  counters[3] = (i64)st.sc.n_endpoints + st.sc.n_changed;
+  counters[4] = st.sc.n_touched;
+  counters[5] = retries;
+  counters[6] = (i64)(st.sc.ray_chunk >> 40);
+  counters[7] = (i64)(st.sc.ray_chunk & CHUNK_FIELD);
+  n_pending_ = 0;
+  if (++update_count == 4) update_count = 1;  // probabilistic_map.cpp:103-105
+  if (profiling) {
+    float ms;
+    for (int k = 0; k < 5; ++k) {
+      cudaEventElapsedTime(&ms, ev_[k], ev_[k + 1]);
+      phase_us[k] = ms * 1e3;
+    }
+    cudaEventElapsedTime(&ms, ev_[0], ev_[5]);
+    phase_us[5] = ms * 1e3;
+  }
+  return grid.maintain(st.gc);
+}
+
+int Map::add_point(const double pt[3], bool miss) {
+  cudaStream_t s = grid.stream();
+  if ((size_t)(n_pending_ + 1) * sizeof(int4) > b_pending_.bytes) {
+    // grow, keeping the queue
+    DevBuf bigger;
+    BNX_TRY(bigger.reserve(b_pending_.bytes * 2));
+    BNX_CUDA(cudaMemcpyAsync(bigger.p, b_pending_.p, (size_t)n_pending_ * sizeof(int4), cudaMemcpyDeviceToDevice, s));
+    BNX_CUDA(cudaStreamSynchronize(s));
+    std::swap(bigger.p, b_pending_.p);
+    std::swap(bigger.bytes, b_pending_.bytes);
+    buf_.pending = b_pending_.as<int4>();
+  }
+  ScanParams p = {};
+  p.miss = options[0];
+  p.hit = options[1];
+  p.cmin = options[2];
+  p.cmax = options[3];
+  p.c = update_count;
+  const int4 e = make_int4((i32)std::floor(pt[0] * grid.inv_resolution), (i32)std::floor(pt[1] * grid.inv_resolution),
+                           (i32)std::floor(pt[2] * grid.inv_resolution), miss ? 1 : 0);
+  u32* d_flag = reinterpret_cast<u32*>(d_sc_);  // scratch word, rewritten by the next scan anyway
+  for (int attempt = 0; attempt < 8; ++attempt) {
+    k_add_point<<<1, 1, 0, s>>>(grid.dev(), p, buf_, e, n_pending_, d_flag);
+    BNX_CUDA(cudaGetLastError());
+    BNX_CUDA(cudaMemcpyAsync(&h_status_->sc, d_sc_, sizeof(u32), cudaMemcpyDeviceToHost, s));
+    GridCounters gc;
+    BNX_TRY(grid.read_counters(&gc));
+    if (gc.error == 0) {
+      u32 queued;
+      std::memcpy(&queued, &h_status_->sc, 4);
+      n_pending_ += queued;
+      return BNX_OK;
+    }
+    BNX_TRY(grid.recover(gc));
+  }
+  set_error("add_point: node pools could not be grown");
+  return BNX_ERR_NOMEM;
+}
+
+int Map::query(const i32* xyz, i64 n, int kind, u8* out, int where) {
+  BNX_REQUIRE(n >= 0 && (n == 0 || (xyz && out)), "query: null input");
+  BNX_REQUIRE(kind == BNX_OCCUPIED || kind == BNX_UNKNOWN || kind == BNX_FREE, "query: unknown kind");
+  if (n == 0) return BNX_OK;
+  cudaStream_t s = grid.stream();
+  const i32* dx = xyz;
+  u8* dout = out;
+  if (where == BNX_HOST) {
+    BNX_TRY(b_q_xyz_.reserve((size_t)n * 12));
+    BNX_TRY(b_q_out_.reserve((size_t)n));
+    BNX_CUDA(cudaMemcpyAsync(b_q_xyz_.p, xyz, (size_t)n * 12, cudaMemcpyHostToDevice, s));
+    dx = b_q_xyz_.as<i32>();
+    dout = b_q_out_.as<u8>();
+  }
+  k_query<<<std::min(blocks_for(n), sm_count() * 8), TPB, 0, s>>>(grid.dev(), dx, n, kind, options[4], dout);
+  BNX_CUDA(cudaGetLastError());
+  if (where == BNX_HOST) {
+    BNX_CUDA(cudaMemcpyAsync(out, dout, (size_t)n, cudaMemcpyDeviceToHost, s));
+    BNX_CUDA(cudaStreamSynchronize(s));
+  }
+  return BNX_OK;
+}
+
+}  // namespace bnx

@@ -1,0 +1,79 @@
+// ProbabilisticMap on the device (bonxai_map/include/bonxai_map/probabilistic_map.hpp:27-203,
+// bonxai_map/src/probabilistic_map.cpp:30-126).
+#pragma once
+
+#include "grid.hpp"
+
+namespace bnx {
+
+// everything a scan's kernels need besides the grid, passed by value
+struct ScanParams {
+  double ox, oy, oz;  // origin promoted to fp64 (ConvertPoint, grid_coord.hpp:134-162)
+  double max_range, max_range_sqr, inv_res;
+  i32 Ox, Oy, Oz;              // origin voxel (probabilistic_map.cpp:91)
+  i32 miss, hit, cmin, cmax;   // Options, probabilistic_map.hpp:56-64
+  u32 c;                       // _update_count in {1,2,3}, probabilistic_map.hpp:129
+  u32 seq;                     // scan serial number: first-touch stamp of leaves
+  u32 n;                       // points in this scan
+  u32 hash_mask;               // endpoint dedupe table slots - 1
+  u32 tile_cap;                // entries of tile_first
+  u32 touched_cap;             // entries of the touched-leaf list
+  u32 max_chunks;              // per-ray chunk limit that keeps the packed (rays, chunks) counter exact
+};
+
+struct ScanCounters {
+  unsigned long long ray_chunk;  // (rays with >= 1 cell) << 40 | 8-cell chunks: ONE atomic orders both
+  unsigned long long sum_m;      // sum of ray lengths in cells
+  u32 n_endpoints;               // endpoint voxels updated this scan (E)
+  u32 n_touched;                 // leaves on the touched list
+  u32 n_changed;                 // cells changed by the free-space apply pass
+  u32 overflow;                  // scan scratch overflow bits
+};
+
+struct ScanBuffers {
+  int4* ep;          // per point: endpoint voxel xyz + type (0 hit, 1 miss)
+  u32* slot_of;      // per point: its slot in the dedupe table
+  u32* table;        // endpoint dedupe table: lowest point index per voxel
+  uint2* ends;       // per updated endpoint: {leaf, cell index | type << 16}
+  int4* rays;        // per ray with >= 1 cell: end voxel xyz + first chunk
+  u32* tile_first;   // per 32-chunk tile: ray that owns the tile's first chunk
+  u32* touched;      // leaves first touched in this scan
+  int4* pending;     // queued addHitPoint/addMissPoint endpoints (xyz, type)
+  ScanCounters* sc;
+};
+
+class Map {
+ public:
+  Map() = default;
+  ~Map();
+  int init(double resolution);
+
+  int insert(const void* points, i64 stride_bytes, i64 n, bool f64, const double origin[3], double max_range, int where);
+  int add_point(const double p[3], bool miss);
+  int query(const i32* xyz, i64 n, int kind, u8* out, int where);
+
+  Grid grid;
+  i32 options[5];
+  u32 update_count = 1;
+  i64 counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  bool profiling = false;
+  double phase_us[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
+ private:
+  int reserve_scan(i64 n, i64 stride_bytes, double max_range);
+  int run_scan(const void* d_points, i64 stride_bytes, bool f64, const ScanParams& base, bool reuse_classify);
+
+  ScanBuffers buf_ = {};
+  DevBuf b_pts_, b_ep_, b_slot_, b_table_, b_ends_, b_rays_, b_tiles_, b_touched_, b_pending_, b_q_xyz_, b_q_out_;
+  ScanCounters* d_sc_ = nullptr;
+  struct Status {
+    ScanCounters sc;
+    GridCounters gc;
+  };
+  Status* h_status_ = nullptr;  // pinned
+  u32 n_pending_ = 0;
+  u32 seq_ = 0;
+  cudaEvent_t ev_[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
+}  // namespace bnx

@@ -1,0 +1,177 @@
+/*
+ * bonxai_b200 — C ABI of the B200-native (sm_100a) implementation of Bonxai's occupancy-mapping hot path.
+ *
+ * The reference (facontidavide/Bonxai) has no FFI boundary: callers include its headers and call C++
+ * members directly. This header IS the boundary this build creates: each entry point
+ * names the reference member it replaces (paths relative to the reference tree). The drop-in C++
+ * headers include/bonxai/bonxai.hpp and include/bonxai_map/probabilistic_map.hpp are thin inline
+ * wrappers over these functions; INTEGRATION.md shows the binding a maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types. Coordinates are int32 xyz triplets
+ *     (Bonxai::CoordT, bonxai_core/include/bonxai/grid_coord.hpp:62-66), densely packed.
+ *   - every function returns a bnx_status (0 = ok); bnx_last_error() gives the thread-local message.
+ *   - `where` says whether the caller's buffers are host (BNX_HOST) or device (BNX_DEVICE) memory.
+ *     Host calls are synchronous on return. Device calls are enqueued on the handle's stream
+ *     (bnx_*_set_stream) and complete in stream order; scalar outputs (counts) make the call wait.
+ *   - one host thread per handle at a time (the reference's single-writer contract, README.md:128-133).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point returns BNX_ERR_CUDA.
+ */
+#ifndef BONXAI_B200_H
+#define BONXAI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define BNX_API
+#else
+#define BNX_API __attribute__((visibility("default")))
+#endif
+
+typedef struct bnx_grid bnx_grid_t; /* Bonxai::VoxelGrid<DataT>, DataT = opaque cell_bytes blob   */
+typedef struct bnx_map bnx_map_t;   /* Bonxai::ProbabilisticMap                                   */
+
+typedef enum {
+  BNX_OK = 0,
+  BNX_ERR_INVALID = 1,   /* bad argument (reference: std::runtime_error, e.g. bonxai.hpp:399-401)   */
+  BNX_ERR_CUDA = 2,      /* CUDA runtime/driver failure or no device                                */
+  BNX_ERR_NOMEM = 3,     /* device memory exhausted while growing node pools                        */
+  BNX_ERR_CAPACITY = 4,  /* caller's output buffer too small (count is still reported)              */
+  BNX_ERR_UNSUPPORTED = 5
+} bnx_status;
+
+enum { BNX_HOST = 0, BNX_DEVICE = 1 };
+/* Bonxai::ClearOption, bonxai.hpp:107-112 */
+enum { BNX_CLEAR_MEMORY = 0, BNX_SET_ALL_CELLS_OFF = 1 };
+/* cell predicates of ProbabilisticMap (probabilistic_map.cpp:56-75,108-126) */
+enum { BNX_OCCUPIED = 0, BNX_UNKNOWN = 1, BNX_FREE = 2 };
+
+BNX_API int bnx_version(void);
+BNX_API const char* bnx_last_error(void);
+/* number of usable CUDA devices; 0 with BNX_OK when the driver is present but no device is */
+BNX_API int bnx_device_count(int* count);
+/* pinned host memory for zero-staging H2D/D2H of point clouds and dumps */
+BNX_API int bnx_host_alloc(void** ptr, size_t bytes);
+BNX_API int bnx_host_free(void* ptr);
+
+/* ------------------------------------------------------------------------------------------------
+ * VoxelGrid<DataT>                                     bonxai_core/include/bonxai/bonxai.hpp:114-333
+ * ---------------------------------------------------------------------------------------------- */
+/* VoxelGrid(voxel_size, inner_bits=2, leaf_bits=3), bonxai.hpp:138,389-402. BNX_ERR_INVALID when
+ * a bit count is < 1 (the reference throws). cell_bytes = sizeof(DataT): 1, 2, 4, 8 or 16.
+ * The grid lives on the calling thread's current CUDA device. */
+BNX_API int bnx_grid_create(double voxel_size, int inner_bits, int leaf_bits, int cell_bytes, bnx_grid_t** out);
+BNX_API int bnx_grid_destroy(bnx_grid_t* g);
+/* cudaStream_t to enqueue on (NULL = the grid's own stream) */
+BNX_API int bnx_grid_set_stream(bnx_grid_t* g, void* cuda_stream);
+BNX_API int bnx_grid_sync(bnx_grid_t* g);
+/* innetBits()/leafBits()/voxelSize(), bonxai.hpp:146-154 */
+BNX_API int bnx_grid_info(const bnx_grid_t* g, double* voxel_size, int* inner_bits, int* leaf_bits, int* cell_bytes);
+
+/* posToCoord, bonxai.hpp:404-410 (fp64 multiply by 1/voxel_size, floor, cast) — xyz[n][3] doubles */
+BNX_API int bnx_grid_pos_to_coord(const bnx_grid_t* g, const double* xyz, int64_t n, int32_t* out, int where);
+/* coordToPos, bonxai.hpp:412-417 */
+BNX_API int bnx_grid_coord_to_pos(const bnx_grid_t* g, const int32_t* xyz, int64_t n, double* out, int where);
+
+/* Accessor::setValue over a batch, bonxai.hpp:449-466. Sequential semantics are kept: when a
+ * coordinate repeats inside the batch the LAST value wins and was_on is false only for the first
+ * occurrence of a previously-off cell. was_on (n bytes) may be NULL. */
+BNX_API int bnx_grid_set_values(bnx_grid_t* g, const int32_t* xyz, const void* values, int64_t n,
+                                uint8_t* was_on, int where);
+/* ConstAccessor::value, bonxai.hpp:496-516: found[i] = 0 (and values[i] untouched) for nullptr */
+BNX_API int bnx_grid_get_values(bnx_grid_t* g, const int32_t* xyz, int64_t n, void* values, uint8_t* found,
+                                int where);
+/* Accessor::value(coord, create_if_missing=true), bonxai.hpp:469-494: missing cells are created
+ * ON with DataT{} (all-zero bytes); returns the cell values */
+BNX_API int bnx_grid_get_or_create(bnx_grid_t* g, const int32_t* xyz, int64_t n, void* values, int where);
+/* write through the pointer value() returned: stores values[i] only where the cell is ON */
+BNX_API int bnx_grid_update_values(bnx_grid_t* g, const int32_t* xyz, const void* values, int64_t n, int where);
+/* Accessor::setCellOn(coord, default_value), bonxai.hpp:537-554 */
+BNX_API int bnx_grid_set_on(bnx_grid_t* g, const int32_t* xyz, int64_t n, const void* default_value,
+                            uint8_t* was_on, int where);
+/* Accessor::setCellOff, bonxai.hpp:557-569 (the value is kept) */
+BNX_API int bnx_grid_set_off(bnx_grid_t* g, const int32_t* xyz, int64_t n, uint8_t* was_on, int where);
+/* ConstAccessor::isCellOn, bonxai.hpp:518-534 */
+BNX_API int bnx_grid_is_on(bnx_grid_t* g, const int32_t* xyz, int64_t n, uint8_t* out, int where);
+
+/* activeCellsCount, bonxai.hpp:689-701 */
+BNX_API int bnx_grid_active_count(bnx_grid_t* g, int64_t* count);
+/* forEachCell, bonxai.hpp:704-743: all ON cells as (coord, value) pairs in unspecified order (the
+ * reference's order is unordered_map order). *count always receives the number of ON cells; when
+ * cap < *count nothing is written and BNX_ERR_CAPACITY is returned. xyz/values may be NULL to count. */
+BNX_API int bnx_grid_dump(bnx_grid_t* g, int32_t* xyz, void* values, int64_t cap, int64_t* count, int where);
+/* clear(ClearOption), bonxai.hpp:678-687 */
+BNX_API int bnx_grid_clear(bnx_grid_t* g, int clear_option);
+/* releaseUnusedMemory, bonxai.hpp:367-387: leaves with every cell OFF go back to the pool, roots
+ * whose leaves are all gone leave the table */
+BNX_API int bnx_grid_release_unused(bnx_grid_t* g);
+/* memUsage, bonxai.hpp:649-676: bytes of device memory in use by live nodes (layout specific,
+ * like the reference's figure) */
+BNX_API int bnx_grid_mem_usage(bnx_grid_t* g, int64_t* bytes);
+/* node statistics: {roots, inner nodes, leaves in use, leaves free-listed, root table slots,
+ * leaf pool capacity, mapped bytes, reserved} */
+BNX_API int bnx_grid_stats(bnx_grid_t* g, int64_t out[8]);
+/* Serialize / Deserialize, bonxai_core/include/bonxai/serialization.hpp:77-116,153-199.
+ * type_name is the demangled DataT the header line carries (e.g. "unsigned int", "float").
+ * serialize: *size receives the byte count; buffer may be NULL to query (host memory only). */
+BNX_API int bnx_grid_serialize(bnx_grid_t* g, const char* type_name, uint8_t* buffer, int64_t cap, int64_t* size);
+BNX_API int bnx_grid_deserialize(const uint8_t* data, int64_t len, int cell_bytes, const char* expect_type_name,
+                                 bnx_grid_t** out);
+
+/* ------------------------------------------------------------------------------------------------
+ * ProbabilisticMap                  bonxai_map/include/bonxai_map/probabilistic_map.hpp:27-139
+ * ---------------------------------------------------------------------------------------------- */
+/* ProbabilisticMap(resolution), probabilistic_map.cpp:14-16: VoxelGrid<CellT> with default bits 2/3.
+ * The cell word is the reference's CellT image: (probability_log << 4) | update_id (hpp:44-53). */
+BNX_API int bnx_map_create(double resolution, bnx_map_t** out);
+BNX_API int bnx_map_destroy(bnx_map_t* m);
+BNX_API int bnx_map_set_stream(bnx_map_t* m, void* cuda_stream);
+BNX_API int bnx_map_sync(bnx_map_t* m);
+/* grid(), probabilistic_map.cpp:10-12,18-20: borrowed handle, owned by the map */
+BNX_API int bnx_map_grid(bnx_map_t* m, bnx_grid_t** grid);
+/* Options {prob_miss_log, prob_hit_log, clamp_min_log, clamp_max_log, occupancy_threshold_log},
+ * probabilistic_map.hpp:56-64; setOptions/options, probabilistic_map.cpp:22-28 */
+BNX_API int bnx_map_set_options(bnx_map_t* m, const int32_t options[5]);
+BNX_API int bnx_map_get_options(const bnx_map_t* m, int32_t options[5]);
+
+/* insertPointCloud<PointT>, probabilistic_map.hpp:141-160 (+ addHit/MissPoint, updateFreeCells,
+ * RayIterator: probabilistic_map.cpp:30-54,77-106, hpp:162-203).
+ *   f32: PointT = {float x,y,z[,...]} every stride_bytes (12 = packed xyz, 16 = pcl::PointXYZ, any
+ *        multiple of 4 >= 12); f64: PointT = 3 doubles every stride_bytes (>= 24, multiple of 8).
+ *   origin is a PointT of the same scalar type, max_range as in the reference (may be +inf).
+ * Bit-exact: after the call a forEachCell dump equals the reference's after the same call. */
+BNX_API int bnx_map_insert_f32(bnx_map_t* m, const void* points, int64_t stride_bytes, int64_t n,
+                               const float origin[3], double max_range, int where);
+BNX_API int bnx_map_insert_f64(bnx_map_t* m, const void* points, int64_t stride_bytes, int64_t n,
+                               const double origin[3], double max_range, int where);
+/* addHitPoint / addMissPoint, probabilistic_map.cpp:30-54: the endpoint cell is updated now, its
+ * ray is cast by the next insertPointCloud from that call's origin (updateFreeCells is private in
+ * the reference, hpp:136) */
+BNX_API int bnx_map_add_hit(bnx_map_t* m, const double point[3]);
+BNX_API int bnx_map_add_miss(bnx_map_t* m, const double point[3]);
+/* isOccupied / isUnknown / isFree, probabilistic_map.cpp:56-75 — kind = BNX_OCCUPIED|UNKNOWN|FREE */
+BNX_API int bnx_map_query(bnx_map_t* m, const int32_t* xyz, int64_t n, int kind, uint8_t* out, int where);
+/* getOccupiedVoxels / getFreeVoxels(std::vector<CoordT>&), probabilistic_map.cpp:108-126.
+ * Same cap/count protocol as bnx_grid_dump. */
+BNX_API int bnx_map_get_voxels(bnx_map_t* m, int kind, int32_t* xyz, int64_t cap, int64_t* count, int where);
+/* getOccupiedVoxels<PointT>, probabilistic_map.hpp:115-124: coord * resolution (voxel corner), doubles */
+BNX_API int bnx_map_get_voxel_points(bnx_map_t* m, int kind, double* xyz, int64_t cap, int64_t* count, int where);
+/* counters of the last insert: {N points, E endpoint voxels updated (= rays cast), V = sum of ray
+ * cells + N, U cells whose word changed, leaves touched, retries after pool growth, 0, 0} */
+BNX_API int bnx_map_counters(bnx_map_t* m, int64_t out[8]);
+/* _update_count, probabilistic_map.hpp:129 (cycles 1,2,3) */
+BNX_API int bnx_map_update_count(const bnx_map_t* m, int* value);
+/* device time of the phases of the last insert in microseconds (CUDA events; enabled by
+ * bnx_map_set_profiling(m,1)): {h2d, classify, resolve, mark, apply, total, 0, 0} */
+BNX_API int bnx_map_set_profiling(bnx_map_t* m, int enable);
+BNX_API int bnx_map_phase_times(bnx_map_t* m, double out_us[8]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BONXAI_B200_H */

