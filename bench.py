@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""bench.py — insertPointCloud throughput on the synthetic 64-beam LiDAR sequence (BASELINE.json config #3).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+A step is ONE scan (131,072 points, 0.1 m voxels, max_range 50 m, sensor moving 1 m per scan) inserted into
+the running map. Printed: ONE JSON line (see DESIGN.md §6 for every field).
+
+  value     points/s with the scans already resident in HBM (device-pointer C-ABI call per scan)
+  e2e       points/s through the same C-ABI call with HOST (pinned) buffers: H2D copy of every scan and the
+            D2H status/counter read-back are inside the timed region
+  roofline  dominant kernel: algorithmic bytes per scan (16*N + 8*U) / its CUDA-event time
+  cpu_baseline  the unmodified reference (oracle/_ref) on ONE host core, first scans of the same sequence
+
+--impl reference times the reference's own CPU implementation (oracle/_ref, else the plain-C port) instead.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from bonxai_b200 import synth  # noqa: E402
+
+RES, MAX_RANGE, BEAMS, AZ = 0.1, 50.0, 64, 2048
+N_PTS = BEAMS * AZ
+WORKLOAD = "lidar64x2048_seq(131072 pts/scan, res 0.1 m, max_range 50 m, 1 m/scan)"
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """SM clock + throttle reasons DURING the timed region. NVML (what nvidia-smi reads) polled every 2 ms from a
+    thread, because the timed region lasts tens of milliseconds — shorter than one `nvidia-smi -lms` period."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.sm, self.reasons, self.power = [], set(), []
+        self.smax = None
+        self.stop_flag = threading.Event()
+        self.thread = None
+
+    def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML indexes physical GPUs: honour CUDA_VISIBLE_DEVICES if it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.gpu
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.gpu])
+                except Exception:
+                    idx = self.gpu
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+            return
+
+        def pump():
+            while not self.stop_flag.is_set():
+                try:
+                    self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                    r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                    for bit, name in self.REASONS.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                    self.power.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                except Exception:
+                    pass
+                time.sleep(0.002)
+
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvml unavailable: " + getattr(self, "err", "?")]}
+        self.stop_flag.set()
+        self.thread.join(timeout=1)
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.smax, "samples": len(self.sm),
+                "power_w_max": max(self.power) if self.power else None, "reasons": sorted(self.reasons)}
+
+
+def gen_scans(first: int, count: int):
+    """the scans of the sequence, generated on the host cores in parallel (fork: call before CUDA is initialised)"""
+    import multiprocessing as mp
+    procs = min(count, max(1, (os.cpu_count() or 2) - 1), 48)
+    if procs <= 1 or count < 4:
+        return [synth.lidar_scan(s) for s in range(first, first + count)]
+    with mp.get_context("fork").Pool(procs) as pool:
+        return pool.map(synth.lidar_scan, range(first, first + count), chunksize=max(1, count // (procs * 4)))
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline
+# ------------------------------------------------------------------------------------------------
+def load_cpu_oracle():
+    import oracle
+    if oracle.available("reference"):
+        return oracle.load("reference"), "reference"
+    return oracle.load("port"), "port"
+
+
+def time_cpu(scans, warmup: int):
+    """single-threaded reference insertPointCloud over `scans`; the clock brackets the call only
+    (bonxai_map/benchmark/benchmark_kitti.cpp:146-152). Returns (seconds over timed scans, n timed)."""
+    lib, kind = load_cpu_oracle()
+    m = lib.map(RES)
+    total = 0.0
+    for i, (pts, origin) in enumerate(scans):
+        m.insert(pts, origin, MAX_RANGE)
+        if i >= warmup:
+            total += m.last_insert_seconds()
+    return total, len(scans) - warmup, kind
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    scans = gen_scans(0, args.warmup + args.steps)
+    secs, n, kind = time_cpu(scans, args.warmup)
+    pts_s = n * N_PTS / secs
+    line = {
+        "impl": "reference", "metric": "insertPointCloud points/sec", "value": pts_s, "unit": "points/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / n, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64+int32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "points_per_scan": N_PTS, "host": "single-threaded reference CPU path"},
+        "cpu_baseline": {"value": pts_s, "unit": "points/s", "cores": 1, "kind": kind,
+                         "sample": f"scans {args.warmup}..{args.warmup + n - 1} of the same sequence, one map"},
+        "e2e": {"value": pts_s, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    K, W = args.steps, args.warmup
+    total = W + K
+    # Multi-GPU (round 1): replicas — every rank maps its own stretch of the street (weak scaling, no exchange).
+    first_scan = rank * 5000
+    scans = gen_scans(first_scan, total)  # before torch/CUDA: the generator forks worker processes
+
+    import torch
+    import torch.distributed as dist
+    from bonxai_b200 import capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: bonxai_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    capi.load_library()
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident arm ("value") ----------------
+    dev_scans = [torch.from_numpy(p).cuda() for p, _ in scans]  # K distinct 2 MiB buffers: > L2 in total for K >= 64
+    m = capi.ProbabilisticMap(RES)
+    m.set_stream(stream.cuda_stream)
+    m.set_profiling(True)
+    U = V = E = 0
+    phases = {k: 0.0 for k in ("classify", "resolve", "mark", "apply", "total")}
+    for i in range(W):
+        m.insert(capi.DevPtr(dev_scans[i].data_ptr()), scans[i][1], MAX_RANGE, n=N_PTS, stride_bytes=16)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = capi.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(W, total):
+        m.insert(capi.DevPtr(dev_scans[i].data_ptr()), scans[i][1], MAX_RANGE, n=N_PTS, stride_bytes=16)
+        c = m.counters()
+        U += c["U"]
+        V += c["V"]
+        E += c["E"]
+        ph = m.phase_times()
+        for k in phases:
+            phases[k] += ph[k]
+    e1.record(stream)
+    barrier()
+    launches = capi.launch_count() - launches0
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    active = m.active_count()
+    del m
+
+    # ---------------- end-to-end arm: host (pinned) buffers through the C ABI ----------------
+    pinned = [torch.from_numpy(p).pin_memory() for p, _ in scans]
+    m2 = capi.ProbabilisticMap(RES)
+    for i in range(W):
+        m2.insert(pinned[i].numpy(), scans[i][1], MAX_RANGE)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(W, total):
+        m2.insert(pinned[i].numpy(), scans[i][1], MAX_RANGE)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    assert m2.active_count() == active, "host-buffer and device-buffer arms disagree"
+    del m2
+
+    tot = torch.tensor([U, V, E, launches], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    U_all, V_all, E_all, launches_all = [float(x) for x in tot.tolist()]
+
+    if rank == 0:
+        peaks, peak_kind = load_peaks()
+        secs = ms_max * 1e-3
+        pts_s = world * K * N_PTS / secs
+        dom = max(("classify", "resolve", "mark", "apply"), key=lambda k: phases[k])
+        dom_us = phases[dom] / K  # average CUDA-event duration of the dominant phase per scan (this rank)
+        alg_bytes = 16.0 * N_PTS + 8.0 * (U / K)
+        achieved = alg_bytes / (dom_us * 1e-6) / 1e9
+        peak = float(peaks["hbm_gbs"])
+        line = {
+            "metric": "insertPointCloud points/sec", "value": pts_s, "unit": "points/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64+int32",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "points_per_scan": N_PTS, "parallelism": "single" if world == 1 else f"replicas x{world}",
+                       "l2": f"{total} distinct 2 MiB scan buffers resident in HBM, each read once; the map itself is state carried between scans",
+                       "active_cells_end": active},
+            "voxel_updates_per_s": U_all / secs, "ray_visits_per_s": V_all / secs, "rays_per_s": E_all / secs,
+            "updates_per_scan": U / K, "visits_per_scan": V / K,
+            "phase_us_per_scan": {k: phases[k] / K for k in phases},
+            "roofline": {"bound": "hbm", "kernel": {"classify": "k_classify", "resolve": "k_resolve", "mark": "k_mark", "apply": "k_apply_endpoints+k_apply_leaves"}[dom],
+                         "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "algorithmic_bytes_per_launch": alg_bytes, "kernel_us": dom_us,
+                         "kernel_share_of_step": phases[dom] / max(phases["total"], 1e-9),
+                         "step_achieved_gbs": alg_bytes * K / secs / 1e9},
+            "e2e": {"value": world * K * N_PTS / e2e_s, "unit": "points/s", "h2d_bytes_per_step": N_PTS * 16, "d2h_bytes_per_step": 56,
+                    "ms_per_step": 1e3 * e2e_s / K},
+            "gpu_launches": int(launches_all),
+            "clocks": clocks,
+        }
+        # CPU baseline beside it: the unmodified reference on one host core, bounded sample of the same sequence
+        if world == 1 and not args.no_cpu:
+            n_cpu = min(total, args.cpu_scans + 2)
+            secs_cpu, n, kind = time_cpu(scans[:n_cpu], 2)
+            line["cpu_baseline"] = {"value": n * N_PTS / secs_cpu, "unit": "points/s", "cores": 1, "kind": kind,
+                                    "sample": f"scans 2..{n_cpu - 1} of the same sequence ({n} scans, {secs_cpu:.1f} s), single thread",
+                                    "ms_per_step": 1e3 * secs_cpu / n}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-scans", type=int, default=60, help="scans timed for the cpu_baseline (about 10-15 s)")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -25,7 +25,7 @@ STATUS_NAMES = {0: "BNX_OK", 1: "BNX_ERR_INVALID", 2: "BNX_ERR_CUDA", 3: "BNX_ER
 
 # every symbol include/bonxai_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = [
-    "bnx_version", "bnx_last_error", "bnx_device_count", "bnx_host_alloc", "bnx_host_free",
+    "bnx_version", "bnx_last_error", "bnx_launch_count", "bnx_device_count", "bnx_host_alloc", "bnx_host_free",
     "bnx_grid_create", "bnx_grid_destroy", "bnx_grid_set_stream", "bnx_grid_sync", "bnx_grid_info",
     "bnx_grid_pos_to_coord", "bnx_grid_coord_to_pos", "bnx_grid_set_values", "bnx_grid_get_values",
     "bnx_grid_get_or_create", "bnx_grid_update_values", "bnx_grid_set_on", "bnx_grid_set_off", "bnx_grid_is_on",
@@ -67,7 +67,9 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.bnx_last_error.restype = C.c_char_p
     for name in SYMBOLS:
         fn = getattr(lib, name)
-        if name != "bnx_last_error":
+        if name == "bnx_launch_count":
+            fn.restype = C.c_int64
+        elif name != "bnx_last_error":
             fn.restype = C.c_int
     _lib = lib
     return lib
@@ -76,6 +78,10 @@ def load_library(path: str | None = None) -> C.CDLL:
 def _check(status: int):
     if status != 0:
         raise BonxaiError(status, load_library().bnx_last_error().decode(errors="replace"))
+
+
+def launch_count() -> int:
+    return int(load_library().bnx_launch_count())
 
 
 def device_count() -> int:

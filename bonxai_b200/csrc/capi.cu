@@ -44,6 +44,7 @@ struct DeviceGuard {
 extern "C" {
 
 int bnx_version(void) { return 100; }
+int64_t bnx_launch_count(void) { return (int64_t)launch_count(); }
 const char* bnx_last_error(void) { return get_error(); }
 
 int bnx_device_count(int* count) {

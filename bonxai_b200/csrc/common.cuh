@@ -49,6 +49,10 @@ struct StatusError {
     }                                                  \
   } while (0)
 
+// every kernel launch of this library is counted (bench.py reports it as gpu_launches)
+void note_launch();
+long long launch_count();
+
 // The B200 has 148 SMs; grids of the grid-stride kernels are sized in multiples of the SM count.
 int sm_count();
 

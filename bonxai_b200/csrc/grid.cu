@@ -3,6 +3,7 @@
 #include "grid.hpp"
 
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -15,6 +16,10 @@ namespace bnx {
 static thread_local std::string t_error;
 void set_error(const std::string& msg) { t_error = msg; }
 const char* get_error() { return t_error.c_str(); }
+
+static std::atomic<long long> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 int sm_count() {
   static int cached[64] = {0};
@@ -528,7 +533,7 @@ int Grid::grow_root_table(u64 min_slots) {
   BNX_CUDA(cudaMalloc(&fresh, slots * sizeof(int4)));
   BNX_CUDA(cudaMemsetAsync(fresh, 0, slots * sizeof(int4), stream_));
   if (root_) {
-    k_rehash<<<grid_for((i64)root_slots_), TPB, 0, stream_>>>(root_, root_slots_, fresh, (u32)(slots - 1), inner_bits + leaf_bits);
+    note_launch(), k_rehash<<<grid_for((i64)root_slots_), TPB, 0, stream_>>>(root_, root_slots_, fresh, (u32)(slots - 1), inner_bits + leaf_bits);
     BNX_CUDA(cudaGetLastError());
     BNX_CUDA(cudaStreamSynchronize(stream_));
     BNX_CUDA(cudaFree(root_));
@@ -603,7 +608,7 @@ int Grid::stage_in(const void* src, size_t bytes, int where, DevBuf& buf, const 
 template <bool CREATE>
 int Grid::locate(const i32* d_xyz, i64 n, u32* d_loc) {
   for (int attempt = 0; attempt < 40; ++attempt) {
-    k_locate<CREATE><<<grid_for(n), TPB, 0, stream_>>>(dev_, d_xyz, n, d_loc);
+    note_launch(), k_locate<CREATE><<<grid_for(n), TPB, 0, stream_>>>(dev_, d_xyz, n, d_loc);
     BNX_CUDA(cudaGetLastError());
     if constexpr (!CREATE) return BNX_OK;
     GridCounters c;
@@ -625,7 +630,7 @@ int Grid::dedupe(const i32* d_xyz, const u32* d_loc, i64 n) {
   BNX_CUDA(cudaMemsetAsync(b_keys_.p, 0xFF, slots * 8, stream_));
   BNX_CUDA(cudaMemsetAsync(b_first_.p, 0xFF, slots * 4, stream_));
   BNX_CUDA(cudaMemsetAsync(b_last_.p, 0x00, slots * 4, stream_));
-  k_dedupe<<<grid_for(n), TPB, 0, stream_>>>(dev_, d_xyz, d_loc, (u32)n, b_keys_.as<unsigned long long>(), b_first_.as<u32>(),
+  note_launch(), k_dedupe<<<grid_for(n), TPB, 0, stream_>>>(dev_, d_xyz, d_loc, (u32)n, b_keys_.as<unsigned long long>(), b_first_.as<u32>(),
                                               b_last_.as<u32>(), b_slot_.as<u32>(), (u32)(slots - 1));
   BNX_CUDA(cudaGetLastError());
   return BNX_OK;
@@ -652,7 +657,7 @@ int Grid::set_values(const i32* xyz, const void* values, i64 n, u8* was_on, int 
     BNX_TRY(b_loc_.reserve((size_t)cnt * 4));
     BNX_TRY(locate<true>(static_cast<const i32*>(dx), cnt, b_loc_.as<u32>()));
     BNX_TRY(dedupe(static_cast<const i32*>(dx), b_loc_.as<u32>(), cnt));
-    k_set_values<<<grid_for(cnt), TPB, 0, stream_>>>(dev_, static_cast<const i32*>(dx), b_loc_.as<u32>(), b_slot_.as<u32>(),
+    note_launch(), k_set_values<<<grid_for(cnt), TPB, 0, stream_>>>(dev_, static_cast<const i32*>(dx), b_loc_.as<u32>(), b_slot_.as<u32>(),
                                                       b_first_.as<u32>(), b_last_.as<u32>(), static_cast<const u8*>(dv), dflag, (u32)cnt);
     BNX_CUDA(cudaGetLastError());
     if (was_on && where == BNX_HOST) BNX_CUDA(cudaMemcpyAsync(was_on + off, dflag, (size_t)cnt, cudaMemcpyDeviceToHost, stream_));
@@ -684,7 +689,7 @@ int Grid::get_values(const i32* xyz, i64 n, void* values, u8* found, int where) 
     }
     BNX_TRY(b_loc_.reserve((size_t)cnt * 4));
     BNX_TRY(locate<false>(static_cast<const i32*>(dx), cnt, b_loc_.as<u32>()));
-    k_read_values<<<grid_for(cnt), TPB, 0, stream_>>>(dev_, static_cast<const i32*>(dx), b_loc_.as<u32>(), dval, dflag, cnt);
+    note_launch(), k_read_values<<<grid_for(cnt), TPB, 0, stream_>>>(dev_, static_cast<const i32*>(dx), b_loc_.as<u32>(), dval, dflag, cnt);
     BNX_CUDA(cudaGetLastError());
     if (where == BNX_HOST) {
       if (values) BNX_CUDA(cudaMemcpyAsync(static_cast<u8*>(values) + off * cell_bytes, dval, (size_t)cnt * cell_bytes, cudaMemcpyDeviceToHost, stream_));
@@ -712,8 +717,8 @@ int Grid::get_or_create(const i32* xyz, i64 n, void* values, int where) {
     BNX_TRY(b_loc_.reserve((size_t)cnt * 4));
     BNX_TRY(locate<true>(static_cast<const i32*>(dx), cnt, b_loc_.as<u32>()));
     BNX_TRY(dedupe(static_cast<const i32*>(dx), b_loc_.as<u32>(), cnt));
-    k_create_cells<<<grid_for(cnt), TPB, 0, stream_>>>(dev_, static_cast<const i32*>(dx), b_loc_.as<u32>(), b_slot_.as<u32>(), b_first_.as<u32>(), (u32)cnt);
-    k_read_values<<<grid_for(cnt), TPB, 0, stream_>>>(dev_, static_cast<const i32*>(dx), b_loc_.as<u32>(), dval, nullptr, cnt);
+    note_launch(), k_create_cells<<<grid_for(cnt), TPB, 0, stream_>>>(dev_, static_cast<const i32*>(dx), b_loc_.as<u32>(), b_slot_.as<u32>(), b_first_.as<u32>(), (u32)cnt);
+    note_launch(), k_read_values<<<grid_for(cnt), TPB, 0, stream_>>>(dev_, static_cast<const i32*>(dx), b_loc_.as<u32>(), dval, nullptr, cnt);
     BNX_CUDA(cudaGetLastError());
     if (where == BNX_HOST) {
       BNX_CUDA(cudaMemcpyAsync(static_cast<u8*>(values) + off * cell_bytes, dval, (size_t)cnt * cell_bytes, cudaMemcpyDeviceToHost, stream_));
@@ -732,7 +737,7 @@ int Grid::update_values(const i32* xyz, const void* values, i64 n, int where) {
     BNX_TRY(b_loc_.reserve((size_t)cnt * 4));
     BNX_TRY(locate<false>(static_cast<const i32*>(dx), cnt, b_loc_.as<u32>()));
     BNX_TRY(dedupe(static_cast<const i32*>(dx), b_loc_.as<u32>(), cnt));
-    k_update_values<<<grid_for(cnt), TPB, 0, stream_>>>(dev_, static_cast<const i32*>(dx), b_loc_.as<u32>(), b_slot_.as<u32>(), b_last_.as<u32>(),
+    note_launch(), k_update_values<<<grid_for(cnt), TPB, 0, stream_>>>(dev_, static_cast<const i32*>(dx), b_loc_.as<u32>(), b_slot_.as<u32>(), b_last_.as<u32>(),
                                                          static_cast<const u8*>(dv), (u32)cnt);
     BNX_CUDA(cudaGetLastError());
     if (where == BNX_HOST) BNX_TRY(sync());
@@ -762,7 +767,7 @@ int Grid::set_on(const i32* xyz, i64 n, const void* default_value, u8* was_on, i
     BNX_TRY(b_loc_.reserve((size_t)cnt * 4));
     BNX_TRY(locate<true>(static_cast<const i32*>(dx), cnt, b_loc_.as<u32>()));
     BNX_TRY(dedupe(static_cast<const i32*>(dx), b_loc_.as<u32>(), cnt));
-    k_set_on<<<grid_for(cnt), TPB, 0, stream_>>>(dev_, static_cast<const i32*>(dx), b_loc_.as<u32>(), b_slot_.as<u32>(), b_first_.as<u32>(),
+    note_launch(), k_set_on<<<grid_for(cnt), TPB, 0, stream_>>>(dev_, static_cast<const i32*>(dx), b_loc_.as<u32>(), b_slot_.as<u32>(), b_first_.as<u32>(),
                                                   b_val_.as<u8>(), dflag, (u32)cnt);
     BNX_CUDA(cudaGetLastError());
     if (was_on && where == BNX_HOST) BNX_CUDA(cudaMemcpyAsync(was_on + off, dflag, (size_t)cnt, cudaMemcpyDeviceToHost, stream_));
@@ -788,7 +793,7 @@ int Grid::set_off(const i32* xyz, i64 n, u8* was_on, int where) {
     BNX_TRY(b_loc_.reserve((size_t)cnt * 4));
     BNX_TRY(locate<false>(static_cast<const i32*>(dx), cnt, b_loc_.as<u32>()));
     BNX_TRY(dedupe(static_cast<const i32*>(dx), b_loc_.as<u32>(), cnt));
-    k_set_off<<<grid_for(cnt), TPB, 0, stream_>>>(dev_, static_cast<const i32*>(dx), b_loc_.as<u32>(), b_slot_.as<u32>(), b_first_.as<u32>(), dflag, (u32)cnt);
+    note_launch(), k_set_off<<<grid_for(cnt), TPB, 0, stream_>>>(dev_, static_cast<const i32*>(dx), b_loc_.as<u32>(), b_slot_.as<u32>(), b_first_.as<u32>(), dflag, (u32)cnt);
     BNX_CUDA(cudaGetLastError());
     if (was_on && where == BNX_HOST) BNX_CUDA(cudaMemcpyAsync(was_on + off, dflag, (size_t)cnt, cudaMemcpyDeviceToHost, stream_));
     if (where == BNX_HOST) BNX_TRY(sync());
@@ -800,7 +805,7 @@ int Grid::pos_to_coord(const double* xyz, i64 n, i32* out, int where) const {
   BNX_REQUIRE(n >= 0 && (n == 0 || (xyz && out)), "pos_to_coord: null input");
   if (n == 0) return BNX_OK;
   if (where == BNX_DEVICE) {
-    k_pos_to_coord<<<grid_for(3 * n), TPB, 0, stream_>>>(xyz, 3 * n, inv_resolution, out);
+    note_launch(), k_pos_to_coord<<<grid_for(3 * n), TPB, 0, stream_>>>(xyz, 3 * n, inv_resolution, out);
     BNX_CUDA(cudaGetLastError());
     return BNX_OK;
   }
@@ -809,7 +814,7 @@ int Grid::pos_to_coord(const double* xyz, i64 n, i32* out, int where) const {
   BNX_CUDA(cudaMalloc(&din, (size_t)n * 24));
   BNX_CUDA(cudaMalloc(&dout, (size_t)n * 12));
   cudaMemcpyAsync(din, xyz, (size_t)n * 24, cudaMemcpyHostToDevice, stream_);
-  k_pos_to_coord<<<grid_for(3 * n), TPB, 0, stream_>>>(din, 3 * n, inv_resolution, dout);
+  note_launch(), k_pos_to_coord<<<grid_for(3 * n), TPB, 0, stream_>>>(din, 3 * n, inv_resolution, dout);
   cudaMemcpyAsync(out, dout, (size_t)n * 12, cudaMemcpyDeviceToHost, stream_);
   cudaError_t e = cudaStreamSynchronize(stream_);
   cudaFree(din);
@@ -822,7 +827,7 @@ int Grid::coord_to_pos(const i32* xyz, i64 n, double* out, int where) const {
   BNX_REQUIRE(n >= 0 && (n == 0 || (xyz && out)), "coord_to_pos: null input");
   if (n == 0) return BNX_OK;
   if (where == BNX_DEVICE) {
-    k_coord_to_pos<<<grid_for(3 * n), TPB, 0, stream_>>>(xyz, 3 * n, resolution, out);
+    note_launch(), k_coord_to_pos<<<grid_for(3 * n), TPB, 0, stream_>>>(xyz, 3 * n, resolution, out);
     BNX_CUDA(cudaGetLastError());
     return BNX_OK;
   }
@@ -831,7 +836,7 @@ int Grid::coord_to_pos(const i32* xyz, i64 n, double* out, int where) const {
   BNX_CUDA(cudaMalloc(&din, (size_t)n * 12));
   BNX_CUDA(cudaMalloc(&dout, (size_t)n * 24));
   cudaMemcpyAsync(din, xyz, (size_t)n * 12, cudaMemcpyHostToDevice, stream_);
-  k_coord_to_pos<<<grid_for(3 * n), TPB, 0, stream_>>>(din, 3 * n, resolution, dout);
+  note_launch(), k_coord_to_pos<<<grid_for(3 * n), TPB, 0, stream_>>>(din, 3 * n, resolution, dout);
   cudaMemcpyAsync(out, dout, (size_t)n * 24, cudaMemcpyDeviceToHost, stream_);
   cudaError_t e = cudaStreamSynchronize(stream_);
   cudaFree(din);
@@ -850,7 +855,7 @@ int Grid::active_count(i64* count) {
   const u32 n_leaves = std::min(c.n_leaves, dev_.leaf_cap);
   BNX_CUDA(cudaMemsetAsync(d_count_, 0, 8, stream_));
   if (n_leaves) {
-    k_count_active<<<grid_for((i64)n_leaves * dev_.mask_words), TPB, 0, stream_>>>(dev_, n_leaves, reinterpret_cast<unsigned long long*>(d_count_));
+    note_launch(), k_count_active<<<grid_for((i64)n_leaves * dev_.mask_words), TPB, 0, stream_>>>(dev_, n_leaves, reinterpret_cast<unsigned long long*>(d_count_));
     BNX_CUDA(cudaGetLastError());
   }
   BNX_CUDA(cudaMemcpyAsync(h_count_, d_count_, 8, cudaMemcpyDeviceToHost, stream_));
@@ -869,7 +874,7 @@ int Grid::dump(i32* xyz, double* pos, void* values, i64 cap, i64* count, int whe
   auto run = [&](i32* dxyz, double* dpos, u8* dval, u64 dcap) -> int {
     BNX_CUDA(cudaMemsetAsync(d_count_, 0, 8, stream_));
     if (n_leaves) {
-      k_dump<<<blocks, TPB, 0, stream_>>>(dev_, n_leaves, pred, thr, resolution, dxyz, dpos, dval, dcap, reinterpret_cast<unsigned long long*>(d_count_));
+      note_launch(), k_dump<<<blocks, TPB, 0, stream_>>>(dev_, n_leaves, pred, thr, resolution, dxyz, dpos, dval, dcap, reinterpret_cast<unsigned long long*>(d_count_));
       BNX_CUDA(cudaGetLastError());
     }
     BNX_CUDA(cudaMemcpyAsync(h_count_, d_count_, 8, cudaMemcpyDeviceToHost, stream_));
@@ -927,7 +932,7 @@ int Grid::clear(int option) {
   const u32 n_leaves = std::min(c.n_leaves, dev_.leaf_cap);
   if (option == BNX_SET_ALL_CELLS_OFF) {
     if (n_leaves) {
-      k_masks_off<<<grid_for((i64)n_leaves * dev_.mask_words), TPB, 0, stream_>>>(dev_, n_leaves);
+      note_launch(), k_masks_off<<<grid_for((i64)n_leaves * dev_.mask_words), TPB, 0, stream_>>>(dev_, n_leaves);
       BNX_CUDA(cudaGetLastError());
     }
     return sync();
@@ -949,13 +954,13 @@ int Grid::release_unused() {
   if (n_inner == 0) return BNX_OK;
   BNX_TRY(free_list_reserve());
   const u32 children = 1u << (3 * inner_bits);
-  k_release_leaves<<<grid_for((i64)n_inner * children), TPB, 0, stream_>>>(dev_, n_inner, children);
-  k_release_zero<<<std::max(1, std::min<int>((int)ceil_div(n_leaves, TPB / 32), sm_count() * 8)), TPB, 0, stream_>>>(dev_, n_leaves);
+  note_launch(), k_release_leaves<<<grid_for((i64)n_inner * children), TPB, 0, stream_>>>(dev_, n_inner, children);
+  note_launch(), k_release_zero<<<std::max(1, std::min<int>((int)ceil_div(n_leaves, TPB / 32), sm_count() * 8)), TPB, 0, stream_>>>(dev_, n_leaves);
   BNX_CUDA(cudaGetLastError());
   int4* fresh = nullptr;
   BNX_CUDA(cudaMalloc(&fresh, root_slots_ * sizeof(int4)));
   BNX_CUDA(cudaMemsetAsync(fresh, 0, root_slots_ * sizeof(int4), stream_));
-  k_rebuild_roots<<<grid_for((i64)root_slots_), TPB, 0, stream_>>>(dev_, root_, root_slots_, fresh, dev_.root_mask, std::max(1u, children / 64u));
+  note_launch(), k_rebuild_roots<<<grid_for((i64)root_slots_), TPB, 0, stream_>>>(dev_, root_, root_slots_, fresh, dev_.root_mask, std::max(1u, children / 64u));
   BNX_CUDA(cudaGetLastError());
   BNX_TRY(sync());
   BNX_CUDA(cudaFree(root_));

@@ -57,7 +57,17 @@ __device__ __forceinline__ int4 classify_point(double px, double py, double pz, 
                    __double2int_rd(__dmul_rn(ez, p.inv_res)), type);
 }
 
-template <bool F64, bool VEC4>
+// Endpoint dedupe table, two flavours (0 always means "empty" so that ONE memset clears counters + table):
+//   PACKED   all endpoint voxels of the scan fit 21 bits per axis (guaranteed by the host from origin and
+//            max_range): 64-bit key = packed xyz + 1 claimed by atomicCAS, value = max(~index) = lowest index.
+//   indirect any coordinates: a slot holds (point index + 1) and its key is ep[index].xyz; needs ep[i] to be
+//            visible (fence) before the slot can name i.
+__device__ __forceinline__ unsigned long long pack_key(const int4& e) {
+  return ((unsigned long long)(u32)(e.x + (1 << 20)) | ((unsigned long long)(u32)(e.y + (1 << 20)) << 21) |
+          ((unsigned long long)(u32)(e.z + (1 << 20)) << 42)) + 1ull;
+}
+
+template <bool F64, bool VEC4, bool PACKED>
 __global__ void __launch_bounds__(TPB) k_classify(const unsigned char* __restrict__ pts, u32 stride, ScanParams p, ScanBuffers b) {
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.n) return;
@@ -80,23 +90,64 @@ __global__ void __launch_bounds__(TPB) k_classify(const unsigned char* __restric
   }
   const int4 e = classify_point(px, py, pz, p);
   b.ep[i] = e;
-  __threadfence();  // ep[i] must be visible before a table slot can name i
-  // scan-local hash with indirect keys: a slot holds a point index, its key is ep[index].xyz
   u32 slot = (u32)hash3(e.x, e.y, e.z) & p.hash_mask;
-  for (;;) {
-    u32 v = b.table[slot];
-    if (v == NONE) {
-      v = atomicCAS(&b.table[slot], NONE, i);
-      if (v == NONE) break;  // claimed an empty slot
+  if (PACKED) {
+    const unsigned long long key = pack_key(e);
+    for (;;) {
+      unsigned long long k = b.keys[slot];
+      if (k == 0ull) k = atomicCAS(&b.keys[slot], 0ull, key);
+      if (k == 0ull || k == key) break;
+      slot = (slot + 1) & p.hash_mask;
     }
-    const int4 o = __ldcg(&b.ep[v]);
-    if (o.x == e.x && o.y == e.y && o.z == e.z) {
-      if (i < v) atomicMin(&b.table[slot], i);
-      break;
+    atomicMax(&b.table[slot], ~i);
+  } else {
+    __threadfence();  // ep[i] must be visible before a table slot can name i
+    for (;;) {
+      u32 v = b.table[slot];
+      if (v == 0u) {
+        v = atomicCAS(&b.table[slot], 0u, i + 1u);
+        if (v == 0u) break;  // claimed an empty slot
+      }
+      const int4 o = __ldcg(&b.ep[v - 1u]);
+      if (o.x == e.x && o.y == e.y && o.z == e.z) {
+        if (i + 1u < v) atomicMin(&b.table[slot], i + 1u);
+        break;
+      }
+      slot = (slot + 1) & p.hash_mask;
     }
-    slot = (slot + 1) & p.hash_mask;
   }
   b.slot_of[i] = slot;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ray geometry shared by resolve (chunk accounting) and mark (the walk)
+// ------------------------------------------------------------------------------------------------
+// A ray origin -> end has m = max|delta| cells k = 0..m-1 (probabilistic_map.hpp:173-183; the end cell is
+// excluded). Along the major axis (|delta| == m) cell k sits exactly at origin + sign*k, so the ray is cut into
+// chunks at the 8-cell LEAF boundaries of that axis: chunk 0 = the len0 cells up to the first boundary, then 8
+// cells each. Inside a chunk the major leaf coordinate is constant and each minor axis crosses at most one
+// leaf boundary.
+struct RayGeom {
+  u32 ax, ay, az, m;
+  int sx, sy, sz;
+  u32 len0, chunks;
+};
+
+__device__ __forceinline__ RayGeom ray_geom(const ScanParams& p, int ex, int ey, int ez) {
+  RayGeom r;
+  const i64 dx = (i64)ex - p.Ox, dy = (i64)ey - p.Oy, dz = (i64)ez - p.Oz;
+  r.ax = (u32)(dx < 0 ? -dx : dx);
+  r.ay = (u32)(dy < 0 ? -dy : dy);
+  r.az = (u32)(dz < 0 ? -dz : dz);
+  r.sx = dx < 0 ? -1 : 1;
+  r.sy = dy < 0 ? -1 : 1;
+  r.sz = dz < 0 ? -1 : 1;
+  r.m = max(max(r.ax, r.ay), r.az);
+  const int Oa = r.ax == r.m ? p.Ox : (r.ay == r.m ? p.Oy : p.Oz);
+  const int sa = r.ax == r.m ? r.sx : (r.ay == r.m ? r.sy : r.sz);
+  r.len0 = sa > 0 ? 8u - ((u32)Oa & 7u) : ((u32)Oa & 7u) + 1u;
+  r.chunks = r.m == 0u ? 0u : (r.m <= r.len0 ? 1u : 1u + (r.m - r.len0 + 7u) / 8u);
+  return r;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -124,14 +175,14 @@ __global__ void __launch_bounds__(TPB) k_resolve(GridDev g, ScanParams p, ScanBu
 
   bool is_end = false;
   int4 e = make_int4(0, 0, 0, 0);
-  u32 leaf = NONE, ci = 0, m = 0;
+  u32 leaf = NONE, ci = 0, m = 0, chunks = 0;
   if (i < count) {
     bool winner;
     if (PENDING) {
       e = b.pending[i];
       winner = true;
     } else {
-      winner = b.table[b.slot_of[i]] == i;
+      winner = b.table[b.slot_of[i]] == (p.packed ? ~i : i + 1u);
       if (winner) e = b.ep[i];
     }
     if (winner) {
@@ -149,13 +200,12 @@ __global__ void __launch_bounds__(TPB) k_resolve(GridDev g, ScanParams p, ScanBu
       }
       if (!stale) {
         is_end = true;
-        const i64 dx = (i64)e.x - p.Ox, dy = (i64)e.y - p.Oy, dz = (i64)e.z - p.Oz;
-        const u64 ax = dx < 0 ? -dx : dx, ay = dy < 0 ? -dy : dy, az = dz < 0 ? -dz : dz;
-        m = (u32)max(max(ax, ay), az);  // probabilistic_map.hpp:180; the ray has exactly m cells (end excluded)
+        const RayGeom rg = ray_geom(p, e.x, e.y, e.z);
+        m = rg.m;  // probabilistic_map.hpp:180; the ray has exactly m cells (end excluded)
+        chunks = rg.chunks;
       }
     }
   }
-  u32 chunks = m / CHUNK + (m % CHUNK != 0);
   if (chunks > p.max_chunks) {  // would overflow the packed counter: refuse the scan (BNX_ERR_UNSUPPORTED)
     atomicOr(&b.sc->overflow, OVF_CHUNKS);
     chunks = 0;
@@ -214,105 +264,80 @@ __global__ void __launch_bounds__(TPB) k_resolve(GridDev g, ScanParams p, ScanBu
 // ------------------------------------------------------------------------------------------------
 // phase 3: mark ray cells
 // ------------------------------------------------------------------------------------------------
-struct LeafCursor {
-  int bx, by, bz;  // current leaf key = coord >> 3
-  int rx, ry, rz;  // current root key = coord >> 5
-  u32 inner, leaf;
-  u32 word;  // current 64-bit word of the touched mask (= z & 7)
-  unsigned long long bits;
-  bool valid;
-};
-
-__device__ __forceinline__ void cursor_flush(const GridDev& g, LeafCursor& c) {
-  if (c.bits && c.leaf != NONE) {
-    unsigned long long* t = reinterpret_cast<unsigned long long*>(leaf_touched(g, c.leaf)) + c.word;
-    if ((*t & c.bits) != c.bits) atomicOr(t, c.bits);  // test first: the leaves around the sensor are hit by every ray
+// One lane = one chunk of one ray.
+//   walk   exact integer DDA restarted from the closed form at the chunk's first cell (cell k of RayIterator,
+//          probabilistic_map.hpp:162-203, is origin + sign * floor((2*k*|d| + m) / (2*m)) per axis with residual
+//          error k*|d| - pos*m, then the reference's own error accumulator). Pure ALU; the (leaf, mask word)
+//          segments it crosses — at most 8, never repeating because every coordinate is monotone — are pushed
+//          on a per-lane stack in shared memory.
+//   flush  all lanes then walk their segment stacks in lock step (convergent): find-or-create the leaf, test
+//          the 64-bit touched word and only atomicOr when it adds bits. The thread that turns a word from 0
+//          to non-zero stamps the leaf and, if the leaf was not stamped in this scan yet, lists it.
+template <typename E>
+__device__ __forceinline__ u32 walk_chunk(const ScanParams& p, const RayGeom& r, u32 k0, u32 k1, int& lx0, int& ly0, int& lz0,
+                                          unsigned long long (*s_bits)[TPB], unsigned char (*s_key)[TPB]) {
+  u32 px, py, pz;
+  if (r.m < 32768u) {
+    px = (2u * k0 * r.ax + r.m) / (2u * r.m);
+    py = (2u * k0 * r.ay + r.m) / (2u * r.m);
+    pz = (2u * k0 * r.az + r.m) / (2u * r.m);
+  } else {
+    px = (u32)((2ull * k0 * r.ax + r.m) / (2ull * r.m));
+    py = (u32)((2ull * k0 * r.ay + r.m) / (2ull * r.m));
+    pz = (u32)((2ull * k0 * r.az + r.m) / (2ull * r.m));
   }
-  c.bits = 0;
-}
-
-__device__ __forceinline__ void cursor_visit(const GridDev& g, const ScanParams& p, const ScanBuffers& b, LeafCursor& c, int x, int y, int z) {
-  const int bx = x >> 3, by = y >> 3, bz = z >> 3;
-  if (!c.valid || bx != c.bx || by != c.by || bz != c.bz) {
-    cursor_flush(g, c);
-    const int rx = x >> 5, ry = y >> 5, rz = z >> 5;
-    if (!c.valid || rx != c.rx || ry != c.ry || rz != c.rz) {
-      const int kx = x & ~31, ky = y & ~31, kz = z & ~31;
-      c.inner = root_find(g, kx, ky, kz);
-      if (c.inner == NONE) c.inner = root_find_or_insert(g, kx, ky, kz);
-      c.rx = rx;
-      c.ry = ry;
-      c.rz = rz;
-    }
-    c.leaf = c.inner == NONE ? NONE : leaf_in_inner_or_create(g, c.inner, x, y, z);
-    c.bx = bx;
-    c.by = by;
-    c.bz = bz;
-    c.valid = true;
-    c.word = (u32)z & 7u;
-    if (c.leaf != NONE) {
-      u32* st = leaf_stamp(g, c.leaf);
-      if (*st != p.seq && atomicExch(st, p.seq) != p.seq) {
-        const u32 at = atomicAdd(&b.sc->n_touched, 1u);
-        if (at < p.touched_cap) b.touched[at] = c.leaf;
+  E ex = (E)((i64)k0 * r.ax - (i64)px * r.m), ey = (E)((i64)k0 * r.ay - (i64)py * r.m), ez = (E)((i64)k0 * r.az - (i64)pz * r.m);
+  int x = p.Ox + r.sx * (int)px, y = p.Oy + r.sy * (int)py, z = p.Oz + r.sz * (int)pz;
+  lx0 = x >> 3;
+  ly0 = y >> 3;
+  lz0 = z >> 3;
+  u32 nseg = 0, key = 0xFFFFFFFFu;
+  unsigned long long bits = 0;
+  const E em = (E)r.m;
+#pragma unroll
+  for (u32 c = 0; c < CHUNK; ++c) {
+    if (k0 + c < k1) {
+      // quadrant = which minor axes have crossed into the neighbouring leaf; word = z & 7
+      const u32 q = (u32)((x >> 3) != lx0) | ((u32)((y >> 3) != ly0) << 1) | ((u32)((z >> 3) != lz0) << 2);
+      const u32 kc = (q << 3) | ((u32)z & 7u);
+      if (kc != key) {
+        if (bits) {
+          s_bits[nseg][threadIdx.x] = bits;
+          s_key[nseg][threadIdx.x] = (unsigned char)key;
+          ++nseg;
+        }
+        key = kc;
+        bits = 0;
+      }
+      bits |= 1ull << (((u32)x & 7u) | (((u32)y & 7u) << 3));
+      ex += (E)r.ax;
+      ey += (E)r.ay;
+      ez += (E)r.az;
+      if ((ex << 1) >= em) {
+        x += r.sx;
+        ex -= em;
+      }
+      if ((ey << 1) >= em) {
+        y += r.sy;
+        ey -= em;
+      }
+      if ((ez << 1) >= em) {
+        z += r.sz;
+        ez -= em;
       }
     }
-  } else if (((u32)z & 7u) != c.word) {
-    cursor_flush(g, c);
-    c.word = (u32)z & 7u;
   }
-  c.bits |= 1ull << (((u32)x & 7u) | (((u32)y & 7u) << 3));
-}
-
-// Cells k0 .. min(k0+8, m)-1 of the ray origin -> end. Cell k of RayIterator (probabilistic_map.hpp:162-203)
-// is origin + sign * floor((2*k*|d| + m) / (2*m)) per axis, with residual error k*|d| - pos*m: the walk is
-// restarted from that closed form and then advanced with the reference's own error accumulator.
-template <typename E>
-__device__ __forceinline__ void walk_chunk(const GridDev& g, const ScanParams& p, const ScanBuffers& b, const int4 ray, u32 k0) {
-  const i64 dx = (i64)ray.x - p.Ox, dy = (i64)ray.y - p.Oy, dz = (i64)ray.z - p.Oz;
-  const u32 ax = (u32)(dx < 0 ? -dx : dx), ay = (u32)(dy < 0 ? -dy : dy), az = (u32)(dz < 0 ? -dz : dz);
-  const int sx = dx < 0 ? -1 : 1, sy = dy < 0 ? -1 : 1, sz = dz < 0 ? -1 : 1;
-  const u32 m = max(max(ax, ay), az);
-  const u32 k1 = min(k0 + CHUNK, m);
-  u32 px, py, pz;
-  if (m < 32768u) {
-    px = (2u * k0 * ax + m) / (2u * m);
-    py = (2u * k0 * ay + m) / (2u * m);
-    pz = (2u * k0 * az + m) / (2u * m);
-  } else {
-    px = (u32)((2ull * k0 * ax + m) / (2ull * m));
-    py = (u32)((2ull * k0 * ay + m) / (2ull * m));
-    pz = (u32)((2ull * k0 * az + m) / (2ull * m));
+  if (bits) {
+    s_bits[nseg][threadIdx.x] = bits;
+    s_key[nseg][threadIdx.x] = (unsigned char)key;
+    ++nseg;
   }
-  E ex = (E)((i64)k0 * ax - (i64)px * m), ey = (E)((i64)k0 * ay - (i64)py * m), ez = (E)((i64)k0 * az - (i64)pz * m);
-  int x = p.Ox + sx * (int)px, y = p.Oy + sy * (int)py, z = p.Oz + sz * (int)pz;
-  LeafCursor c;
-  c.valid = false;
-  c.bits = 0;
-  c.leaf = NONE;
-  c.inner = NONE;
-  for (u32 k = k0; k < k1; ++k) {
-    cursor_visit(g, p, b, c, x, y, z);
-    ex += (E)ax;
-    ey += (E)ay;
-    ez += (E)az;
-    if ((ex << 1) >= (E)m) {
-      x += sx;
-      ex -= (E)m;
-    }
-    if ((ey << 1) >= (E)m) {
-      y += sy;
-      ey -= (E)m;
-    }
-    if ((ez << 1) >= (E)m) {
-      z += sz;
-      ez -= (E)m;
-    }
-  }
-  cursor_flush(g, c);
+  return nseg;
 }
 
 __global__ void __launch_bounds__(TPB) k_mark(GridDev g, ScanParams p, ScanBuffers b) {
+  __shared__ unsigned long long s_bits[CHUNK][TPB];
+  __shared__ unsigned char s_key[CHUNK][TPB];
   const unsigned long long rc = b.sc->ray_chunk;
   const u32 n_rays = (u32)(rc >> 40);
   const u32 total = (u32)(rc & CHUNK_FIELD);
@@ -331,18 +356,67 @@ __global__ void __launch_bounds__(TPB) k_mark(GridDev g, ScanParams p, ScanBuffe
     }
     const u32 starts = __reduce_or_sync(0xffffffffu, bit);
     const u32 chunk = c0 + lane;
+    u32 nseg = 0;
+    int lx0 = 0, ly0 = 0, lz0 = 0, sx = 1, sy = 1, sz = 1;
     if (chunk < total) {
       const u32 r = r_first + __popc(starts & ((2u << lane) - 1u));
       const int4 ray = b.rays[r];
-      const u32 k0 = (chunk - (u32)ray.w) * CHUNK;
-      const i64 dx = (i64)ray.x - p.Ox, dy = (i64)ray.y - p.Oy, dz = (i64)ray.z - p.Oz;
-      const u64 mm = max(max(dx < 0 ? -dx : dx, dy < 0 ? -dy : dy), dz < 0 ? -dz : dz);
-      if (mm < (1u << 29)) {
-        walk_chunk<int>(g, p, b, ray, k0);
-      } else {
-        walk_chunk<i64>(g, p, b, ray, k0);
+      const RayGeom rg = ray_geom(p, ray.x, ray.y, ray.z);
+      const u32 j = chunk - (u32)ray.w;
+      const u32 k0 = j == 0u ? 0u : rg.len0 + 8u * (j - 1u);
+      const u32 k1 = min(rg.m, j == 0u ? rg.len0 : k0 + 8u);
+      sx = rg.sx;
+      sy = rg.sy;
+      sz = rg.sz;
+      nseg = rg.m < (1u << 29) ? walk_chunk<int>(p, rg, k0, k1, lx0, ly0, lz0, s_bits, s_key)
+                               : walk_chunk<i64>(p, rg, k0, k1, lx0, ly0, lz0, s_bits, s_key);
+    }
+    // ---- flush, segment ordinal by segment ordinal (segments with the same leaf are consecutive)
+    const u32 nmax = __reduce_max_sync(0xffffffffu, nseg);
+    u32 cur_q = 0xFFu, leaf = NONE, inner = NONE;
+    int rrx = 0, rry = 0, rrz = 0;
+    bool have_root = false;
+    for (u32 sgi = 0; sgi < nmax; ++sgi) {
+      if (sgi < nseg) {
+        const u32 key = s_key[sgi][threadIdx.x];
+        const unsigned long long bits = s_bits[sgi][threadIdx.x];
+        const u32 q = key >> 3, w = key & 7u;
+        if (q != cur_q) {
+          cur_q = q;
+          const int lx = lx0 + ((q & 1u) ? sx : 0), ly = ly0 + ((q & 2u) ? sy : 0), lz = lz0 + ((q & 4u) ? sz : 0);
+          const int rx = lx >> 2, ry = ly >> 2, rz = lz >> 2;
+          if (!have_root || rx != rrx || ry != rry || rz != rrz) {
+            inner = root_find(g, rx << 5, ry << 5, rz << 5);
+            if (inner == NONE) inner = root_find_or_insert(g, rx << 5, ry << 5, rz << 5);
+            rrx = rx;
+            rry = ry;
+            rrz = rz;
+            have_root = true;
+          }
+          leaf = inner == NONE ? NONE : leaf_in_inner_or_create(g, inner, lx << 3, ly << 3, lz << 3);
+        }
+        if (leaf != NONE) {
+          unsigned long long* t = reinterpret_cast<unsigned long long*>(leaf_touched(g, leaf)) + w;
+          // test first (a stale L1 line only costs a redundant atomic): the leaves around the sensor are hit by every ray
+          if ((*t & bits) != bits) {
+            const unsigned long long old = atomicOr(t, bits);
+            if (old == 0ull && atomicExch(leaf_stamp(g, leaf), p.seq) != p.seq) {
+              const u32 at = atomicAdd(&b.sc->n_touched, 1u);
+              if (at < p.touched_cap) b.touched[at] = leaf;
+            }
+          }
+        }
       }
     }
+  }
+}
+
+// retry path only: a failed attempt leaves touched bits behind; the list of that attempt says where
+__global__ void __launch_bounds__(TPB) k_clear_touched(GridDev g, ScanBuffers b, u32 n) {
+  const u32 lane = threadIdx.x & 31;
+  const u32 warps = gridDim.x * (TPB / 32);
+  for (u32 t = blockIdx.x * (TPB / 32) + (threadIdx.x >> 5); t < n; t += warps) {
+    if (lane < 8) reinterpret_cast<unsigned long long*>(leaf_touched(g, b.touched[t]))[lane] = 0ull;
   }
 }
 
@@ -370,6 +444,8 @@ __global__ void __launch_bounds__(TPB) k_apply_endpoints(GridDev g, ScanParams p
 
 // clearPoint over the union of all rays, probabilistic_map.cpp:81-89: one warp per touched leaf
 __global__ void __launch_bounds__(TPB) k_apply_leaves(GridDev g, ScanParams p, ScanBuffers b) {
+  // last kernel of the scan: the host reads counters + grid counters with one copy
+  if (blockIdx.x == 0 && threadIdx.x == 0) b.sc->gc = *g.ctr;
   if (g.ctr->error | b.sc->overflow) return;
   const u32 n = min(b.sc->n_touched, p.touched_cap);
   const u32 lane = threadIdx.x & 31;
@@ -385,23 +461,25 @@ __global__ void __launch_bounds__(TPB) k_apply_leaves(GridDev g, ScanParams p, S
       tw = touched[lane];
       aw = active[lane];
     }
+    // lane owns cells it*32 + lane, it = 0..15 (coalesced 128-B rows); bit `it` of mine/on = that cell touched/ON
+    u32 mine = 0, on = 0;
 #pragma unroll
     for (u32 w = 0; w < 8; ++w) {
       const unsigned long long t64 = __shfl_sync(0xffffffffu, tw, w);
-      if (t64 == 0) continue;
       const unsigned long long a64 = __shfl_sync(0xffffffffu, aw, w);
+      mine |= (u32)((t64 >> lane) & 1ull) << (2 * w) | (u32)((t64 >> (32 + lane)) & 1ull) << (2 * w + 1);
+      on |= (u32)((a64 >> lane) & 1ull) << (2 * w) | (u32)((a64 >> (32 + lane)) & 1ull) << (2 * w + 1);
+    }
+    // all loads of this leaf are issued before the first use (memory-level parallelism)
+    u32 word[16];
 #pragma unroll
-      for (u32 half = 0; half < 2; ++half) {
-        const u32 bit = half * 32 + lane;
-        if ((t64 >> bit) & 1ull) {
-          u32* cell = cells + w * 64 + bit;
-          const u32 word = ((a64 >> bit) & 1ull) ? *cell : 0u;
-          if ((word & 0xFu) != p.c) {
-            const i32 prob = max(((i32)word >> 4) + p.miss, p.cmin);
-            *cell = ((u32)prob << 4) | p.c;
-            ++changed;
-          }
-        }
+    for (u32 it = 0; it < 16; ++it) word[it] = ((mine & on) >> it) & 1u ? cells[it * 32 + lane] : 0u;
+#pragma unroll
+    for (u32 it = 0; it < 16; ++it) {
+      if (((mine >> it) & 1u) && (word[it] & 0xFu) != p.c) {
+        const i32 prob = max(((i32)word[it] >> 4) + p.miss, p.cmin);
+        cells[it * 32 + lane] = ((u32)prob << 4) | p.c;
+        ++changed;
       }
     }
     if (lane < 8 && tw) {
@@ -461,7 +539,6 @@ __global__ void __launch_bounds__(TPB) k_query(GridDev g, const i32* __restrict_
 // ------------------------------------------------------------------------------------------------
 Map::~Map() {
   if (grid.stream()) cudaStreamSynchronize(grid.stream());
-  if (d_sc_) cudaFree(d_sc_);
   if (h_status_) cudaFreeHost(h_status_);
   for (auto& e : ev_)
     if (e) cudaEventDestroy(e);
@@ -471,6 +548,15 @@ static i32 logods_host(float prob) {  // probabilistic_map.hpp:34-36
   return (i32)(1e6 * std::log(prob / (1.0 - prob)));
 }
 
+constexpr size_t SC_BYTES = 128;  // ScanCounters header of b_table_
+static_assert(sizeof(ScanCounters) <= SC_BYTES, "ScanCounters must fit its header");
+
+static u64 table_slots(i64 n) {
+  u64 slots = 1024;
+  while (slots < (u64)n * 2) slots <<= 1;
+  return slots;
+}
+
 int Map::init(double resolution) {
   BNX_TRY(grid.init(resolution, 2, 3, 4));  // probabilistic_map.cpp:14-16
   options[0] = logods_host(0.4f);
@@ -478,13 +564,11 @@ int Map::init(double resolution) {
   options[2] = logods_host(0.12f);
   options[3] = logods_host(0.97f);
   options[4] = logods_host(0.5f);
-  BNX_CUDA(cudaMalloc(&d_sc_, sizeof(ScanCounters)));
-  BNX_CUDA(cudaMallocHost(&h_status_, sizeof(Status)));
+  BNX_CUDA(cudaMallocHost(&h_status_, sizeof(ScanCounters)));
   for (auto& e : ev_) BNX_CUDA(cudaEventCreate(&e));
-  buf_.sc = d_sc_;
   BNX_TRY(b_pending_.reserve(1024 * sizeof(int4)));
   buf_.pending = b_pending_.as<int4>();
-  return BNX_OK;
+  return reserve_scan(0, 16, 1.0);
 }
 
 int Map::reserve_scan(i64 n, i64 stride_bytes, double max_range) {
@@ -494,18 +578,21 @@ int Map::reserve_scan(i64 n, i64 stride_bytes, double max_range) {
   BNX_TRY(b_slot_.reserve(np * 4));
   BNX_TRY(b_ends_.reserve(np * sizeof(uint2)));
   BNX_TRY(b_rays_.reserve(np * sizeof(int4)));
-  u64 slots = 1024;
-  while (slots < (u64)n * 2) slots <<= 1;
-  BNX_TRY(b_table_.reserve(slots * 4));
+  // [ScanCounters | table u32[slots] | keys u64[slots]] — contiguous so that one memset clears all of it
+  const u64 slots = table_slots(n);
+  BNX_TRY(b_table_.reserve(SC_BYTES + slots * 12));
   // 32-chunk tiles: estimated from the longest possible ray, grown on overflow
   double cells = std::isfinite(max_range) ? std::ceil(max_range * grid.inv_resolution) + 2.0 : 512.0;
   cells = std::min(cells, 4096.0);
-  const size_t tiles = (size_t)((double)np * (cells / CHUNK + 1.0) / 32.0) + np / 32 + 64;
+  const size_t tiles = (size_t)((double)np * (cells / CHUNK + 2.0) / 32.0) + np / 32 + 64;
   BNX_TRY(b_tiles_.reserve(tiles * 4));
   BNX_TRY(b_touched_.reserve((size_t)grid.dev().leaf_cap * 4));
+  d_sc_ = b_table_.as<ScanCounters>();
+  buf_.sc = d_sc_;
+  buf_.table = reinterpret_cast<u32*>(b_table_.as<unsigned char>() + SC_BYTES);
+  buf_.keys = reinterpret_cast<unsigned long long*>(b_table_.as<unsigned char>() + SC_BYTES + slots * 4);
   buf_.ep = b_ep_.as<int4>();
   buf_.slot_of = b_slot_.as<u32>();
-  buf_.table = b_table_.as<u32>();
   buf_.ends = b_ends_.as<uint2>();
   buf_.rays = b_rays_.as<int4>();
   buf_.tile_first = b_tiles_.as<u32>();
@@ -549,27 +636,45 @@ int Map::insert(const void* points, i64 stride_bytes, i64 n, bool f64, const dou
   p.c = update_count;
   p.n = (u32)n;
   p.max_chunks = (u32)std::min<u64>(((1ull << 40) - 1) / (u64)std::max<i64>(n + n_pending_, 1), 1ull << 28);
+  // every endpoint lies within max_range of the origin (hits by the range test, misses by truncation): if that
+  // ball fits 21 bits per axis the dedupe table can use packed keys
+  p.packed = 0;
+  if (std::isfinite(max_range) && max_range >= 0.0) {
+    const double reach = std::ceil(max_range * grid.inv_resolution) + 4.0;
+    const double lim = (double)(1 << 20) - 1.0;
+    if (std::fabs((double)p.Ox) + reach < lim && std::fabs((double)p.Oy) + reach < lim && std::fabs((double)p.Oz) + reach < lim) p.packed = 1;
+  }
   return run_scan(d_points, stride_bytes, f64, p, false);
+}
+
+template <bool F64, bool VEC4>
+static void launch_classify(bool packed, int blocks, cudaStream_t s, const unsigned char* pts, u32 stride, const ScanParams& p, const ScanBuffers& b) {
+  note_launch();
+  if (packed) {
+    k_classify<F64, VEC4, true><<<blocks, TPB, 0, s>>>(pts, stride, p, b);
+  } else {
+    k_classify<F64, VEC4, false><<<blocks, TPB, 0, s>>>(pts, stride, p, b);
+  }
 }
 
 int Map::run_scan(const void* d_points, i64 stride_bytes, bool f64, const ScanParams& base, bool) {
   cudaStream_t s = grid.stream();
   ScanParams p = base;
   const i64 n = p.n;
-  u64 slots = 1024;
-  while (slots < (u64)n * 2) slots <<= 1;
+  const u64 slots = table_slots(n);
   p.hash_mask = (u32)(slots - 1);
   if (profiling) cudaEventRecord(ev_[1], s);
+  // counters + dedupe table (+ packed keys) in one clear
+  BNX_CUDA(cudaMemsetAsync(d_sc_, 0, n > 0 ? SC_BYTES + slots * (p.packed ? 12 : 4) : SC_BYTES, s));
   if (n > 0) {
-    BNX_CUDA(cudaMemsetAsync(buf_.table, 0xFF, slots * 4, s));
     const unsigned char* pts = static_cast<const unsigned char*>(d_points);
     const int blocks = blocks_for(n);
     if (f64) {
-      k_classify<true, false><<<blocks, TPB, 0, s>>>(pts, (u32)stride_bytes, p, buf_);
+      launch_classify<true, false>(p.packed, blocks, s, pts, (u32)stride_bytes, p, buf_);
     } else if (stride_bytes == 16 && (reinterpret_cast<uintptr_t>(pts) & 15u) == 0) {
-      k_classify<false, true><<<blocks, TPB, 0, s>>>(pts, 16u, p, buf_);
+      launch_classify<false, true>(p.packed, blocks, s, pts, 16u, p, buf_);
     } else {
-      k_classify<false, false><<<blocks, TPB, 0, s>>>(pts, (u32)stride_bytes, p, buf_);
+      launch_classify<false, false>(p.packed, blocks, s, pts, (u32)stride_bytes, p, buf_);
     }
     BNX_CUDA(cudaGetLastError());
   }
@@ -586,44 +691,48 @@ int Map::run_scan(const void* d_points, i64 stride_bytes, bool f64, const ScanPa
     p.tile_cap = (u32)std::min<size_t>(b_tiles_.bytes / 4, 0xFFFFFFFFull);
     p.touched_cap = (u32)std::min<size_t>(b_touched_.bytes / 4, 0xFFFFFFFFull);
     const GridDev g = grid.dev();
-    BNX_CUDA(cudaMemsetAsync(d_sc_, 0, sizeof(ScanCounters), s));
-    if (n_pending_) k_resolve<true><<<blocks_for(n_pending_), TPB, 0, s>>>(g, p, buf_, n_pending_);
-    if (n > 0) k_resolve<false><<<blocks_for(n), TPB, 0, s>>>(g, p, buf_, (u32)n);
+    if (retries) BNX_CUDA(cudaMemsetAsync(d_sc_, 0, SC_BYTES, s));
+    if (n_pending_) note_launch(), k_resolve<true><<<blocks_for(n_pending_), TPB, 0, s>>>(g, p, buf_, n_pending_);
+    if (n > 0) note_launch(), k_resolve<false><<<blocks_for(n), TPB, 0, s>>>(g, p, buf_, (u32)n);
     if (profiling && retries == 0) cudaEventRecord(ev_[3], s);
-    k_mark<<<persistent, TPB, 0, s>>>(g, p, buf_);
+    note_launch(), k_mark<<<persistent, TPB, 0, s>>>(g, p, buf_);
     if (profiling && retries == 0) cudaEventRecord(ev_[4], s);
-    k_apply_endpoints<<<std::min(persistent, blocks_for(n + 1)), TPB, 0, s>>>(g, p, buf_);
-    k_apply_leaves<<<persistent, TPB, 0, s>>>(g, p, buf_);
+    note_launch(), k_apply_endpoints<<<std::min(persistent, blocks_for(n + 1)), TPB, 0, s>>>(g, p, buf_);
+    note_launch(), k_apply_leaves<<<persistent, TPB, 0, s>>>(g, p, buf_);
     BNX_CUDA(cudaGetLastError());
     if (profiling && retries == 0) cudaEventRecord(ev_[5], s);
-    BNX_CUDA(cudaMemcpyAsync(&h_status_->sc, d_sc_, sizeof(ScanCounters), cudaMemcpyDeviceToHost, s));
-    BNX_CUDA(cudaMemcpyAsync(&h_status_->gc, g.ctr, sizeof(GridCounters), cudaMemcpyDeviceToHost, s));
+    BNX_CUDA(cudaMemcpyAsync(h_status_, d_sc_, sizeof(ScanCounters), cudaMemcpyDeviceToHost, s));
     BNX_CUDA(cudaStreamSynchronize(s));
-    const Status st = *h_status_;
-    if (st.gc.error == 0 && st.sc.overflow == 0) break;
+    const ScanCounters st = *h_status_;
+    if (st.gc.error == 0 && st.overflow == 0) break;
     // phases 4/5 skipped themselves: nothing was applied. Grow what was short and repeat from phase 2.
-    if (st.sc.overflow & OVF_CHUNKS) {
+    if (st.overflow & OVF_CHUNKS) {
       set_error("insert: more than 2^32 ray chunks in one scan");
       return BNX_ERR_UNSUPPORTED;
     }
+    if (st.n_touched) {
+      note_launch(), k_clear_touched<<<persistent, TPB, 0, s>>>(g, buf_, std::min(st.n_touched, p.touched_cap));
+      BNX_CUDA(cudaGetLastError());
+      BNX_CUDA(cudaStreamSynchronize(s));
+    }
     if (st.gc.error) BNX_TRY(grid.recover(st.gc));
-    if (st.sc.overflow & OVF_TILES) {
-      const u64 chunks = st.sc.ray_chunk & CHUNK_FIELD;
+    if (st.overflow & OVF_TILES) {
+      const u64 chunks = st.ray_chunk & CHUNK_FIELD;
       BNX_TRY(b_tiles_.reserve((size_t)(chunks / 32 + 64) * 4));
       buf_.tile_first = b_tiles_.as<u32>();
     }
     BNX_TRY(b_touched_.reserve((size_t)grid.dev().leaf_cap * 4));
     buf_.touched = b_touched_.as<u32>();
   }
-  const Status st = *h_status_;
+  const ScanCounters st = *h_status_;
   counters[0] = n;
-  counters[1] = (i64)st.sc.n_endpoints + n_pending_;
-  counters[2] = (i64)st.sc.sum_m + n;
-  counters[3] = (i64)st.sc.n_endpoints + st.sc.n_changed;
-  counters[4] = st.sc.n_touched;
+  counters[1] = (i64)st.n_endpoints + n_pending_;
+  counters[2] = (i64)st.sum_m + n;
+  counters[3] = (i64)st.n_endpoints + st.n_changed;
+  counters[4] = st.n_touched;
   counters[5] = retries;
-  counters[6] = (i64)(st.sc.ray_chunk >> 40);
-  counters[7] = (i64)(st.sc.ray_chunk & CHUNK_FIELD);
+  counters[6] = (i64)(st.ray_chunk >> 40);
+  counters[7] = (i64)(st.ray_chunk & CHUNK_FIELD);
   n_pending_ = 0;
   if (++update_count == 4) update_count = 1;  // probabilistic_map.cpp:103-105
   if (profiling) {
@@ -660,14 +769,14 @@ int Map::add_point(const double pt[3], bool miss) {
                            (i32)std::floor(pt[2] * grid.inv_resolution), miss ? 1 : 0);
   u32* d_flag = reinterpret_cast<u32*>(d_sc_);  // scratch word, rewritten by the next scan anyway
   for (int attempt = 0; attempt < 8; ++attempt) {
-    k_add_point<<<1, 1, 0, s>>>(grid.dev(), p, buf_, e, n_pending_, d_flag);
+    note_launch(), k_add_point<<<1, 1, 0, s>>>(grid.dev(), p, buf_, e, n_pending_, d_flag);
     BNX_CUDA(cudaGetLastError());
-    BNX_CUDA(cudaMemcpyAsync(&h_status_->sc, d_sc_, sizeof(u32), cudaMemcpyDeviceToHost, s));
+    BNX_CUDA(cudaMemcpyAsync(h_status_, d_sc_, sizeof(u32), cudaMemcpyDeviceToHost, s));
     GridCounters gc;
     BNX_TRY(grid.read_counters(&gc));
     if (gc.error == 0) {
       u32 queued;
-      std::memcpy(&queued, &h_status_->sc, 4);
+      std::memcpy(&queued, h_status_, 4);
       n_pending_ += queued;
       return BNX_OK;
     }
@@ -691,7 +800,7 @@ int Map::query(const i32* xyz, i64 n, int kind, u8* out, int where) {
     dx = b_q_xyz_.as<i32>();
     dout = b_q_out_.as<u8>();
   }
-  k_query<<<std::min(blocks_for(n), sm_count() * 8), TPB, 0, s>>>(grid.dev(), dx, n, kind, options[4], dout);
+  note_launch(), k_query<<<std::min(blocks_for(n), sm_count() * 8), TPB, 0, s>>>(grid.dev(), dx, n, kind, options[4], dout);
   BNX_CUDA(cudaGetLastError());
   if (where == BNX_HOST) {
     BNX_CUDA(cudaMemcpyAsync(out, dout, (size_t)n, cudaMemcpyDeviceToHost, s));

@@ -19,6 +19,7 @@ struct ScanParams {
   u32 tile_cap;                // entries of tile_first
   u32 touched_cap;             // entries of the touched-leaf list
   u32 max_chunks;              // per-ray chunk limit that keeps the packed (rays, chunks) counter exact
+  u32 packed;                  // 1: dedupe table uses packed 64-bit keys (all endpoints fit 21 bits per axis)
 };
 
 struct ScanCounters {
@@ -28,12 +29,14 @@ struct ScanCounters {
   u32 n_touched;                 // leaves on the touched list
   u32 n_changed;                 // cells changed by the free-space apply pass
   u32 overflow;                  // scan scratch overflow bits
+  GridCounters gc;               // snapshot of the grid counters taken by the last kernel of the scan
 };
 
 struct ScanBuffers {
   int4* ep;          // per point: endpoint voxel xyz + type (0 hit, 1 miss)
   u32* slot_of;      // per point: its slot in the dedupe table
   u32* table;        // endpoint dedupe table: lowest point index per voxel
+  unsigned long long* keys;  // packed-key flavour of the table
   uint2* ends;       // per updated endpoint: {leaf, cell index | type << 16}
   int4* rays;        // per ray with >= 1 cell: end voxel xyz + first chunk
   u32* tile_first;   // per 32-chunk tile: ray that owns the tile's first chunk
@@ -65,12 +68,8 @@ class Map {
 
   ScanBuffers buf_ = {};
   DevBuf b_pts_, b_ep_, b_slot_, b_table_, b_ends_, b_rays_, b_tiles_, b_touched_, b_pending_, b_q_xyz_, b_q_out_;
-  ScanCounters* d_sc_ = nullptr;
-  struct Status {
-    ScanCounters sc;
-    GridCounters gc;
-  };
-  Status* h_status_ = nullptr;  // pinned
+  ScanCounters* d_sc_ = nullptr;    // head of b_table_: counters + dedupe table are cleared by ONE memset
+  ScanCounters* h_status_ = nullptr;  // pinned
   u32 n_pending_ = 0;
   u32 seq_ = 0;
   cudaEvent_t ev_[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};

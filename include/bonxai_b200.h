@@ -53,6 +53,8 @@ enum { BNX_OCCUPIED = 0, BNX_UNKNOWN = 1, BNX_FREE = 2 };
 
 BNX_API int bnx_version(void);
 BNX_API const char* bnx_last_error(void);
+/* number of CUDA kernels this library has launched in this process (instrumentation for bench.py) */
+BNX_API int64_t bnx_launch_count(void);
 /* number of usable CUDA devices; 0 with BNX_OK when the driver is present but no device is */
 BNX_API int bnx_device_count(int* count);
 /* pinned host memory for zero-staging H2D/D2H of point clouds and dumps */
