@@ -35,6 +35,7 @@ SYMBOLS = [
     "bnx_map_get_options", "bnx_map_insert_f32", "bnx_map_insert_f64", "bnx_map_add_hit", "bnx_map_add_miss",
     "bnx_map_query", "bnx_map_get_voxels", "bnx_map_get_voxel_points", "bnx_map_counters", "bnx_map_update_count",
     "bnx_map_set_profiling", "bnx_map_phase_times",
+    "bnx_map_shard_config", "bnx_map_shard_begin", "bnx_map_shard_resolve_mark", "bnx_map_shard_merge", "bnx_map_shard_finish",
 ]
 
 

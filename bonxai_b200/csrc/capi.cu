@@ -267,6 +267,32 @@ int bnx_map_get_voxel_points(bnx_map_t* h, int kind, double* xyz, int64_t cap, i
   DeviceGuard dg(h->m.grid.device);
   return h->m.grid.dump(nullptr, xyz, nullptr, cap, count, where, kind, h->m.options[4]);
 }
+int bnx_map_shard_config(bnx_map_t* h, int rank, int world) {
+  BNX_HANDLE(h);
+  DeviceGuard dg(h->m.grid.device);
+  return h->m.shard_config(rank, world);
+}
+int bnx_map_shard_begin(bnx_map_t* h, const void* points, int64_t stride_bytes, int64_t n, int is_f64, uint32_t index_base,
+                        const double origin[3], double max_range, void* send_records, int64_t cap_records, int where) {
+  BNX_HANDLE(h);
+  DeviceGuard dg(h->m.grid.device);
+  return h->m.shard_begin(points, stride_bytes, n, is_f64 != 0, index_base, origin, max_range, send_records, cap_records, where);
+}
+int bnx_map_shard_resolve_mark(bnx_map_t* h, const void* recv_records, void* send_leaves, int64_t cap_leaves) {
+  BNX_HANDLE(h);
+  DeviceGuard dg(h->m.grid.device);
+  return h->m.shard_resolve_mark(recv_records, send_leaves, cap_leaves);
+}
+int bnx_map_shard_merge(bnx_map_t* h, const void* recv_leaves, void* flags) {
+  BNX_HANDLE(h);
+  DeviceGuard dg(h->m.grid.device);
+  return h->m.shard_merge(recv_leaves, flags);
+}
+int bnx_map_shard_finish(bnx_map_t* h, const void* flags_reduced, int* retry) {
+  BNX_HANDLE(h);
+  DeviceGuard dg(h->m.grid.device);
+  return h->m.shard_finish(flags_reduced, retry);
+}
 int bnx_map_counters(bnx_map_t* h, int64_t out[8]) {
   BNX_HANDLE(h);
   std::memcpy(out, h->m.counters, sizeof(int64_t) * 8);

@@ -76,7 +76,8 @@ class Grid {
   // ---- plumbing shared with the map
   GridDev dev() const { return dev_; }
   cudaStream_t stream() const { return stream_; }
-  void set_stream(cudaStream_t s) { stream_ = s ? s : own_stream_; }
+  // any stream handle, including 0 (the legacy default stream); BNX_OWN_STREAM selects the grid's private stream
+  void set_stream(cudaStream_t s) { stream_ = (s == reinterpret_cast<cudaStream_t>(~(uintptr_t)0)) ? own_stream_ : s; }
   int sync();
   // read the device counters (synchronises the stream)
   int read_counters(GridCounters* out);

@@ -31,7 +31,7 @@ namespace {
 constexpr int TPB = 256;
 constexpr u32 CHUNK = 8;  // ray cells per work item
 constexpr unsigned long long CHUNK_FIELD = (1ull << 40) - 1ull;
-constexpr u32 OVF_TILES = 1u, OVF_CHUNKS = 2u;
+constexpr u32 OVF_TILES = 1u, OVF_CHUNKS = 2u, OVF_RECORDS = 4u, OVF_LEAVES = 8u;
 
 inline int blocks_for(i64 n, int tpb = TPB) { return (int)std::max<i64>(1, ceil_div(n, tpb)); }
 
@@ -161,10 +161,19 @@ __device__ __forceinline__ unsigned long long warp_incl_scan(unsigned long long 
   return v;
 }
 
-// PENDING = false: one thread per point of the scan. PENDING = true: one thread per queued addHitPoint /
-// addMissPoint endpoint (already updated and stamped when it was queued; it only needs its ray).
-template <bool PENDING>
+// which root does which rank own (map sharding)? Uses the upper hash bits: the root table slot uses the lower.
+__host__ __device__ __forceinline__ u32 shard_owner(int rx, int ry, int rz, u32 world) {
+  return (u32)((hash3(rx, ry, rz) >> 34) % world);
+}
+
+// MODE 0: one thread per point of the scan (winner = lowest index of its endpoint voxel).
+// MODE 1: one thread per queued addHitPoint / addMissPoint endpoint (already updated and stamped when it was
+//         queued; it only needs its ray).
+// MODE 2: sharded map — one thread per slot of the received endpoint records [world][rec_cap]; w = global point
+//         index << 1 | type, winner = lowest w of its voxel.
+template <int MODE>
 __global__ void __launch_bounds__(TPB) k_resolve(GridDev g, ScanParams p, ScanBuffers b, u32 count) {
+  constexpr bool PENDING = MODE == 1;
   __shared__ unsigned long long s_warp[TPB / 32];
   __shared__ u32 s_warp_e[TPB / 32];
   __shared__ unsigned long long s_base, s_m;
@@ -178,9 +187,17 @@ __global__ void __launch_bounds__(TPB) k_resolve(GridDev g, ScanParams p, ScanBu
   u32 leaf = NONE, ci = 0, m = 0, chunks = 0;
   if (i < count) {
     bool winner;
-    if (PENDING) {
+    if (MODE == 1) {
       e = b.pending[i];
       winner = true;
+    } else if (MODE == 2) {
+      const u32 j = i % p.rec_cap;
+      winner = j >= 1u && j <= (u32)b.recs[i - j].x;  // a filled slot of its peer block
+      if (winner) {
+        e = b.recs[i];
+        winner = b.table[b.slot_of[i]] == ~(u32)e.w;
+        e.w &= 1;
+      }
     } else {
       winner = b.table[b.slot_of[i]] == (p.packed ? ~i : i + 1u);
       if (winner) e = b.ep[i];
@@ -335,7 +352,34 @@ __device__ __forceinline__ u32 walk_chunk(const ScanParams& p, const RayGeom& r,
   return nseg;
 }
 
-__global__ void __launch_bounds__(TPB) k_mark(GridDev g, ScanParams p, ScanBuffers b) {
+// leaf of (lx,ly,lz) [leaf coordinates] in grid G, creating root / inner / leaf as needed
+__device__ __forceinline__ u32 mark_leaf(const GridDev& G, u32& inner, bool new_root, int lx, int ly, int lz) {
+  if (new_root) {
+    const int kx = (lx >> 2) << 5, ky = (ly >> 2) << 5, kz = (lz >> 2) << 5;
+    inner = root_find(G, kx, ky, kz);
+    if (inner == NONE) inner = root_find_or_insert(G, kx, ky, kz);
+  }
+  return inner == NONE ? NONE : leaf_in_inner_or_create(G, inner, lx << 3, ly << 3, lz << 3);
+}
+
+// OR `bits` into word w of the leaf's touched mask; the thread that turns the word non-zero stamps the leaf and,
+// if nobody stamped it in this scan yet, appends it to the touched list
+__device__ __forceinline__ void mark_bits(const GridDev& G, u32 leaf, u32 w, unsigned long long bits, u32 seq, u32* n_list, u32* list, u32 cap) {
+  unsigned long long* t = reinterpret_cast<unsigned long long*>(leaf_touched(G, leaf)) + w;
+  // test first (a stale L1 line only costs a redundant atomic): the leaves around the sensor are hit by every ray
+  if ((*t & bits) != bits) {
+    const unsigned long long old = atomicOr(t, bits);
+    if (old == 0ull && atomicExch(leaf_stamp(G, leaf), seq) != seq) {
+      const u32 at = atomicAdd(n_list, 1u);
+      if (at < cap) list[at] = leaf;
+    }
+  }
+}
+
+// SHARD: cells whose root this rank does not own are marked in the scratch grid gs (same code, other pools);
+// their (leaf, mask) records travel to the owner after the kernel.
+template <bool SHARD>
+__global__ void __launch_bounds__(TPB) k_mark(GridDev g, GridDev gs, ScanParams p, ScanBuffers b) {
   __shared__ unsigned long long s_bits[CHUNK][TPB];
   __shared__ unsigned char s_key[CHUNK][TPB];
   const unsigned long long rc = b.sc->ray_chunk;
@@ -375,7 +419,7 @@ __global__ void __launch_bounds__(TPB) k_mark(GridDev g, ScanParams p, ScanBuffe
     const u32 nmax = __reduce_max_sync(0xffffffffu, nseg);
     u32 cur_q = 0xFFu, leaf = NONE, inner = NONE;
     int rrx = 0, rry = 0, rrz = 0;
-    bool have_root = false;
+    bool have_root = false, own = true;
     for (u32 sgi = 0; sgi < nmax; ++sgi) {
       if (sgi < nseg) {
         const u32 key = s_key[sgi][threadIdx.x];
@@ -385,25 +429,21 @@ __global__ void __launch_bounds__(TPB) k_mark(GridDev g, ScanParams p, ScanBuffe
           cur_q = q;
           const int lx = lx0 + ((q & 1u) ? sx : 0), ly = ly0 + ((q & 2u) ? sy : 0), lz = lz0 + ((q & 4u) ? sz : 0);
           const int rx = lx >> 2, ry = ly >> 2, rz = lz >> 2;
-          if (!have_root || rx != rrx || ry != rry || rz != rrz) {
-            inner = root_find(g, rx << 5, ry << 5, rz << 5);
-            if (inner == NONE) inner = root_find_or_insert(g, rx << 5, ry << 5, rz << 5);
+          const bool new_root = !have_root || rx != rrx || ry != rry || rz != rrz;
+          if (new_root) {
             rrx = rx;
             rry = ry;
             rrz = rz;
             have_root = true;
+            if (SHARD) own = shard_owner(rx, ry, rz, p.world) == p.rank;
           }
-          leaf = inner == NONE ? NONE : leaf_in_inner_or_create(g, inner, lx << 3, ly << 3, lz << 3);
+          leaf = (!SHARD || own) ? mark_leaf(g, inner, new_root, lx, ly, lz) : mark_leaf(gs, inner, new_root, lx, ly, lz);
         }
         if (leaf != NONE) {
-          unsigned long long* t = reinterpret_cast<unsigned long long*>(leaf_touched(g, leaf)) + w;
-          // test first (a stale L1 line only costs a redundant atomic): the leaves around the sensor are hit by every ray
-          if ((*t & bits) != bits) {
-            const unsigned long long old = atomicOr(t, bits);
-            if (old == 0ull && atomicExch(leaf_stamp(g, leaf), p.seq) != p.seq) {
-              const u32 at = atomicAdd(&b.sc->n_touched, 1u);
-              if (at < p.touched_cap) b.touched[at] = leaf;
-            }
+          if (!SHARD || own) {
+            mark_bits(g, leaf, w, bits, p.seq, &b.sc->n_touched, b.touched, p.touched_cap);
+          } else {
+            mark_bits(gs, leaf, w, bits, p.seq, &b.sc->n_touched2, b.touched2, p.touched2_cap);
           }
         }
       }
@@ -426,6 +466,7 @@ __global__ void __launch_bounds__(TPB) k_clear_touched(GridDev g, ScanBuffers b,
 // addHitPoint / addMissPoint on the winning endpoint voxels, probabilistic_map.cpp:30-54
 __global__ void __launch_bounds__(TPB) k_apply_endpoints(GridDev g, ScanParams p, ScanBuffers b) {
   if (g.ctr->error | b.sc->overflow) return;
+  if (b.gate && (b.gate[0] | b.gate[1])) return;  // some rank of a sharded map must repeat the scan
   const u32 n = b.sc->n_endpoints;
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint2 rec = b.ends[i];
@@ -447,6 +488,7 @@ __global__ void __launch_bounds__(TPB) k_apply_leaves(GridDev g, ScanParams p, S
   // last kernel of the scan: the host reads counters + grid counters with one copy
   if (blockIdx.x == 0 && threadIdx.x == 0) b.sc->gc = *g.ctr;
   if (g.ctr->error | b.sc->overflow) return;
+  if (b.gate && (b.gate[0] | b.gate[1])) return;
   const u32 n = min(b.sc->n_touched, p.touched_cap);
   const u32 lane = threadIdx.x & 31;
   const u32 warps = gridDim.x * (TPB / 32);
@@ -489,6 +531,103 @@ __global__ void __launch_bounds__(TPB) k_apply_leaves(GridDev g, ScanParams p, S
   }
   for (int o = 16; o; o >>= 1) changed += __shfl_xor_sync(0xffffffffu, changed, o);
   if (lane == 0 && changed) atomicAdd(&b.sc->n_changed, changed);
+}
+
+// ------------------------------------------------------------------------------------------------
+// sharded map: staging kernels around the two exchanges
+// ------------------------------------------------------------------------------------------------
+// exchange 1, sender: every locally winning endpoint goes to the rank that owns its root:
+// record = {x, y, z, global point index << 1 | type}; slot 0 of a peer block carries the count
+__global__ void __launch_bounds__(TPB) k_shard_bucket(ScanParams p, ScanBuffers b, u32 index_base, int4* send, u32 cap) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n) return;
+  if (b.table[b.slot_of[i]] != ~i) return;  // not the lowest local index of its voxel
+  const int4 e = b.ep[i];
+  const u32 o = shard_owner(e.x >> 5, e.y >> 5, e.z >> 5, p.world);
+  int4* block = send + (size_t)o * cap;
+  const u32 at = atomicAdd(reinterpret_cast<u32*>(&block[0].x), 1u) + 1u;
+  if (at < cap) {
+    block[at] = make_int4(e.x, e.y, e.z, (int)(((index_base + i) << 1) | (u32)e.w));
+  } else {
+    atomicOr(&b.sc->overflow, OVF_RECORDS);
+  }
+}
+
+// exchange 1, receiver: lowest global index per endpoint voxel over the records of all ranks
+__global__ void __launch_bounds__(TPB) k_shard_dedupe(ScanParams p, ScanBuffers b, u32 count) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const u32 j = i % p.rec_cap;
+  if (j == 0u || j > (u32)b.recs[i - j].x) return;
+  const int4 e = b.recs[i];
+  const unsigned long long key = pack_key(e);
+  u32 slot = (u32)hash3(e.x, e.y, e.z) & p.hash_mask;
+  for (;;) {
+    unsigned long long k = b.keys[slot];
+    if (k == 0ull) k = atomicCAS(&b.keys[slot], 0ull, key);
+    if (k == 0ull || k == key) break;
+    slot = (slot + 1) & p.hash_mask;
+  }
+  atomicMax(&b.table[slot], ~(u32)e.w);
+  b.slot_of[i] = slot;
+}
+
+// exchange 2, sender: one warp per scratch leaf touched in this scan -> {leaf origin, 512-bit mask} to the owner
+// of its root; the scratch mask is cleared for the next scan. Record = 5 x int4 (80 B).
+__global__ void __launch_bounds__(TPB) k_shard_emit(GridDev gs, ScanParams p, ScanBuffers b, int4* send, u32 cap) {
+  const u32 n = min(b.sc->n_touched2, p.touched2_cap);
+  const u32 lane = threadIdx.x & 31;
+  const u32 warps = gridDim.x * (TPB / 32);
+  for (u32 t = blockIdx.x * (TPB / 32) + (threadIdx.x >> 5); t < n; t += warps) {
+    const u32 leaf = b.touched2[t];
+    const int4 hdr = *reinterpret_cast<const int4*>(leaf_ptr(gs, leaf));
+    unsigned long long* touched = reinterpret_cast<unsigned long long*>(leaf_touched(gs, leaf));
+    const u32 o = shard_owner(hdr.x >> 5, hdr.y >> 5, hdr.z >> 5, p.world);
+    int4* block = send + (size_t)o * cap * 5;
+    u32 at = 0;
+    if (lane == 0) at = atomicAdd(reinterpret_cast<u32*>(&block[0].x), 1u) + 1u;
+    at = __shfl_sync(0xffffffffu, at, 0);
+    unsigned long long m = 0;
+    if (lane < 8) {
+      m = touched[lane];
+      touched[lane] = 0ull;
+    }
+    if (at < cap) {
+      if (lane == 0) block[(size_t)at * 5] = make_int4(hdr.x, hdr.y, hdr.z, 0);
+      if (lane < 8) reinterpret_cast<unsigned long long*>(block + (size_t)at * 5 + 1)[lane] = m;
+    } else if (lane == 0) {
+      atomicOr(&b.sc->overflow, OVF_LEAVES);
+    }
+  }
+}
+
+// exchange 2, receiver: OR the remote masks into this rank's leaves (one warp per record)
+__global__ void __launch_bounds__(TPB) k_shard_merge(GridDev g, ScanParams p, ScanBuffers b, const int4* recv, u32 cap) {
+  const u32 lane = threadIdx.x & 31;
+  const u32 warps = gridDim.x * (TPB / 32);
+  const u32 slots = p.world * cap;
+  for (u32 t = blockIdx.x * (TPB / 32) + (threadIdx.x >> 5); t < slots; t += warps) {
+    const u32 j = t % cap;
+    const int4* block = recv + (size_t)(t - j) * 5;
+    if (j == 0u || j > min((u32)block[0].x, cap - 1u)) continue;
+    const int4 hdr = block[(size_t)j * 5];
+    u32 leaf = NONE;
+    if (lane == 0) leaf = leaf_find_or_create(g, hdr.x, hdr.y, hdr.z);
+    leaf = __shfl_sync(0xffffffffu, leaf, 0);
+    if (leaf == NONE) continue;
+    if (lane < 8) {
+      const unsigned long long bits = reinterpret_cast<const unsigned long long*>(block + (size_t)j * 5 + 1)[lane];
+      if (bits) mark_bits(g, leaf, lane, bits, p.seq, &b.sc->n_touched, b.touched, p.touched_cap);
+    }
+  }
+}
+
+// flags of this rank for the all-reduce(MAX) that gates the apply phases on every rank
+__global__ void k_shard_flags(GridDev g, GridDev gs, ScanBuffers b, u32* flags) {
+  flags[0] = g.ctr->error | (gs.ctr->error << 8);
+  flags[1] = b.sc->overflow;
+  flags[2] = 0;
+  flags[3] = 0;
 }
 
 // public addHitPoint / addMissPoint (probabilistic_map.cpp:30-54): update now, queue the ray
@@ -539,6 +678,7 @@ __global__ void __launch_bounds__(TPB) k_query(GridDev g, const i32* __restrict_
 // ------------------------------------------------------------------------------------------------
 Map::~Map() {
   if (grid.stream()) cudaStreamSynchronize(grid.stream());
+  delete scratch_;
   if (h_status_) cudaFreeHost(h_status_);
   for (auto& e : ev_)
     if (e) cudaEventDestroy(e);
@@ -564,7 +704,7 @@ int Map::init(double resolution) {
   options[2] = logods_host(0.12f);
   options[3] = logods_host(0.97f);
   options[4] = logods_host(0.5f);
-  BNX_CUDA(cudaMallocHost(&h_status_, sizeof(ScanCounters)));
+  BNX_CUDA(cudaMallocHost(&h_status_, sizeof(ScanCounters) + 16));
   for (auto& e : ev_) BNX_CUDA(cudaEventCreate(&e));
   BNX_TRY(b_pending_.reserve(1024 * sizeof(int4)));
   buf_.pending = b_pending_.as<int4>();
@@ -692,10 +832,10 @@ int Map::run_scan(const void* d_points, i64 stride_bytes, bool f64, const ScanPa
     p.touched_cap = (u32)std::min<size_t>(b_touched_.bytes / 4, 0xFFFFFFFFull);
     const GridDev g = grid.dev();
     if (retries) BNX_CUDA(cudaMemsetAsync(d_sc_, 0, SC_BYTES, s));
-    if (n_pending_) note_launch(), k_resolve<true><<<blocks_for(n_pending_), TPB, 0, s>>>(g, p, buf_, n_pending_);
-    if (n > 0) note_launch(), k_resolve<false><<<blocks_for(n), TPB, 0, s>>>(g, p, buf_, (u32)n);
+    if (n_pending_) note_launch(), k_resolve<1><<<blocks_for(n_pending_), TPB, 0, s>>>(g, p, buf_, n_pending_);
+    if (n > 0) note_launch(), k_resolve<0><<<blocks_for(n), TPB, 0, s>>>(g, p, buf_, (u32)n);
     if (profiling && retries == 0) cudaEventRecord(ev_[3], s);
-    note_launch(), k_mark<<<persistent, TPB, 0, s>>>(g, p, buf_);
+    note_launch(), k_mark<false><<<persistent, TPB, 0, s>>>(g, g, p, buf_);
     if (profiling && retries == 0) cudaEventRecord(ev_[4], s);
     note_launch(), k_apply_endpoints<<<std::min(persistent, blocks_for(n + 1)), TPB, 0, s>>>(g, p, buf_);
     note_launch(), k_apply_leaves<<<persistent, TPB, 0, s>>>(g, p, buf_);
@@ -744,6 +884,190 @@ int Map::run_scan(const void* d_points, i64 stride_bytes, bool f64, const ScanPa
     cudaEventElapsedTime(&ms, ev_[0], ev_[5]);
     phase_us[5] = ms * 1e3;
   }
+  return grid.maintain(st.gc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// sharded map (one shard per process / GPU) — host side of the stages
+// ------------------------------------------------------------------------------------------------
+int Map::shard_config(int rank, int world) {
+  BNX_REQUIRE(world >= 1 && rank >= 0 && rank < world, "shard_config: bad rank/world");
+  rank_ = rank;
+  world_ = world;
+  if (world > 1 && !scratch_) {
+    scratch_ = new Grid();
+    const int st = scratch_->init(grid.resolution, 2, 3, 4);
+    if (st != BNX_OK) {
+      delete scratch_;
+      scratch_ = nullptr;
+      return st;
+    }
+  }
+  return BNX_OK;
+}
+
+int Map::shard_begin(const void* points, i64 stride_bytes, i64 n, bool f64, u32 index_base, const double origin[3], double max_range,
+                     void* send_records, i64 cap_records, int where) {
+  BNX_REQUIRE(world_ > 1 && scratch_, "shard_begin: call shard_config(rank, world > 1) first");
+  BNX_REQUIRE(n >= 0 && n < (1ll << 24) && (u64)index_base + (u64)n < (1ull << 31), "shard_begin: point count / index out of range");
+  BNX_REQUIRE(n_pending_ == 0, "shard_begin: addHitPoint/addMissPoint queues are not supported on a sharded map");
+  BNX_REQUIRE(origin && send_records && cap_records >= 2, "shard_begin: null argument");
+  BNX_REQUIRE(f64 ? (stride_bytes >= 24 && stride_bytes % 8 == 0) : (stride_bytes >= 12 && stride_bytes % 4 == 0), "shard_begin: bad stride");
+  cudaStream_t s = grid.stream();
+  scratch_->set_stream(s);
+  const i64 slots = (i64)world_ * cap_records;
+  BNX_TRY(reserve_scan(std::max<i64>(n, slots), stride_bytes, max_range));
+  const void* d_points = points;
+  if (where == BNX_HOST && n > 0) {
+    BNX_TRY(b_pts_.reserve((size_t)n * stride_bytes));
+    BNX_CUDA(cudaMemcpyAsync(b_pts_.p, points, (size_t)n * stride_bytes, cudaMemcpyHostToDevice, s));
+    d_points = b_pts_.p;
+  }
+  ScanParams p = {};
+  p.ox = origin[0];
+  p.oy = origin[1];
+  p.oz = origin[2];
+  p.max_range = max_range;
+  p.max_range_sqr = max_range * max_range;
+  p.inv_res = grid.inv_resolution;
+  p.Ox = (i32)std::floor(origin[0] * grid.inv_resolution);
+  p.Oy = (i32)std::floor(origin[1] * grid.inv_resolution);
+  p.Oz = (i32)std::floor(origin[2] * grid.inv_resolution);
+  p.miss = options[0];
+  p.hit = options[1];
+  p.cmin = options[2];
+  p.cmax = options[3];
+  p.c = update_count;
+  p.n = (u32)n;
+  p.rank = (u32)rank_;
+  p.world = (u32)world_;
+  p.rec_cap = (u32)cap_records;
+  p.max_chunks = (u32)std::min<u64>(((1ull << 40) - 1) / (u64)std::max<i64>(slots, 1), 1ull << 28);
+  const double reach = std::ceil(max_range * grid.inv_resolution) + 4.0, lim = (double)(1 << 20) - 1.0;
+  p.packed = std::isfinite(max_range) && max_range >= 0.0 && std::fabs((double)p.Ox) + reach < lim &&
+             std::fabs((double)p.Oy) + reach < lim && std::fabs((double)p.Oz) + reach < lim;
+  if (!p.packed) {
+    set_error("sharded insert needs a finite max_range and |voxel coordinates| < 2^20");
+    return BNX_ERR_UNSUPPORTED;
+  }
+  const u64 tslots = table_slots(std::max<i64>(n, slots));
+  p.hash_mask = (u32)(tslots - 1);
+  sp_ = p;
+  shard_retries_ = 0;
+  BNX_CUDA(cudaMemsetAsync(d_sc_, 0, SC_BYTES + tslots * 12, s));
+  BNX_CUDA(cudaMemset2DAsync(send_records, (size_t)cap_records * 16, 0, 16, (size_t)world_, s));  // block headers
+  if (n > 0) {
+    const unsigned char* pts = static_cast<const unsigned char*>(d_points);
+    const int blocks = blocks_for(n);
+    if (f64) {
+      launch_classify<true, false>(true, blocks, s, pts, (u32)stride_bytes, p, buf_);
+    } else if (stride_bytes == 16 && (reinterpret_cast<uintptr_t>(pts) & 15u) == 0) {
+      launch_classify<false, true>(true, blocks, s, pts, 16u, p, buf_);
+    } else {
+      launch_classify<false, false>(true, blocks, s, pts, (u32)stride_bytes, p, buf_);
+    }
+    note_launch(), k_shard_bucket<<<blocks, TPB, 0, s>>>(p, buf_, index_base, static_cast<int4*>(send_records), (u32)cap_records);
+    BNX_CUDA(cudaGetLastError());
+  }
+  return BNX_OK;
+}
+
+int Map::shard_resolve_mark(const void* recv_records, void* send_leaves, i64 cap_leaves) {
+  BNX_REQUIRE(world_ > 1 && scratch_ && recv_records && send_leaves && cap_leaves >= 2, "shard_resolve_mark: bad argument");
+  cudaStream_t s = grid.stream();
+  ScanParams& p = sp_;
+  const u32 slots = p.world * p.rec_cap;
+  const int persistent = sm_count() * 8;
+  BNX_TRY(b_touched_.reserve((size_t)grid.dev().leaf_cap * 4));
+  BNX_TRY(b_touched2_.reserve((size_t)scratch_->dev().leaf_cap * 4));
+  buf_.touched = b_touched_.as<u32>();
+  buf_.touched2 = b_touched2_.as<u32>();
+  buf_.recs = static_cast<const int4*>(recv_records);
+  buf_.gate = nullptr;
+  p.seq = ++seq_;
+  p.tile_cap = (u32)std::min<size_t>(b_tiles_.bytes / 4, 0xFFFFFFFFull);
+  p.touched_cap = (u32)std::min<size_t>(b_touched_.bytes / 4, 0xFFFFFFFFull);
+  p.touched2_cap = (u32)std::min<size_t>(b_touched2_.bytes / 4, 0xFFFFFFFFull);
+  p.leaf_cap2 = (u32)cap_leaves;
+  const u64 tslots = (u64)p.hash_mask + 1;
+  BNX_CUDA(cudaMemsetAsync(d_sc_, 0, SC_BYTES + tslots * 12, s));
+  BNX_CUDA(cudaMemset2DAsync(send_leaves, (size_t)cap_leaves * 80, 0, 16, (size_t)world_, s));
+  const GridDev g = grid.dev(), gs = scratch_->dev();
+  note_launch(), k_shard_dedupe<<<blocks_for(slots), TPB, 0, s>>>(p, buf_, slots);
+  note_launch(), k_resolve<2><<<blocks_for(slots), TPB, 0, s>>>(g, p, buf_, slots);
+  note_launch(), k_mark<true><<<persistent, TPB, 0, s>>>(g, gs, p, buf_);
+  note_launch(), k_shard_emit<<<persistent, TPB, 0, s>>>(gs, p, buf_, static_cast<int4*>(send_leaves), (u32)cap_leaves);
+  BNX_CUDA(cudaGetLastError());
+  return BNX_OK;
+}
+
+int Map::shard_merge(const void* recv_leaves, void* flags) {
+  BNX_REQUIRE(world_ > 1 && scratch_ && recv_leaves && flags, "shard_merge: bad argument");
+  cudaStream_t s = grid.stream();
+  const GridDev g = grid.dev(), gs = scratch_->dev();
+  note_launch(), k_shard_merge<<<sm_count() * 8, TPB, 0, s>>>(g, sp_, buf_, static_cast<const int4*>(recv_leaves), sp_.leaf_cap2);
+  note_launch(), k_shard_flags<<<1, 1, 0, s>>>(g, gs, buf_, static_cast<u32*>(flags));
+  BNX_CUDA(cudaGetLastError());
+  return BNX_OK;
+}
+
+int Map::shard_finish(const void* flags_reduced, int* retry) {
+  BNX_REQUIRE(world_ > 1 && scratch_ && flags_reduced && retry, "shard_finish: bad argument");
+  cudaStream_t s = grid.stream();
+  const int persistent = sm_count() * 8;
+  const GridDev g = grid.dev();
+  buf_.gate = static_cast<const u32*>(flags_reduced);
+  note_launch(), k_apply_endpoints<<<persistent, TPB, 0, s>>>(g, sp_, buf_);
+  note_launch(), k_apply_leaves<<<persistent, TPB, 0, s>>>(g, sp_, buf_);
+  BNX_CUDA(cudaGetLastError());
+  u32* h_flags = reinterpret_cast<u32*>(reinterpret_cast<unsigned char*>(h_status_) + sizeof(ScanCounters));
+  BNX_CUDA(cudaMemcpyAsync(h_status_, d_sc_, sizeof(ScanCounters), cudaMemcpyDeviceToHost, s));
+  BNX_CUDA(cudaMemcpyAsync(h_flags, flags_reduced, 16, cudaMemcpyDeviceToHost, s));
+  BNX_CUDA(cudaStreamSynchronize(s));
+  buf_.gate = nullptr;
+  const ScanCounters st = *h_status_;
+  const u32 any_pool = h_flags[0], any_ovf = h_flags[1];
+  *retry = 0;
+  if (any_pool | any_ovf) {
+    // some rank ran short: nobody applied. Every rank drops this attempt's marks; the short ones grow.
+    if (any_ovf & OVF_CHUNKS) {
+      set_error("insert: more than 2^32 ray chunks in one scan");
+      return BNX_ERR_UNSUPPORTED;
+    }
+    if (++shard_retries_ > 48) {
+      set_error("sharded insert: node pools could not be grown enough for this scan");
+      return BNX_ERR_NOMEM;
+    }
+    if (st.n_touched) {
+      note_launch(), k_clear_touched<<<persistent, TPB, 0, s>>>(g, buf_, std::min(st.n_touched, sp_.touched_cap));
+      BNX_CUDA(cudaGetLastError());
+      BNX_CUDA(cudaStreamSynchronize(s));
+    }
+    if (st.gc.error) BNX_TRY(grid.recover(st.gc));
+    GridCounters sgc;
+    BNX_TRY(scratch_->read_counters(&sgc));
+    if (sgc.error) BNX_TRY(scratch_->recover(sgc));
+    if (st.overflow & OVF_TILES) {
+      const u64 chunks = st.ray_chunk & CHUNK_FIELD;
+      BNX_TRY(b_tiles_.reserve((size_t)(chunks / 32 + 64) * 4));
+      buf_.tile_first = b_tiles_.as<u32>();
+    }
+    // bit 0: repeat from shard_resolve_mark; bits 8..: exchange buffers that were too small (caller grows them)
+    *retry = 1 | (int)((any_ovf & (OVF_RECORDS | OVF_LEAVES)) << 8);
+    return BNX_OK;
+  }
+  counters[0] = sp_.n;
+  counters[1] = st.n_endpoints;
+  counters[2] = (i64)st.sum_m;  // ray cells of the rays this rank cast; the caller adds N once over all ranks
+  counters[3] = (i64)st.n_endpoints + st.n_changed;
+  counters[4] = st.n_touched;
+  counters[5] = shard_retries_;
+  counters[6] = (i64)(st.ray_chunk >> 40);
+  counters[7] = (i64)(st.ray_chunk & CHUNK_FIELD);
+  if (++update_count == 4) update_count = 1;
+  GridCounters sgc;
+  BNX_TRY(scratch_->read_counters(&sgc));
+  BNX_TRY(scratch_->maintain(sgc));
   return grid.maintain(st.gc);
 }
 

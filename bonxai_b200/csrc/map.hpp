@@ -20,6 +20,10 @@ struct ScanParams {
   u32 touched_cap;             // entries of the touched-leaf list
   u32 max_chunks;              // per-ray chunk limit that keeps the packed (rays, chunks) counter exact
   u32 packed;                  // 1: dedupe table uses packed 64-bit keys (all endpoints fit 21 bits per axis)
+  u32 rank, world;             // map sharding: this process owns the roots with shard_owner(root) == rank
+  u32 rec_cap;                 // sharded: slots per peer block of the endpoint record exchange
+  u32 leaf_cap2;               // sharded: slots per peer block of the leaf-mask exchange
+  u32 touched2_cap;            // sharded: entries of the scratch-grid touched list
 };
 
 struct ScanCounters {
@@ -29,6 +33,8 @@ struct ScanCounters {
   u32 n_touched;                 // leaves on the touched list
   u32 n_changed;                 // cells changed by the free-space apply pass
   u32 overflow;                  // scan scratch overflow bits
+  u32 n_touched2;                // sharded: scratch-grid leaves touched (cells owned by other ranks)
+  u32 pad_;
   GridCounters gc;               // snapshot of the grid counters taken by the last kernel of the scan
 };
 
@@ -42,6 +48,9 @@ struct ScanBuffers {
   u32* tile_first;   // per 32-chunk tile: ray that owns the tile's first chunk
   u32* touched;      // leaves first touched in this scan
   int4* pending;     // queued addHitPoint/addMissPoint endpoints (xyz, type)
+  u32* touched2;     // sharded: scratch-grid leaves touched in this scan
+  const int4* recs;  // sharded: received endpoint records, [world][rec_cap], element 0 of a block = {count}
+  const u32* gate;   // sharded: all-reduced error flags; the apply kernels skip when any is set (NULL otherwise)
   ScanCounters* sc;
 };
 
@@ -53,6 +62,15 @@ class Map {
 
   int insert(const void* points, i64 stride_bytes, i64 n, bool f64, const double origin[3], double max_range, int where);
   int add_point(const double p[3], bool miss);
+
+  // ---- root-key sharding across processes (one map shard per GPU). The caller runs the two exchanges
+  // (all-to-all of the staged device buffers) between the stages; see bonxai_b200/sharded.py.
+  int shard_config(int rank, int world);
+  int shard_begin(const void* points, i64 stride_bytes, i64 n, bool f64, u32 index_base, const double origin[3], double max_range,
+                  void* send_records, i64 cap_records, int where);
+  int shard_resolve_mark(const void* recv_records, void* send_leaves, i64 cap_leaves);
+  int shard_merge(const void* recv_leaves, void* flags);
+  int shard_finish(const void* flags_reduced, int* retry);
   int query(const i32* xyz, i64 n, int kind, u8* out, int where);
 
   Grid grid;
@@ -71,6 +89,11 @@ class Map {
   ScanCounters* d_sc_ = nullptr;    // head of b_table_: counters + dedupe table are cleared by ONE memset
   ScanCounters* h_status_ = nullptr;  // pinned
   u32 n_pending_ = 0;
+  int rank_ = 0, world_ = 1;
+  Grid* scratch_ = nullptr;  // sharded: staging grid for cells whose root another rank owns (masks only)
+  ScanParams sp_ = {};       // sharded: parameters of the scan in flight
+  i64 shard_retries_ = 0;
+  DevBuf b_touched2_;
   u32 seq_ = 0;
   cudaEvent_t ev_[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };

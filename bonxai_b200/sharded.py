@@ -1,0 +1,197 @@
+"""One ProbabilisticMap sharded over several GPUs by root key.
+
+Each rank owns the roots with shard_owner(root) == rank and holds 1/world of every scan's points. The CUDA
+stages live behind the C ABI (bnx_map_shard_*); this module only moves the staged device buffers between ranks:
+
+    ShardedMap       one process per GPU, exchanges = torch.distributed (NCCL) all_to_all_single / all_reduce
+    LocalShardGroup  all shards in ONE process on one GPU, exchanges = block transposes on the device; used by
+                     the single-GPU tests to run the whole protocol (every kernel, every record format)
+
+Bit-exactness: the union of the shards' forEachCell dumps equals the unsharded map's dump after every scan.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+REC_WORDS = 4     # endpoint record: int4 {x, y, z, global index << 1 | type}
+LEAF_WORDS = 20   # leaf record: int4 {leaf origin xyz, 0} + u64 mask[8]
+
+
+def split_points(n: int, world: int):
+    """contiguous index ranges [lo, hi) per rank"""
+    bounds = [(n * r) // world for r in range(world + 1)]
+    return [(bounds[r], bounds[r + 1]) for r in range(world)]
+
+
+class _Shard:
+    """a ProbabilisticMap shard + its staging buffers (torch CUDA tensors)"""
+
+    def __init__(self, resolution: float, rank: int, world: int, device, cap_records: int = 1 << 15, cap_leaves: int = 1 << 13):
+        import torch
+        self.torch = torch
+        self.rank, self.world, self.device = rank, world, device
+        self.map = capi.ProbabilisticMap(resolution)
+        self.lib = self.map.lib
+        capi._check(self.lib.bnx_map_shard_config(self.map.h, rank, world))
+        self.cap_records, self.cap_leaves = 0, 0
+        self._alloc_records(cap_records)
+        self._alloc_leaves(cap_leaves)
+        self.flags = torch.zeros(4, dtype=torch.int32, device=device)
+        self.n_local = 0
+
+    def _alloc_records(self, cap):
+        t = self.torch
+        self.cap_records = int(cap)
+        self.send1 = t.empty((self.world, self.cap_records, REC_WORDS), dtype=t.int32, device=self.device)
+        self.recv1 = t.empty_like(self.send1)
+
+    def _alloc_leaves(self, cap):
+        t = self.torch
+        self.cap_leaves = int(cap)
+        self.send2 = t.empty((self.world, self.cap_leaves, LEAF_WORDS), dtype=t.int32, device=self.device)
+        self.recv2 = t.empty_like(self.send2)
+
+    def set_stream(self, stream: int):
+        self.map.set_stream(stream)
+
+    # ---- the four stages (bnx_map_shard_*)
+    def begin(self, pts, n, stride_bytes, f64, index_base, origin, max_range):
+        if n + 2 > self.cap_records:
+            self._alloc_records(max(n + 2, self.cap_records * 2))
+        o = np.ascontiguousarray(origin, dtype=np.float64)
+        if isinstance(pts, capi.DevPtr):
+            p, where = C.c_void_p(pts.address), capi.BNX_DEVICE
+        else:
+            arr = np.ascontiguousarray(pts)
+            p, where = C.c_void_p(arr.ctypes.data), capi.BNX_HOST
+        self.n_local = n
+        capi._check(self.lib.bnx_map_shard_begin(self.map.h, p, C.c_int64(stride_bytes), C.c_int64(n), int(bool(f64)), C.c_uint32(index_base),
+                                                 C.c_void_p(o.ctypes.data), C.c_double(max_range), C.c_void_p(self.send1.data_ptr()),
+                                                 C.c_int64(self.cap_records), where))
+
+    def resolve_mark(self):
+        capi._check(self.lib.bnx_map_shard_resolve_mark(self.map.h, C.c_void_p(self.recv1.data_ptr()), C.c_void_p(self.send2.data_ptr()),
+                                                        C.c_int64(self.cap_leaves)))
+
+    def merge(self):
+        capi._check(self.lib.bnx_map_shard_merge(self.map.h, C.c_void_p(self.recv2.data_ptr()), C.c_void_p(self.flags.data_ptr())))
+
+    def finish(self) -> int:
+        retry = C.c_int(0)
+        capi._check(self.lib.bnx_map_shard_finish(self.map.h, C.c_void_p(self.flags.data_ptr()), C.byref(retry)))
+        return retry.value
+
+    def grow_after(self, retry: int):
+        if retry & (4 << 8):   # OVF_RECORDS cannot happen: cap_records >= n_local + 2
+            raise RuntimeError("endpoint record exchange overflowed")
+        if retry & (8 << 8):
+            self._alloc_leaves(self.cap_leaves * 4)
+
+
+class ShardedMap:
+    """one rank of a map sharded over torch.distributed ranks (NCCL, one process per GPU)"""
+
+    def __init__(self, resolution: float, group=None, cap_leaves: int = 1 << 13):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.group = torch, dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        assert self.world > 1, "use capi.ProbabilisticMap for a single GPU"
+        self.shard = _Shard(resolution, self.rank, self.world, torch.device("cuda", torch.cuda.current_device()), cap_leaves=cap_leaves)
+        self.shard.set_stream(torch.cuda.current_stream().cuda_stream)
+        self.map = self.shard.map
+        self.attempts = 0
+
+    def insert(self, pts_local, n_local, stride_bytes, index_base, origin, max_range, f64=False):
+        """this rank's slice of the scan: points [index_base, index_base + n_local) of the global cloud"""
+        s, dist = self.shard, self.dist
+        n_max = self.torch.tensor([n_local], dtype=self.torch.int64, device=s.device)
+        if n_local + 2 > s.cap_records:  # keep record capacities equal on all ranks (equal-split all-to-all)
+            pass
+        dist.all_reduce(n_max, op=dist.ReduceOp.MAX, group=self.group)
+        need = int(n_max.item()) + 2
+        if need > s.cap_records:
+            s._alloc_records(max(need, s.cap_records * 2))
+        s.begin(pts_local, n_local, stride_bytes, f64, index_base, origin, max_range)
+        dist.all_to_all_single(s.recv1.view(-1), s.send1.view(-1), group=self.group)
+        while True:
+            self.attempts += 1
+            s.resolve_mark()
+            dist.all_to_all_single(s.recv2.view(-1), s.send2.view(-1), group=self.group)
+            s.merge()
+            dist.all_reduce(s.flags, op=dist.ReduceOp.MAX, group=self.group)
+            retry = s.finish()
+            if not retry:
+                return
+            s.grow_after(retry)  # the flags are all-reduced: every rank takes the same branch
+
+    def counters(self):
+        return self.map.counters()
+
+
+class LocalShardGroup:
+    """all `world` shards of one map inside ONE process on one GPU: the exchanges are device-side block
+    transposes. Same stages, kernels and record formats as ShardedMap; no NCCL needed."""
+
+    def __init__(self, resolution: float, world: int, device="cuda:0", cap_leaves: int = 1 << 13):
+        import torch
+        self.torch = torch
+        self.world = world
+        self.shards = [_Shard(resolution, r, world, torch.device(device), cap_leaves=cap_leaves) for r in range(world)]
+        stream = torch.cuda.current_stream().cuda_stream
+        for s in self.shards:
+            s.set_stream(stream)
+        self.attempts = 0
+
+    def insert(self, pts: np.ndarray, origin, max_range):
+        pts = np.ascontiguousarray(pts)
+        f64 = pts.dtype == np.float64
+        stride = pts.shape[1] * pts.dtype.itemsize
+        parts = split_points(len(pts), self.world)
+        need = max(hi - lo for lo, hi in parts) + 2
+        for s in self.shards:
+            if need > s.cap_records:
+                s._alloc_records(max(need, s.cap_records * 2))
+        for s, (lo, hi) in zip(self.shards, parts):
+            s.begin(pts[lo:hi], hi - lo, stride, f64, lo, origin, max_range)
+        self._exchange("send1", "recv1")
+        while True:
+            self.attempts += 1
+            for s in self.shards:
+                s.resolve_mark()
+            self._exchange("send2", "recv2")
+            for s in self.shards:
+                s.merge()
+            flags = self.torch.stack([s.flags for s in self.shards]).max(dim=0).values
+            for s in self.shards:
+                s.flags.copy_(flags)
+            retries = [s.finish() for s in self.shards]
+            assert len(set(retries)) == 1
+            if not retries[0]:
+                return
+            for s in self.shards:
+                s.grow_after(retries[0])
+
+    def _exchange(self, send, recv):
+        # all-to-all: block o of rank r's send buffer becomes block r of rank o's receive buffer
+        for r, s in enumerate(self.shards):
+            for o, d in enumerate(self.shards):
+                getattr(d, recv)[r].copy_(getattr(s, send)[o])
+
+    def dump(self, sort=True):
+        xs, ws = zip(*[s.map.dump(sort=False) for s in self.shards])
+        xyz, w = np.concatenate(xs), np.concatenate(ws)
+        if sort and len(xyz):
+            order = np.lexsort((xyz[:, 2], xyz[:, 1], xyz[:, 0]))
+            xyz, w = xyz[order], w[order]
+        return xyz, w
+
+    def counters(self):
+        cs = [s.map.counters() for s in self.shards]
+        n = sum(c["N"] for c in cs)
+        return dict(N=n, E=sum(c["E"] for c in cs), V=sum(c["V"] for c in cs) + n, U=sum(c["U"] for c in cs),
+                    retries=max(c["retries"] for c in cs))

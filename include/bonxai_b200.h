@@ -69,7 +69,10 @@ BNX_API int bnx_host_free(void* ptr);
  * The grid lives on the calling thread's current CUDA device. */
 BNX_API int bnx_grid_create(double voxel_size, int inner_bits, int leaf_bits, int cell_bytes, bnx_grid_t** out);
 BNX_API int bnx_grid_destroy(bnx_grid_t* g);
-/* cudaStream_t to enqueue on (NULL = the grid's own stream) */
+/* cudaStream_t to enqueue on. Any stream handle is taken as is — including 0, the legacy default stream
+ * (what torch.cuda.current_stream().cuda_stream returns by default); BNX_OWN_STREAM goes back to the handle's
+ * private non-blocking stream, which is what a new grid/map uses. */
+#define BNX_OWN_STREAM ((void*)~(uintptr_t)0)
 BNX_API int bnx_grid_set_stream(bnx_grid_t* g, void* cuda_stream);
 BNX_API int bnx_grid_sync(bnx_grid_t* g);
 /* innetBits()/leafBits()/voxelSize(), bonxai.hpp:146-154 */
@@ -172,6 +175,32 @@ BNX_API int bnx_map_update_count(const bnx_map_t* m, int* value);
  * bnx_map_set_profiling(m,1)): {h2d, classify, resolve, mark, apply, total, 0, 0} */
 BNX_API int bnx_map_set_profiling(bnx_map_t* m, int enable);
 BNX_API int bnx_map_phase_times(bnx_map_t* m, double out_us[8]);
+
+/* ------------------------------------------------------------------------------------------------
+ * One map sharded over several GPUs (one process per GPU): roots are owned by hash(root key) mod world,
+ * every rank holds 1/world of a scan's points. insertPointCloud becomes four stages with two exchanges the
+ * CALLER performs on the staged device buffers (NCCL all-to-all, see bonxai_b200/sharded.py and DESIGN.md §7):
+ *
+ *   shard_begin         classify + local dedupe; endpoint records bucketed by owner -> send_records
+ *        exchange 1:    all-to-all of [world][cap_records] x 16-B records (slot 0 of a block = count)
+ *   shard_resolve_mark  owner: lowest global index per voxel, stale test, rays; ray cells of foreign roots are
+ *                       staged as {leaf origin, 512-bit mask} records -> send_leaves
+ *        exchange 2:    all-to-all of [world][cap_leaves] x 80-B records
+ *   shard_merge         owner: OR the received masks into its leaves; writes this rank's error flags
+ *        all-reduce(MAX) of the 4 x u32 flags
+ *   shard_finish        apply (skipped everywhere if any rank ran short); *retry != 0 -> repeat from
+ *                       shard_resolve_mark with the same recv_records (bits 8.. say which exchange buffer to grow)
+ *
+ * All buffers are device memory on the map's stream. The union of the shards equals the unsharded map bit for
+ * bit. Needs a finite max_range; addHitPoint/addMissPoint queues are not supported on a sharded map.
+ * ---------------------------------------------------------------------------------------------- */
+BNX_API int bnx_map_shard_config(bnx_map_t* m, int rank, int world);
+BNX_API int bnx_map_shard_begin(bnx_map_t* m, const void* points, int64_t stride_bytes, int64_t n, int is_f64,
+                                uint32_t index_base, const double origin[3], double max_range, void* send_records,
+                                int64_t cap_records, int where);
+BNX_API int bnx_map_shard_resolve_mark(bnx_map_t* m, const void* recv_records, void* send_leaves, int64_t cap_leaves);
+BNX_API int bnx_map_shard_merge(bnx_map_t* m, const void* recv_leaves, void* flags);
+BNX_API int bnx_map_shard_finish(bnx_map_t* m, const void* flags_reduced, int* retry);
 
 #ifdef __cplusplus
 }

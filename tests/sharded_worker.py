@@ -1,0 +1,48 @@
+"""torchrun worker for tests/test_gpu_sharded.py::test_nccl_two_ranks (and manual N-GPU checks):
+every rank inserts its slice of each scan into a root-key-sharded map over NCCL; rank 0 gathers the shard dumps
+and compares their union with the CPU oracle."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from bonxai_b200 import capi, synth  # noqa: E402
+from bonxai_b200.sharded import ShardedMap, split_points  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    sm = ShardedMap(0.1)
+    if rank == 0:
+        import oracle
+        om = oracle.load("port").map(0.1)
+    for scan in range(3):
+        pts, origin = synth.lidar_scan(scan * 2, beams=32, azimuths=1024)
+        lo, hi = split_points(len(pts), world)[rank]
+        dev = torch.from_numpy(pts[lo:hi]).cuda()
+        sm.insert(capi.DevPtr(dev.data_ptr()), hi - lo, 16, lo, origin, 40.0)
+        xyz, w = sm.map.dump(sort=False)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (xyz, w))
+        if rank == 0:
+            om.insert(pts, origin, 40.0)
+            gx = np.concatenate([g[0] for g in gathered])
+            gw = np.concatenate([g[1] for g in gathered])
+            order = np.lexsort((gx[:, 2], gx[:, 1], gx[:, 0]))
+            ox, ow = om.dump()
+            assert np.array_equal(gx[order], ox) and np.array_equal(gw[order], ow), f"scan {scan}: sharded map differs from the oracle"
+    dist.barrier()
+    if rank == 0:
+        print("SHARDED_OK", world)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,71 @@
+"""Row (e): one map sharded by root key over several ranks. The union of the shards must equal the unsharded
+map (== the oracle) after every scan. LocalShardGroup runs every rank's CUDA stages in one process on one GPU
+(exchanges = device block transposes); the NCCL flavour is exercised by test_nccl_two_ranks on >= 2 GPUs."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from bonxai_b200 import synth
+from conftest import assert_same_dump
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_local_shard_group_equals_oracle(bnx, port, world):
+    from bonxai_b200.sharded import LocalShardGroup
+    g, om = LocalShardGroup(0.1, world), port.map(0.1)
+    for scan in range(4):
+        pts, origin = synth.lidar_scan(scan * 3, beams=32, azimuths=1024)
+        g.insert(pts, origin, 40.0)
+        om.insert(pts, origin, 40.0)
+        assert_same_dump(g.dump(), om.dump(), f"world {world} scan {scan}")
+        gc, oc = g.counters(), om.counters()
+        assert (gc["N"], gc["E"], gc["V"], gc["U"]) == (oc["N"], oc["E"], oc["V"], oc["U"]), (gc, oc)
+    # every rank holds only cells whose root it owns: the shards are disjoint
+    sizes = [s.map.active_count() for s in g.shards]
+    assert sum(sizes) == om.active_count() and min(sizes) > 0
+
+
+def test_local_shard_group_random_and_stale(bnx, port):
+    from bonxai_b200.sharded import LocalShardGroup
+    rng = np.random.default_rng(3)
+    g, om = LocalShardGroup(0.05, 4), port.map(0.05)
+    a = (rng.normal(0, 2.0, (3000, 3))).astype(np.float32)
+    b = (rng.normal(0, 2.0, (2500, 3)) + [0.5, 0, 0]).astype(np.float32)
+    a[:400] = a[0]  # duplicates split across ranks: the lowest GLOBAL index must win
+    for k, pts in enumerate([a, b, b, a, a, b]):  # a returns when update_id has wrapped: stale endpoints cast no ray
+        o = np.float32([0.1 * k, 0.0, 0.05])
+        g.insert(pts, o, 3.0)
+        om.insert(pts, o, 3.0)
+        assert_same_dump(g.dump(), om.dump(), f"scan {k}")
+    f64 = rng.normal(0, 1.5, (2000, 3))
+    g.insert(f64, [0.0, 0.0, 0.0], 2.0)
+    om.insert(f64, [0.0, 0.0, 0.0], 2.0)
+    assert_same_dump(g.dump(), om.dump(), "f64 scan")
+
+
+def test_local_shard_group_growth_and_small_exchange_buffers(bnx, port, monkeypatch):
+    monkeypatch.setenv("BNX_INIT_LEAF_MB", "1")
+    monkeypatch.setenv("BNX_INIT_INNER_MB", "0")
+    from bonxai_b200.sharded import LocalShardGroup
+    g, om = LocalShardGroup(0.1, 2, cap_leaves=64), port.map(0.1)
+    for scan in range(2):
+        pts, origin = synth.lidar_scan(scan, beams=32, azimuths=1024)
+        g.insert(pts, origin, 40.0)
+        om.insert(pts, origin, 40.0)
+        assert_same_dump(g.dump(), om.dump(), f"growth scan {scan}")
+    assert g.attempts > 2  # pools and the leaf exchange buffer had to grow
+
+
+def test_nccl_two_ranks(bnx):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29611", os.path.join(ROOT, "tests", "sharded_worker.py")], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "SHARDED_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
