@@ -93,8 +93,10 @@ def _street_boxes(x_center: float, seed: int):
 
 
 def lidar_scan(scan: int, beams: int = 64, azimuths: int = 2048, seed: int = 7, speed: float = 1.0,
-               stride4: bool = True, path: str = "line"):
-    """One 64x2048 scan (131,072 points). Returns (points float32 (n,4|3), origin float32 (3,))."""
+               stride4: bool = True, path: str = "line", index_range=None):
+    """One beams x azimuths scan (131,072 points by default), beam-major point order.
+    Returns (points float32 (n,4|3), origin float32 (3,)). index_range=(lo, hi) generates only the points
+    [lo, hi) of the scan (every point depends on its own index only), e.g. one rank's slice."""
     if path == "line":
         ox, oy, yaw = speed * scan, 0.0, 0.0
     else:  # serpentine city path for the multi-GPU config: long parallel streets 60 m apart
@@ -106,11 +108,12 @@ def lidar_scan(scan: int, beams: int = 64, azimuths: int = 2048, seed: int = 7, 
         oy = 60.0 * k
         yaw = 0.0 if k % 2 == 0 else np.pi
     o = np.array([ox, oy, 1.8])
-    el = np.deg2rad(np.linspace(-24.8, 2.0, beams))
-    az = yaw + np.arange(azimuths) * (2.0 * np.pi / azimuths)
-    ce, se = np.cos(el)[:, None], np.sin(el)[:, None]
-    d = np.stack([ce * np.cos(az)[None, :], ce * np.sin(az)[None, :], np.broadcast_to(se, (beams, azimuths))],
-                 axis=2).reshape(-1, 3)
+    lo, hi = (0, beams * azimuths) if index_range is None else index_range
+    idx = np.arange(lo, hi, dtype=np.int64)
+    el = np.deg2rad(np.linspace(-24.8, 2.0, beams))[idx // azimuths]
+    az = yaw + (idx % azimuths) * (2.0 * np.pi / azimuths)
+    ce, se = np.cos(el), np.sin(el)
+    d = np.stack([ce * np.cos(az), ce * np.sin(az), se], axis=1)
     n = d.shape[0]
     t = np.full(n, 120.0)  # no return -> beyond max_range -> truncated miss ray
     with np.errstate(divide="ignore", invalid="ignore"):
@@ -120,9 +123,9 @@ def lidar_scan(scan: int, beams: int = 64, azimuths: int = 2048, seed: int = 7, 
     wall_z = o[2] + tw * d[:, 2]
     tw = np.where((tw > 0) & (wall_z >= 0.0) & (wall_z <= 12.0), tw, np.inf)
     t = np.minimum(t, np.minimum(tg, tw))
-    boxes = [(lo + np.array([0.0, oy, 0.0]), hi + np.array([0.0, oy, 0.0])) for lo, hi in _street_boxes(ox, seed)]
+    boxes = [(b0 + np.array([0.0, oy, 0.0]), b1 + np.array([0.0, oy, 0.0])) for b0, b1 in _street_boxes(ox, seed)]
     t = _ray_enter_boxes(o, d, boxes, t)
-    noise = uniform01(seed, 1 + scan, np.arange(n)) * 0.04 - 0.02
+    noise = uniform01(seed, 1 + scan, idx) * 0.04 - 0.02
     t = np.where(t < 120.0, t + noise, t)
     p = (o[None, :] + d * t[:, None]).astype(np.float32)
     if stride4:
