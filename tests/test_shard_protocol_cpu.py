@@ -1,0 +1,27 @@
+"""CPU suite, N > 1 path: the sharded-map protocol (two exchanges, owner-side verdicts, apply order) run as a
+numpy model over torch.distributed/gloo with 2 and 3 processes, checked against the oracle after every scan."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("world,port", [(2, 29711), (3, 29712)])
+def test_shard_protocol_model_over_gloo(world, port):
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), os.path.join(ROOT, "tests", "shard_model.py")], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and f"SHARD_MODEL_OK {world}" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
+
+
+def test_split_points_covers_every_index_once():
+    from bonxai_b200.sharded import split_points
+    for n in (0, 1, 7, 131072, 1_024_000):
+        for world in (1, 2, 3, 8):
+            parts = split_points(n, world)
+            assert parts[0][0] == 0 and parts[-1][1] == n and all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+            assert max(h - l for l, h in parts) - min(h - l for l, h in parts) <= 1
