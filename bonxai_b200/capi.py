@@ -35,6 +35,7 @@ SYMBOLS = [
     "bnx_map_get_options", "bnx_map_insert_f32", "bnx_map_insert_f64", "bnx_map_add_hit", "bnx_map_add_miss",
     "bnx_map_query", "bnx_map_get_voxels", "bnx_map_get_voxel_points", "bnx_map_counters", "bnx_map_update_count",
     "bnx_map_set_profiling", "bnx_map_phase_times",
+    "bnx_map_insert_async_f32", "bnx_map_insert_async_f64", "bnx_map_totals",
     "bnx_map_shard_config", "bnx_map_shard_begin", "bnx_map_shard_resolve_mark", "bnx_map_shard_merge", "bnx_map_shard_finish",
 ]
 
@@ -331,6 +332,26 @@ class ProbabilisticMap:
         else:
             o = np.ascontiguousarray(origin, dtype=np.float32)
             _check(self.lib.bnx_map_insert_f32(self.h, p, C.c_int64(stride_bytes), C.c_int64(n), C.c_void_p(o.ctypes.data), C.c_double(max_range), where))
+
+    def insert_async(self, pts, origin, max_range, n=None, stride_bytes=None, f64=False):
+        """pipelined insertPointCloud: enqueue and return. The buffer behind `pts` must stay alive until sync()."""
+        if isinstance(pts, DevPtr):
+            p, where = C.c_void_p(pts.address), BNX_DEVICE
+        else:
+            assert pts.flags["C_CONTIGUOUS"] and pts.ndim == 2, "pass the array itself (no temporary copies): it must outlive the call"
+            f64 = pts.dtype == np.float64
+            p, where, n, stride_bytes = C.c_void_p(pts.ctypes.data), BNX_HOST, len(pts), pts.shape[1] * pts.dtype.itemsize
+        if f64:
+            o = np.ascontiguousarray(origin, dtype=np.float64)
+            _check(self.lib.bnx_map_insert_async_f64(self.h, p, C.c_int64(stride_bytes), C.c_int64(n), C.c_void_p(o.ctypes.data), C.c_double(max_range), where))
+        else:
+            o = np.ascontiguousarray(origin, dtype=np.float32)
+            _check(self.lib.bnx_map_insert_async_f32(self.h, p, C.c_int64(stride_bytes), C.c_int64(n), C.c_void_p(o.ctypes.data), C.c_double(max_range), where))
+
+    def totals(self):
+        a = (C.c_int64 * 4)()
+        _check(self.lib.bnx_map_totals(self.h, a))
+        return dict(N=a[0], E=a[1], V=a[2], U=a[3])
 
     def add_hit(self, p):
         a = np.ascontiguousarray(p, dtype=np.float64)

@@ -10,6 +10,7 @@ using namespace bnx;
 struct bnx_grid {
   Grid* g;
   bool owned;  // false for the grid borrowed from a map
+  Map* map;    // that map: its pipelined scans are completed before the grid is touched
 };
 struct bnx_map {
   Map m;
@@ -82,7 +83,7 @@ int bnx_grid_create(double voxel_size, int inner_bits, int leaf_bits, int cell_b
     delete g;
     return s;
   }
-  *out = new bnx_grid{g, true};
+  *out = new bnx_grid{g, true, nullptr};
   return BNX_OK;
 }
 
@@ -119,9 +120,10 @@ int bnx_grid_info(const bnx_grid_t* h, double* voxel_size, int* inner_bits, int*
   return BNX_OK;
 }
 
-#define GRID_CALL(h, expr)        \
-  BNX_HANDLE(h);                  \
-  DeviceGuard dg((h)->g->device); \
+#define GRID_CALL(h, expr)                       \
+  BNX_HANDLE(h);                                 \
+  DeviceGuard dg((h)->g->device);                \
+  if ((h)->map) BNX_TRY((h)->map->drain());      \
   return (h)->g->expr
 
 int bnx_grid_pos_to_coord(const bnx_grid_t* h, const double* xyz, int64_t n, int32_t* out, int where) {
@@ -167,7 +169,7 @@ int bnx_grid_deserialize(const uint8_t* data, int64_t len, int cell_bytes, const
   *out = nullptr;
   Grid* g = nullptr;
   BNX_TRY(Grid::deserialize(data, len, cell_bytes, expect_type_name, &g));
-  *out = new bnx_grid{g, true};
+  *out = new bnx_grid{g, true, nullptr};
   return BNX_OK;
 }
 
@@ -184,6 +186,7 @@ int bnx_map_create(double resolution, bnx_map_t** out) {
   }
   h->grid_handle.g = &h->m.grid;
   h->grid_handle.owned = false;
+  h->grid_handle.map = &h->m;
   *out = h;
   return BNX_OK;
 }
@@ -203,6 +206,7 @@ int bnx_map_set_stream(bnx_map_t* h, void* stream) {
 int bnx_map_sync(bnx_map_t* h) {
   BNX_HANDLE(h);
   DeviceGuard dg(h->m.grid.device);
+  BNX_TRY(h->m.drain());
   return h->m.grid.sync();
 }
 int bnx_map_grid(bnx_map_t* h, bnx_grid_t** grid) {
@@ -238,6 +242,27 @@ int bnx_map_insert_f64(bnx_map_t* h, const void* points, int64_t stride_bytes, i
   DeviceGuard dg(h->m.grid.device);
   return h->m.insert(points, stride_bytes, n, true, origin, max_range, where);
 }
+int bnx_map_insert_async_f32(bnx_map_t* h, const void* points, int64_t stride_bytes, int64_t n, const float origin[3], double max_range,
+                             int where) {
+  BNX_HANDLE(h);
+  BNX_REQUIRE(origin != nullptr, "null origin");
+  DeviceGuard dg(h->m.grid.device);
+  const double o[3] = {(double)origin[0], (double)origin[1], (double)origin[2]};
+  return h->m.insert_async(points, stride_bytes, n, false, o, max_range, where);
+}
+int bnx_map_insert_async_f64(bnx_map_t* h, const void* points, int64_t stride_bytes, int64_t n, const double origin[3], double max_range,
+                             int where) {
+  BNX_HANDLE(h);
+  DeviceGuard dg(h->m.grid.device);
+  return h->m.insert_async(points, stride_bytes, n, true, origin, max_range, where);
+}
+int bnx_map_totals(bnx_map_t* h, int64_t out[4]) {
+  BNX_HANDLE(h);
+  DeviceGuard dg(h->m.grid.device);
+  BNX_TRY(h->m.drain());
+  std::memcpy(out, h->m.totals, sizeof(int64_t) * 4);
+  return BNX_OK;
+}
 int bnx_map_add_hit(bnx_map_t* h, const double point[3]) {
   BNX_HANDLE(h);
   BNX_REQUIRE(point != nullptr, "null point");
@@ -257,12 +282,14 @@ int bnx_map_query(bnx_map_t* h, const int32_t* xyz, int64_t n, int kind, uint8_t
 }
 int bnx_map_get_voxels(bnx_map_t* h, int kind, int32_t* xyz, int64_t cap, int64_t* count, int where) {
   BNX_HANDLE(h);
+  BNX_TRY(h->m.drain());
   BNX_REQUIRE(kind == BNX_OCCUPIED || kind == BNX_FREE, "get_voxels: kind must be BNX_OCCUPIED or BNX_FREE");
   DeviceGuard dg(h->m.grid.device);
   return h->m.grid.dump(xyz, nullptr, nullptr, cap, count, where, kind, h->m.options[4]);
 }
 int bnx_map_get_voxel_points(bnx_map_t* h, int kind, double* xyz, int64_t cap, int64_t* count, int where) {
   BNX_HANDLE(h);
+  BNX_TRY(h->m.drain());
   BNX_REQUIRE(kind == BNX_OCCUPIED || kind == BNX_FREE, "get_voxel_points: kind must be BNX_OCCUPIED or BNX_FREE");
   DeviceGuard dg(h->m.grid.device);
   return h->m.grid.dump(nullptr, xyz, nullptr, cap, count, where, kind, h->m.options[4]);
@@ -295,6 +322,7 @@ int bnx_map_shard_finish(bnx_map_t* h, const void* flags_reduced, int* retry) {
 }
 int bnx_map_counters(bnx_map_t* h, int64_t out[8]) {
   BNX_HANDLE(h);
+  BNX_TRY(h->m.drain());
   std::memcpy(out, h->m.counters, sizeof(int64_t) * 8);
   return BNX_OK;
 }

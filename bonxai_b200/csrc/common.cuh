@@ -65,6 +65,7 @@ enum : u32 {
   ERR_INNER_POOL = 2u,  // inner-node pool exhausted
   ERR_ROOT_TABLE = 4u,  // root hash table full
   ERR_RAY_LIST = 8u,    // scan scratch overflow (should not happen: sized from n)
+  ERR_SCAN = 16u,       // async pipeline: a scan's scratch lists overflowed; sticky until the host recovers
 };
 
 }  // namespace bnx

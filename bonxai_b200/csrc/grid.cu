@@ -491,8 +491,11 @@ int Grid::init(double voxel_size, int ib, int lb, int cbytes) {
   BNX_TRY(leaf_arena_.init(total_b));
   BNX_TRY(inner_arena_.init(std::max<size_t>(total_b / 4, 1ull << 30)));
   BNX_CUDA(cudaMalloc(&d_ctr_, sizeof(GridCounters)));
-  BNX_CUDA(cudaMemsetAsync(d_ctr_, 0, sizeof(GridCounters), stream_));
   BNX_CUDA(cudaMallocHost(&h_ctr_, sizeof(GridCounters)));
+  std::memset(h_ctr_, 0, sizeof(GridCounters));
+  h_ctr_->failed_id = NONE;
+  BNX_CUDA(cudaMemcpyAsync(d_ctr_, h_ctr_, sizeof(GridCounters), cudaMemcpyHostToDevice, stream_));
+  BNX_CUDA(cudaStreamSynchronize(stream_));
   BNX_CUDA(cudaMalloc(&d_count_, 64));
   BNX_CUDA(cudaMallocHost(&h_count_, 64));
   d.ctr = d_ctr_;
@@ -558,6 +561,8 @@ int Grid::recover(const GridCounters& seen) {
   fix.n_leaves = std::min(seen.n_leaves, dev_.leaf_cap);
   fix.n_inner = std::min(seen.n_inner, dev_.inner_cap);
   fix.error = 0;
+  fix.failed_id = NONE;
+  fix.done_blocks = 0;
   if (fix.n_free < 0) fix.n_free = 0;
   *h_ctr_ = fix;
   BNX_CUDA(cudaMemcpyAsync(d_ctr_, h_ctr_, sizeof(GridCounters), cudaMemcpyHostToDevice, stream_));
@@ -943,7 +948,9 @@ int Grid::clear(int option) {
   if (n_leaves) BNX_CUDA(cudaMemsetAsync(dev_.leaf, 0, (size_t)n_leaves * dev_.leaf_stride, stream_));
   if (n_inner) BNX_CUDA(cudaMemsetAsync(dev_.inner, 0, (size_t)n_inner * dev_.inner_stride * 4, stream_));
   BNX_CUDA(cudaMemsetAsync(root_, 0, root_slots_ * sizeof(int4), stream_));
-  BNX_CUDA(cudaMemsetAsync(d_ctr_, 0, sizeof(GridCounters), stream_));
+  std::memset(h_ctr_, 0, sizeof(GridCounters));
+  h_ctr_->failed_id = NONE;
+  BNX_CUDA(cudaMemcpyAsync(d_ctr_, h_ctr_, sizeof(GridCounters), cudaMemcpyHostToDevice, stream_));
   return sync();
 }
 

@@ -37,7 +37,9 @@ struct GridCounters {
   u32 n_leaves;  // leaves bump-allocated (may overshoot leaf_cap after a failed scan; host clamps)
   u32 error;     // ERR_* bits
   int n_free;    // entries on the leaf free list
-  u32 pad[3];
+  u32 failed_id;    // async pipeline: id of the first scan that failed (NONE when healthy)
+  u32 done_blocks;  // last-block ticket of the scan epilogue
+  u32 pad;
 };
 
 struct GridDev {

@@ -31,6 +31,7 @@ namespace {
 constexpr int TPB = 256;
 constexpr u32 CHUNK = 8;  // ray cells per work item
 constexpr unsigned long long CHUNK_FIELD = (1ull << 40) - 1ull;
+constexpr u32 RING_SIZE = 1024;  // entries of the pipelined-insert record ring (Map::RING)
 constexpr u32 OVF_TILES = 1u, OVF_CHUNKS = 2u, OVF_RECORDS = 4u, OVF_LEAVES = 8u;
 
 inline int blocks_for(i64 n, int tpb = TPB) { return (int)std::max<i64>(1, ceil_div(n, tpb)); }
@@ -70,7 +71,7 @@ __device__ __forceinline__ unsigned long long pack_key(const int4& e) {
 template <bool F64, bool VEC4, bool PACKED>
 __global__ void __launch_bounds__(TPB) k_classify(const unsigned char* __restrict__ pts, u32 stride, ScanParams p, ScanBuffers b) {
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= p.n) return;
+  if (i >= p.n || *b.poison) return;
   double px, py, pz;
   if (F64) {
     const double* q = reinterpret_cast<const double*>(pts + (size_t)i * stride);
@@ -180,6 +181,7 @@ __global__ void __launch_bounds__(TPB) k_resolve(GridDev g, ScanParams p, ScanBu
   __shared__ u32 s_base_e;
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (MODE == 0 && *b.poison) return;  // an earlier pipelined scan ran short: freeze until the host recovers
   if (threadIdx.x == 0) s_m = 0;
 
   bool is_end = false;
@@ -385,7 +387,7 @@ __global__ void __launch_bounds__(TPB) k_mark(GridDev g, GridDev gs, ScanParams 
   const unsigned long long rc = b.sc->ray_chunk;
   const u32 n_rays = (u32)(rc >> 40);
   const u32 total = (u32)(rc & CHUNK_FIELD);
-  if (b.sc->overflow) return;
+  if (b.sc->overflow | *b.poison) return;
   const u32 lane = threadIdx.x & 31;
   const u32 warps = gridDim.x * (TPB / 32);
   for (u32 tile = blockIdx.x * (TPB / 32) + (threadIdx.x >> 5); (u64)tile * 32 < total; tile += warps) {
@@ -487,9 +489,8 @@ __global__ void __launch_bounds__(TPB) k_apply_endpoints(GridDev g, ScanParams p
 __global__ void __launch_bounds__(TPB) k_apply_leaves(GridDev g, ScanParams p, ScanBuffers b) {
   // last kernel of the scan: the host reads counters + grid counters with one copy
   if (blockIdx.x == 0 && threadIdx.x == 0) b.sc->gc = *g.ctr;
-  if (g.ctr->error | b.sc->overflow) return;
-  if (b.gate && (b.gate[0] | b.gate[1])) return;
-  const u32 n = min(b.sc->n_touched, p.touched_cap);
+  const bool skip = (g.ctr->error | b.sc->overflow) || (b.gate && (b.gate[0] | b.gate[1]));
+  const u32 n = skip ? 0u : min(b.sc->n_touched, p.touched_cap);
   const u32 lane = threadIdx.x & 31;
   const u32 warps = gridDim.x * (TPB / 32);
   u32 changed = 0;
@@ -531,6 +532,46 @@ __global__ void __launch_bounds__(TPB) k_apply_leaves(GridDev g, ScanParams p, S
   }
   for (int o = 16; o; o >>= 1) changed += __shfl_xor_sync(0xffffffffu, changed, o);
   if (lane == 0 && changed) atomicAdd(&b.sc->n_changed, changed);
+  if (p.async_id == NONE) return;
+  // pipelined insert: the LAST block to get here publishes the scan's record to the host ring (zero copy) and
+  // makes a failure sticky, so that every later scan in the queue skips itself until the host has recovered
+  __shared__ bool s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicAdd(&g.ctr->done_blocks, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!s_last || threadIdx.x != 0) return;
+  g.ctr->done_blocks = 0;
+  __threadfence();
+  const volatile ScanCounters* sc = b.sc;
+  u32 err = g.ctr->error;
+  if (sc->overflow && !err) {
+    err = ERR_SCAN;
+    atomicOr(&g.ctr->error, ERR_SCAN);
+  }
+  if (err && g.ctr->failed_id == NONE) g.ctr->failed_id = p.async_id;
+  AsyncRecord* r = b.ring + (p.async_id & (RING_SIZE - 1u));
+  r->error = err;
+  r->n_leaves = g.ctr->n_leaves;
+  r->n_inner = g.ctr->n_inner;
+  r->n_roots = g.ctr->n_roots;
+  r->n_endpoints = sc->n_endpoints;
+  r->n_changed = sc->n_changed;
+  r->n_touched = sc->n_touched;
+  r->n_points = p.n;
+  r->sum_m = sc->sum_m;
+  r->ray_chunk = sc->ray_chunk;
+  __threadfence_system();
+  r->id = p.async_id;
+}
+
+// pipelined insert: clears the scan counters + dedupe table like the memset of the synchronous path, unless the
+// pipeline is frozen (the failed scan's counters and touched list must survive until the host has seen them)
+__global__ void __launch_bounds__(TPB) k_begin_scan(ScanBuffers b, uint4* base, u32 n16) {
+  if (*b.poison) return;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x) base[i] = make_uint4(0, 0, 0, 0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -678,6 +719,15 @@ __global__ void __launch_bounds__(TPB) k_query(GridDev g, const i32* __restrict_
 // ------------------------------------------------------------------------------------------------
 Map::~Map() {
   if (grid.stream()) cudaStreamSynchronize(grid.stream());
+  if (copy_stream_) {
+    cudaStreamSynchronize(copy_stream_);
+    cudaStreamDestroy(copy_stream_);
+  }
+  for (int k = 0; k < 2; ++k) {
+    if (ev_copied_[k]) cudaEventDestroy(ev_copied_[k]);
+    if (ev_consumed_[k]) cudaEventDestroy(ev_consumed_[k]);
+  }
+  if (h_ring_) cudaFreeHost(h_ring_);
   delete scratch_;
   if (h_status_) cudaFreeHost(h_status_);
   for (auto& e : ev_)
@@ -708,6 +758,16 @@ int Map::init(double resolution) {
   for (auto& e : ev_) BNX_CUDA(cudaEventCreate(&e));
   BNX_TRY(b_pending_.reserve(1024 * sizeof(int4)));
   buf_.pending = b_pending_.as<int4>();
+  BNX_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h_ring_), sizeof(AsyncRecord) * RING, cudaHostAllocMapped));
+  std::memset(h_ring_, 0xFF, sizeof(AsyncRecord) * RING);
+  BNX_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_ring_), h_ring_, 0));
+  BNX_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+  for (int k = 0; k < 2; ++k) {
+    BNX_CUDA(cudaEventCreateWithFlags(&ev_copied_[k], cudaEventDisableTiming));
+    BNX_CUDA(cudaEventCreateWithFlags(&ev_consumed_[k], cudaEventDisableTiming));
+  }
+  buf_.poison = &grid.dev().ctr->error;
+  buf_.ring = d_ring_;
   return reserve_scan(0, 16, 1.0);
 }
 
@@ -740,24 +800,7 @@ int Map::reserve_scan(i64 n, i64 stride_bytes, double max_range) {
   return BNX_OK;
 }
 
-int Map::insert(const void* points, i64 stride_bytes, i64 n, bool f64, const double origin[3], double max_range, int where) {
-  BNX_REQUIRE(n >= 0 && n + (i64)n_pending_ < (1ll << 24), "insert: at most 2^24-1 points per scan");
-  BNX_REQUIRE(n == 0 || points != nullptr, "insert: null points");
-  BNX_REQUIRE(origin != nullptr, "insert: null origin");
-  if (f64) {
-    BNX_REQUIRE(stride_bytes >= 24 && stride_bytes % 8 == 0, "insert_f64: stride must be a multiple of 8, >= 24");
-  } else {
-    BNX_REQUIRE(stride_bytes >= 12 && stride_bytes % 4 == 0, "insert_f32: stride must be a multiple of 4, >= 12");
-  }
-  cudaStream_t s = grid.stream();
-  if (profiling) cudaEventRecord(ev_[0], s);
-  BNX_TRY(reserve_scan(n, stride_bytes, max_range));
-  const void* d_points = points;
-  if (where == BNX_HOST && n > 0) {
-    BNX_TRY(b_pts_.reserve((size_t)n * stride_bytes));
-    BNX_CUDA(cudaMemcpyAsync(b_pts_.p, points, (size_t)n * stride_bytes, cudaMemcpyHostToDevice, s));
-    d_points = b_pts_.p;
-  }
+int Map::build_params(i64 n, const double origin[3], double max_range, ScanParams* out) {
   ScanParams p = {};
   p.ox = origin[0];
   p.oy = origin[1];
@@ -775,6 +818,8 @@ int Map::insert(const void* points, i64 stride_bytes, i64 n, bool f64, const dou
   p.cmax = options[3];
   p.c = update_count;
   p.n = (u32)n;
+  p.world = 1;
+  p.async_id = NONE;
   p.max_chunks = (u32)std::min<u64>(((1ull << 40) - 1) / (u64)std::max<i64>(n + n_pending_, 1), 1ull << 28);
   // every endpoint lies within max_range of the origin (hits by the range test, misses by truncation): if that
   // ball fits 21 bits per axis the dedupe table can use packed keys
@@ -784,7 +829,40 @@ int Map::insert(const void* points, i64 stride_bytes, i64 n, bool f64, const dou
     const double lim = (double)(1 << 20) - 1.0;
     if (std::fabs((double)p.Ox) + reach < lim && std::fabs((double)p.Oy) + reach < lim && std::fabs((double)p.Oz) + reach < lim) p.packed = 1;
   }
-  return run_scan(d_points, stride_bytes, f64, p, false);
+  p.hash_mask = (u32)(table_slots(n) - 1);
+  *out = p;
+  return BNX_OK;
+}
+
+static int check_insert_args(const void* points, i64 stride_bytes, i64 n, bool f64, const double origin[3], i64 pending) {
+  BNX_REQUIRE(n >= 0 && n + pending < (1ll << 24), "insert: at most 2^24-1 points per scan");
+  BNX_REQUIRE(n == 0 || points != nullptr, "insert: null points");
+  BNX_REQUIRE(origin != nullptr, "insert: null origin");
+  if (f64) {
+    BNX_REQUIRE(stride_bytes >= 24 && stride_bytes % 8 == 0, "insert_f64: stride must be a multiple of 8, >= 24");
+  } else {
+    BNX_REQUIRE(stride_bytes >= 12 && stride_bytes % 4 == 0, "insert_f32: stride must be a multiple of 4, >= 12");
+  }
+  return BNX_OK;
+}
+
+int Map::insert(const void* points, i64 stride_bytes, i64 n, bool f64, const double origin[3], double max_range, int where) {
+  BNX_TRY(check_insert_args(points, stride_bytes, n, f64, origin, n_pending_));
+  BNX_TRY(drain());
+  cudaStream_t s = grid.stream();
+  if (profiling) cudaEventRecord(ev_[0], s);
+  BNX_TRY(reserve_scan(n, stride_bytes, max_range));
+  const void* d_points = points;
+  if (where == BNX_HOST && n > 0) {
+    BNX_TRY(b_pts_.reserve((size_t)n * stride_bytes));
+    BNX_CUDA(cudaMemcpyAsync(b_pts_.p, points, (size_t)n * stride_bytes, cudaMemcpyHostToDevice, s));
+    d_points = b_pts_.p;
+  }
+  ScanParams p;
+  BNX_TRY(build_params(n, origin, max_range, &p));
+  BNX_TRY(run_scan(d_points, stride_bytes, f64, p, false));
+  if (++update_count == 4) update_count = 1;  // probabilistic_map.cpp:103-105
+  return BNX_OK;
 }
 
 template <bool F64, bool VEC4>
@@ -797,29 +875,71 @@ static void launch_classify(bool packed, int blocks, cudaStream_t s, const unsig
   }
 }
 
+// the kernel sequence of ONE attempt at a scan (no synchronisation)
+int Map::launch_scan(const void* d_points, i64 stride_bytes, bool f64, ScanParams& p, bool first_attempt) {
+  cudaStream_t s = grid.stream();
+  const i64 n = p.n;
+  const u64 slots = (u64)p.hash_mask + 1;
+  const int persistent = sm_count() * 8;
+  const GridDev g = grid.dev();
+  buf_.poison = &g.ctr->error;
+  buf_.ring = d_ring_;
+  p.seq = ++seq_;
+  p.tile_cap = (u32)std::min<size_t>(b_tiles_.bytes / 4, 0xFFFFFFFFull);
+  p.touched_cap = (u32)std::min<size_t>(b_touched_.bytes / 4, 0xFFFFFFFFull);
+  if (first_attempt) {
+    if (profiling) cudaEventRecord(ev_[1], s);
+    // counters + dedupe table (+ packed keys) in one clear
+    const size_t bytes = n > 0 ? SC_BYTES + slots * (p.packed ? 12 : 4) : SC_BYTES;
+    if (p.async_id == NONE) {
+      BNX_CUDA(cudaMemsetAsync(d_sc_, 0, bytes, s));
+    } else {
+      note_launch(), k_begin_scan<<<std::min<int>(persistent, blocks_for((i64)(bytes / 16))), TPB, 0, s>>>(buf_, reinterpret_cast<uint4*>(d_sc_), (u32)(bytes / 16));
+    }
+    if (n > 0) {
+      const unsigned char* pts = static_cast<const unsigned char*>(d_points);
+      const int blocks = blocks_for(n);
+      if (f64) {
+        launch_classify<true, false>(p.packed, blocks, s, pts, (u32)stride_bytes, p, buf_);
+      } else if (stride_bytes == 16 && (reinterpret_cast<uintptr_t>(pts) & 15u) == 0) {
+        launch_classify<false, true>(p.packed, blocks, s, pts, 16u, p, buf_);
+      } else {
+        launch_classify<false, false>(p.packed, blocks, s, pts, (u32)stride_bytes, p, buf_);
+      }
+    }
+    if (profiling) cudaEventRecord(ev_[2], s);
+  } else {
+    BNX_CUDA(cudaMemsetAsync(d_sc_, 0, SC_BYTES, s));
+  }
+  if (n_pending_) note_launch(), k_resolve<1><<<blocks_for(n_pending_), TPB, 0, s>>>(g, p, buf_, n_pending_);
+  if (n > 0) note_launch(), k_resolve<0><<<blocks_for(n), TPB, 0, s>>>(g, p, buf_, (u32)n);
+  if (profiling && first_attempt) cudaEventRecord(ev_[3], s);
+  note_launch(), k_mark<false><<<persistent, TPB, 0, s>>>(g, g, p, buf_);
+  if (profiling && first_attempt) cudaEventRecord(ev_[4], s);
+  note_launch(), k_apply_endpoints<<<std::min(persistent, blocks_for(n + n_pending_ + 1)), TPB, 0, s>>>(g, p, buf_);
+  note_launch(), k_apply_leaves<<<persistent, TPB, 0, s>>>(g, p, buf_);
+  BNX_CUDA(cudaGetLastError());
+  if (profiling && first_attempt) cudaEventRecord(ev_[5], s);
+  return BNX_OK;
+}
+
+void Map::account(const ScanCounters& st, i64 n, i64 pending, i64 retries) {
+  counters[0] = n;
+  counters[1] = (i64)st.n_endpoints + pending;
+  counters[2] = (i64)st.sum_m + n;
+  counters[3] = (i64)st.n_endpoints + st.n_changed;
+  counters[4] = st.n_touched;
+  counters[5] = retries;
+  counters[6] = (i64)(st.ray_chunk >> 40);
+  counters[7] = (i64)(st.ray_chunk & CHUNK_FIELD);
+  for (int k = 0; k < 4; ++k) totals[k] += counters[k];
+}
+
+// synchronous scan: attempts until the pools were large enough (each failed attempt changed nothing)
 int Map::run_scan(const void* d_points, i64 stride_bytes, bool f64, const ScanParams& base, bool) {
   cudaStream_t s = grid.stream();
   ScanParams p = base;
-  const i64 n = p.n;
-  const u64 slots = table_slots(n);
-  p.hash_mask = (u32)(slots - 1);
-  if (profiling) cudaEventRecord(ev_[1], s);
-  // counters + dedupe table (+ packed keys) in one clear
-  BNX_CUDA(cudaMemsetAsync(d_sc_, 0, n > 0 ? SC_BYTES + slots * (p.packed ? 12 : 4) : SC_BYTES, s));
-  if (n > 0) {
-    const unsigned char* pts = static_cast<const unsigned char*>(d_points);
-    const int blocks = blocks_for(n);
-    if (f64) {
-      launch_classify<true, false>(p.packed, blocks, s, pts, (u32)stride_bytes, p, buf_);
-    } else if (stride_bytes == 16 && (reinterpret_cast<uintptr_t>(pts) & 15u) == 0) {
-      launch_classify<false, true>(p.packed, blocks, s, pts, 16u, p, buf_);
-    } else {
-      launch_classify<false, false>(p.packed, blocks, s, pts, (u32)stride_bytes, p, buf_);
-    }
-    BNX_CUDA(cudaGetLastError());
-  }
-  if (profiling) cudaEventRecord(ev_[2], s);
-
+  p.async_id = NONE;
   const int persistent = sm_count() * 8;
   i64 retries = 0;
   for (;; ++retries) {
@@ -827,20 +947,7 @@ int Map::run_scan(const void* d_points, i64 stride_bytes, bool f64, const ScanPa
       set_error("insert: node pools could not be grown enough for this scan");
       return BNX_ERR_NOMEM;
     }
-    p.seq = ++seq_;
-    p.tile_cap = (u32)std::min<size_t>(b_tiles_.bytes / 4, 0xFFFFFFFFull);
-    p.touched_cap = (u32)std::min<size_t>(b_touched_.bytes / 4, 0xFFFFFFFFull);
-    const GridDev g = grid.dev();
-    if (retries) BNX_CUDA(cudaMemsetAsync(d_sc_, 0, SC_BYTES, s));
-    if (n_pending_) note_launch(), k_resolve<1><<<blocks_for(n_pending_), TPB, 0, s>>>(g, p, buf_, n_pending_);
-    if (n > 0) note_launch(), k_resolve<0><<<blocks_for(n), TPB, 0, s>>>(g, p, buf_, (u32)n);
-    if (profiling && retries == 0) cudaEventRecord(ev_[3], s);
-    note_launch(), k_mark<false><<<persistent, TPB, 0, s>>>(g, g, p, buf_);
-    if (profiling && retries == 0) cudaEventRecord(ev_[4], s);
-    note_launch(), k_apply_endpoints<<<std::min(persistent, blocks_for(n + 1)), TPB, 0, s>>>(g, p, buf_);
-    note_launch(), k_apply_leaves<<<persistent, TPB, 0, s>>>(g, p, buf_);
-    BNX_CUDA(cudaGetLastError());
-    if (profiling && retries == 0) cudaEventRecord(ev_[5], s);
+    BNX_TRY(launch_scan(d_points, stride_bytes, f64, p, retries == 0));
     BNX_CUDA(cudaMemcpyAsync(h_status_, d_sc_, sizeof(ScanCounters), cudaMemcpyDeviceToHost, s));
     BNX_CUDA(cudaStreamSynchronize(s));
     const ScanCounters st = *h_status_;
@@ -851,7 +958,7 @@ int Map::run_scan(const void* d_points, i64 stride_bytes, bool f64, const ScanPa
       return BNX_ERR_UNSUPPORTED;
     }
     if (st.n_touched) {
-      note_launch(), k_clear_touched<<<persistent, TPB, 0, s>>>(g, buf_, std::min(st.n_touched, p.touched_cap));
+      note_launch(), k_clear_touched<<<persistent, TPB, 0, s>>>(grid.dev(), buf_, std::min(st.n_touched, p.touched_cap));
       BNX_CUDA(cudaGetLastError());
       BNX_CUDA(cudaStreamSynchronize(s));
     }
@@ -865,16 +972,8 @@ int Map::run_scan(const void* d_points, i64 stride_bytes, bool f64, const ScanPa
     buf_.touched = b_touched_.as<u32>();
   }
   const ScanCounters st = *h_status_;
-  counters[0] = n;
-  counters[1] = (i64)st.n_endpoints + n_pending_;
-  counters[2] = (i64)st.sum_m + n;
-  counters[3] = (i64)st.n_endpoints + st.n_changed;
-  counters[4] = st.n_touched;
-  counters[5] = retries;
-  counters[6] = (i64)(st.ray_chunk >> 40);
-  counters[7] = (i64)(st.ray_chunk & CHUNK_FIELD);
+  account(st, p.n, n_pending_, retries);
   n_pending_ = 0;
-  if (++update_count == 4) update_count = 1;  // probabilistic_map.cpp:103-105
   if (profiling) {
     float ms;
     for (int k = 0; k < 5; ++k) {
@@ -885,6 +984,118 @@ int Map::run_scan(const void* d_points, i64 stride_bytes, bool f64, const ScanPa
     phase_us[5] = ms * 1e3;
   }
   return grid.maintain(st.gc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// pipelined insert
+// ------------------------------------------------------------------------------------------------
+int Map::insert_async(const void* points, i64 stride_bytes, i64 n, bool f64, const double origin[3], double max_range, int where) {
+  BNX_TRY(check_insert_args(points, stride_bytes, n, f64, origin, n_pending_));
+  if (n_pending_ || world_ > 1) return insert(points, stride_bytes, n, f64, origin, max_range, where);  // rare paths stay synchronous
+  cudaStream_t s = grid.stream();
+  if (queue_.size() >= RING / 2) BNX_TRY(drain());
+  // head-room check on the newest record the device has published (no synchronisation): grow early
+  if (!queue_.empty()) {
+    for (size_t k = queue_.size(); k-- > 0;) {
+      const AsyncRecord& r = h_ring_[queue_[k].p.async_id & (RING - 1)];
+      if (r.id != queue_[k].p.async_id) continue;
+      const GridDev g = grid.dev();
+      if (r.error || (u64)r.n_leaves * 2 > g.leaf_cap || (u64)r.n_inner * 2 > g.inner_cap || (u64)r.n_roots * 2 > (u64)g.root_mask + 1) BNX_TRY(drain());
+      break;
+    }
+  }
+  // scratch must not be reallocated under scans in flight
+  const size_t np = (size_t)n + 32;
+  const bool fits = np * sizeof(int4) <= b_ep_.bytes && SC_BYTES + table_slots(n) * 12 <= b_table_.bytes &&
+                    (size_t)grid.dev().leaf_cap * 4 <= b_touched_.bytes;
+  if (!fits) BNX_TRY(drain());
+  BNX_TRY(reserve_scan(n, stride_bytes, max_range));
+  Queued q;
+  BNX_TRY(build_params(n, origin, max_range, &q.p));
+  q.p.async_id = async_next_++;
+  q.points = points;
+  q.stride = stride_bytes;
+  q.f64 = f64;
+  q.where = where;
+  const void* d_points = points;
+  if (where == BNX_HOST && n > 0) {
+    // double-buffered staging on a copy stream: the copy of scan k+1 overlaps the kernels of scan k
+    const int slot = (int)(q.p.async_id & 1u);
+    if ((size_t)n * stride_bytes > b_stage_[slot].bytes) {
+      BNX_TRY(drain());
+      BNX_TRY(b_stage_[slot].reserve((size_t)n * stride_bytes));
+    }
+    if (stage_used_[slot]) BNX_CUDA(cudaStreamWaitEvent(copy_stream_, ev_consumed_[slot], 0));
+    BNX_CUDA(cudaMemcpyAsync(b_stage_[slot].p, points, (size_t)n * stride_bytes, cudaMemcpyHostToDevice, copy_stream_));
+    BNX_CUDA(cudaEventRecord(ev_copied_[slot], copy_stream_));
+    BNX_CUDA(cudaStreamWaitEvent(s, ev_copied_[slot], 0));
+    d_points = b_stage_[slot].p;
+  }
+  BNX_TRY(launch_scan(d_points, stride_bytes, f64, q.p, true));
+  if (where == BNX_HOST && n > 0) {
+    const int slot = (int)(q.p.async_id & 1u);
+    BNX_CUDA(cudaEventRecord(ev_consumed_[slot], s));
+    stage_used_[slot] = true;
+  }
+  queue_.push_back(q);
+  if (++update_count == 4) update_count = 1;
+  return BNX_OK;
+}
+
+int Map::drain() {
+  if (queue_.empty()) return BNX_OK;
+  cudaStream_t s = grid.stream();
+  BNX_CUDA(cudaMemcpyAsync(h_status_, d_sc_, sizeof(ScanCounters), cudaMemcpyDeviceToHost, s));
+  GridCounters gc;
+  BNX_TRY(grid.read_counters(&gc));  // synchronises the stream
+  std::vector<Queued> q;
+  q.swap(queue_);
+  size_t done = q.size();
+  if (gc.error) {
+    // frozen at the first scan that ran short: everything before it is applied, nothing after it is
+    done = 0;
+    while (done < q.size() && q[done].p.async_id != gc.failed_id) ++done;
+  }
+  for (size_t k = 0; k < done; ++k) {
+    const AsyncRecord& r = h_ring_[q[k].p.async_id & (RING - 1)];
+    ScanCounters st = {};
+    st.n_endpoints = r.n_endpoints;
+    st.n_changed = r.n_changed;
+    st.n_touched = r.n_touched;
+    st.sum_m = r.sum_m;
+    st.ray_chunk = r.ray_chunk;
+    account(st, q[k].p.n, 0, 0);
+  }
+  if (!gc.error) return grid.maintain(gc);
+  // the failed scan's touched list is still intact (later scans skipped themselves): drop its marks, grow, replay
+  const ScanCounters st = *h_status_;
+  if (st.overflow & OVF_CHUNKS) {
+    set_error("insert: more than 2^32 ray chunks in one scan");
+    return BNX_ERR_UNSUPPORTED;
+  }
+  if (st.n_touched) {
+    note_launch(), k_clear_touched<<<sm_count() * 8, TPB, 0, s>>>(grid.dev(), buf_, std::min<u32>(st.n_touched, (u32)(b_touched_.bytes / 4)));
+    BNX_CUDA(cudaGetLastError());
+    BNX_CUDA(cudaStreamSynchronize(s));
+  }
+  BNX_TRY(grid.recover(gc));
+  if (st.overflow & OVF_TILES) {
+    const u64 chunks = st.ray_chunk & CHUNK_FIELD;
+    BNX_TRY(b_tiles_.reserve((size_t)(chunks / 32 + 64) * 4));
+    buf_.tile_first = b_tiles_.as<u32>();
+  }
+  for (size_t k = done; k < q.size(); ++k) {
+    const Queued& e = q[k];
+    BNX_TRY(reserve_scan(e.p.n, e.stride, e.p.max_range));
+    const void* d_points = e.points;
+    if (e.where == BNX_HOST && e.p.n > 0) {
+      BNX_TRY(b_pts_.reserve((size_t)e.p.n * e.stride));
+      BNX_CUDA(cudaMemcpyAsync(b_pts_.p, e.points, (size_t)e.p.n * e.stride, cudaMemcpyHostToDevice, s));
+      d_points = b_pts_.p;
+    }
+    BNX_TRY(run_scan(d_points, e.stride, e.f64, e.p, false));  // keeps the update_id this scan was queued with
+  }
+  return BNX_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -913,6 +1124,7 @@ int Map::shard_begin(const void* points, i64 stride_bytes, i64 n, bool f64, u32 
   BNX_REQUIRE(n_pending_ == 0, "shard_begin: addHitPoint/addMissPoint queues are not supported on a sharded map");
   BNX_REQUIRE(origin && send_records && cap_records >= 2, "shard_begin: null argument");
   BNX_REQUIRE(f64 ? (stride_bytes >= 24 && stride_bytes % 8 == 0) : (stride_bytes >= 12 && stride_bytes % 4 == 0), "shard_begin: bad stride");
+  BNX_TRY(drain());
   cudaStream_t s = grid.stream();
   scratch_->set_stream(s);
   const i64 slots = (i64)world_ * cap_records;
@@ -941,6 +1153,7 @@ int Map::shard_begin(const void* points, i64 stride_bytes, i64 n, bool f64, u32 
   p.n = (u32)n;
   p.rank = (u32)rank_;
   p.world = (u32)world_;
+  p.async_id = NONE;
   p.rec_cap = (u32)cap_records;
   p.max_chunks = (u32)std::min<u64>(((1ull << 40) - 1) / (u64)std::max<i64>(slots, 1), 1ull << 28);
   const double reach = std::ceil(max_range * grid.inv_resolution) + 4.0, lim = (double)(1 << 20) - 1.0;
@@ -1072,6 +1285,7 @@ int Map::shard_finish(const void* flags_reduced, int* retry) {
 }
 
 int Map::add_point(const double pt[3], bool miss) {
+  BNX_TRY(drain());
   cudaStream_t s = grid.stream();
   if ((size_t)(n_pending_ + 1) * sizeof(int4) > b_pending_.bytes) {
     // grow, keeping the queue
@@ -1114,6 +1328,7 @@ int Map::query(const i32* xyz, i64 n, int kind, u8* out, int where) {
   BNX_REQUIRE(n >= 0 && (n == 0 || (xyz && out)), "query: null input");
   BNX_REQUIRE(kind == BNX_OCCUPIED || kind == BNX_UNKNOWN || kind == BNX_FREE, "query: unknown kind");
   if (n == 0) return BNX_OK;
+  BNX_TRY(drain());
   cudaStream_t s = grid.stream();
   const i32* dx = xyz;
   u8* dout = out;

@@ -24,6 +24,7 @@ struct ScanParams {
   u32 rec_cap;                 // sharded: slots per peer block of the endpoint record exchange
   u32 leaf_cap2;               // sharded: slots per peer block of the leaf-mask exchange
   u32 touched2_cap;            // sharded: entries of the scratch-grid touched list
+  u32 async_id;                // pipelined insert: serial of this scan (NONE for the synchronous path)
 };
 
 struct ScanCounters {
@@ -37,6 +38,16 @@ struct ScanCounters {
   u32 pad_;
   GridCounters gc;               // snapshot of the grid counters taken by the last kernel of the scan
 };
+
+// one record per pipelined scan, written by the device into pinned host memory (zero copy) when the scan ends
+struct AsyncRecord {
+  u32 error, n_leaves, n_inner, n_roots;
+  u32 n_endpoints, n_changed, n_touched, n_points;
+  unsigned long long sum_m, ray_chunk;
+  u32 pad[3];
+  volatile u32 id;  // written last
+};
+static_assert(sizeof(AsyncRecord) == 64, "one record per 64 bytes");
 
 struct ScanBuffers {
   int4* ep;          // per point: endpoint voxel xyz + type (0 hit, 1 miss)
@@ -52,6 +63,8 @@ struct ScanBuffers {
   const int4* recs;  // sharded: received endpoint records, [world][rec_cap], element 0 of a block = {count}
   const u32* gate;   // sharded: all-reduced error flags; the apply kernels skip when any is set (NULL otherwise)
   ScanCounters* sc;
+  AsyncRecord* ring;  // pipelined insert: mapped pinned host memory, RING entries
+  const u32* poison;  // &GridCounters::error of the map's grid: non-zero freezes every scan kernel
 };
 
 class Map {
@@ -71,6 +84,12 @@ class Map {
   int shard_resolve_mark(const void* recv_records, void* send_leaves, i64 cap_leaves);
   int shard_merge(const void* recv_leaves, void* flags);
   int shard_finish(const void* flags_reduced, int* retry);
+
+  // ---- pipelined insert: enqueue a scan and return; drain() completes everything queued (growing pools and
+  // replaying from the first scan that ran short, if any). Input buffers must stay valid until drain().
+  int insert_async(const void* points, i64 stride_bytes, i64 n, bool f64, const double origin[3], double max_range, int where);
+  int drain();
+  i64 totals[4] = {0, 0, 0, 0};  // cumulative N, E, V, U over every scan inserted so far
   int query(const i32* xyz, i64 n, int kind, u8* out, int where);
 
   Grid grid;
@@ -93,6 +112,26 @@ class Map {
   Grid* scratch_ = nullptr;  // sharded: staging grid for cells whose root another rank owns (masks only)
   ScanParams sp_ = {};       // sharded: parameters of the scan in flight
   i64 shard_retries_ = 0;
+  // pipelined insert
+  static constexpr u32 RING = 1024;
+  struct Queued {
+    ScanParams p;
+    const void* points;
+    i64 stride;
+    bool f64;
+    int where;
+  };
+  std::vector<Queued> queue_;
+  AsyncRecord* h_ring_ = nullptr;  // pinned + mapped
+  AsyncRecord* d_ring_ = nullptr;
+  u32 async_next_ = 0;
+  cudaStream_t copy_stream_ = nullptr;
+  cudaEvent_t ev_copied_[2] = {nullptr, nullptr}, ev_consumed_[2] = {nullptr, nullptr};
+  bool stage_used_[2] = {false, false};
+  DevBuf b_stage_[2];
+  int build_params(i64 n, const double origin[3], double max_range, ScanParams* out);
+  int launch_scan(const void* d_points, i64 stride_bytes, bool f64, ScanParams& p, bool first_attempt);
+  void account(const ScanCounters& st, i64 n, i64 pending, i64 retries);
   DevBuf b_touched2_;
   u32 seq_ = 0;
   cudaEvent_t ev_[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};

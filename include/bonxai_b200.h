@@ -154,6 +154,19 @@ BNX_API int bnx_map_insert_f32(bnx_map_t* m, const void* points, int64_t stride_
                                const float origin[3], double max_range, int where);
 BNX_API int bnx_map_insert_f64(bnx_map_t* m, const void* points, int64_t stride_bytes, int64_t n,
                                const double origin[3], double max_range, int where);
+/* Pipelined insertPointCloud: same result as bnx_map_insert_*, but the call only ENQUEUES the scan on the map's
+ * stream and returns; no host synchronisation per scan. The input buffer (device memory, or host memory —
+ * pinned for a real overlap of the copy with the previous scan's kernels) must stay valid and unchanged until
+ * bnx_map_sync() or any other call on the map returns; those complete the queue first. If a queued scan runs
+ * out of pool space the device freezes the pipeline at that scan (later scans skip themselves), and the next
+ * synchronising call grows the pools and replays from there: the map is always exactly what the synchronous
+ * calls would have produced. */
+BNX_API int bnx_map_insert_async_f32(bnx_map_t* m, const void* points, int64_t stride_bytes, int64_t n,
+                                     const float origin[3], double max_range, int where);
+BNX_API int bnx_map_insert_async_f64(bnx_map_t* m, const void* points, int64_t stride_bytes, int64_t n,
+                                     const double origin[3], double max_range, int where);
+/* cumulative {N, E, V, U} over every scan inserted so far (completes the queue) */
+BNX_API int bnx_map_totals(bnx_map_t* m, int64_t out[4]);
 /* addHitPoint / addMissPoint, probabilistic_map.cpp:30-54: the endpoint cell is updated now, its
  * ray is cast by the next insertPointCloud from that call's origin (updateFreeCells is private in
  * the reference, hpp:136) */

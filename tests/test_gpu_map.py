@@ -270,3 +270,50 @@ def test_device_resident_input(bnx, port):
     gm.insert(bnx.DevPtr(t.data_ptr()), origin, 50.0, n=len(pts), stride_bytes=16)
     om.insert(pts, origin, 50.0)
     check_scan(gm, om, "device input")
+
+
+def test_async_pipeline_equals_sync(bnx, port):
+    """pipelined inserts (no host sync per scan), host and device inputs mixed, equal the oracle scan by scan in total"""
+    import torch
+    gm, om = bnx.ProbabilisticMap(0.1), port.map(0.1)
+    keep, tot = [], dict(N=0, E=0, V=0, U=0)
+    for scan in range(12):
+        pts, origin = synth.lidar_scan(scan, beams=32, azimuths=1024)
+        if scan % 3 == 0:
+            t = torch.from_numpy(pts).cuda()
+            keep.append(t)
+            gm.insert_async(bnx.DevPtr(t.data_ptr()), origin, 45.0, n=len(pts), stride_bytes=16)
+        else:
+            keep.append(pts)
+            gm.insert_async(pts, origin, 45.0)
+        om.insert(pts, origin, 45.0)
+        for k in tot:
+            tot[k] += om.counters()[k]
+    gm.sync()
+    assert_same_dump(gm.dump(), om.dump(), "after 12 pipelined scans")
+    assert gm.totals() == tot
+    assert gm.update_count() == 1  # 12 scans: the counter cycled 4 times
+    # a synchronous insert after the pipeline continues seamlessly
+    pts, origin = synth.lidar_scan(12, beams=32, azimuths=1024)
+    gm.insert(pts, origin, 45.0)
+    om.insert(pts, origin, 45.0)
+    check_scan(gm, om, "sync after async")
+
+
+def test_async_pipeline_freeze_and_replay(bnx, port, monkeypatch):
+    """tiny pools: a queued scan runs short, the device freezes the pipeline, sync() grows and replays: still exact"""
+    monkeypatch.setenv("BNX_INIT_LEAF_MB", "2")
+    monkeypatch.setenv("BNX_INIT_INNER_MB", "0")
+    gm, om = bnx.ProbabilisticMap(0.1), port.map(0.1)
+    keep = []
+    for scan in range(8):
+        pts, origin = synth.lidar_scan(scan * 5, beams=32, azimuths=1024)
+        keep.append(pts)
+        gm.insert_async(pts, origin, 45.0)
+        om.insert(pts, origin, 45.0)
+        if scan == 4:  # a query in the middle of the queue drains it first
+            q = np.random.default_rng(0).integers(-200, 200, (1000, 3)).astype(np.int32)
+            assert np.array_equal(gm.query(q, bnx.BNX_OCCUPIED), om.query(q, 0))
+    gm.sync()
+    assert_same_dump(gm.dump(), om.dump(), "after freeze + replay")
+    assert gm.grid().stats()["leaf_capacity"] > 910  # the 2 MB pool had to grow
