@@ -7,6 +7,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <string>
+#include <vector>
 
 namespace bnx {
 
@@ -431,6 +433,87 @@ __global__ void __launch_bounds__(TPB) k_rebuild_roots(GridDev g, const int4* __
         break;
       }
       slot = (slot + 1) & new_mask;
+    }
+  }
+}
+
+// Serialize, bonxai_core/include/bonxai/serialization.hpp:77-116 — one warp per root (inner node). The body of a
+// root is {int32 key[3]; u64 inner_mask[Wi]; per ON child in ascending index: u64 leaf_mask[W], then the ON cells'
+// raw bytes in ascending leaf index}. Root order is unspecified in the reference (unordered_map order); here it
+// is the order in which warps reserve their range with one atomicAdd. out == nullptr: size query.
+__device__ __forceinline__ void put_bytes(u8* dst, const void* src, u32 n) {
+  const u8* s8 = static_cast<const u8*>(src);
+  for (u32 i = 0; i < n; ++i) dst[i] = s8[i];
+}
+
+__global__ void __launch_bounds__(TPB) k_serialize(GridDev g, u32 n_inner, u32 children, u32 Wi, u8* out, unsigned long long* total,
+                                                    unsigned long long* n_roots) {
+  const u32 lane = threadIdx.x & 31;
+  const u32 warps = gridDim.x * (TPB / 32);
+  const u32 W = g.mask_words;
+  for (u32 inner = blockIdx.x * (TPB / 32) + (threadIdx.x >> 5); inner < n_inner; inner += warps) {
+    const u32* node = inner_ptr(g, inner);
+    if (!(node[3] & 1u)) continue;
+    // pass 1: bytes of this root
+    unsigned long long bytes = 0;
+    for (u32 c = lane; c < children; c += 32) {
+      const u32 v = node[g.inner_child_off + c];
+      if (v >= 2u) {
+        const u64* act = leaf_active(g, v - 2u);
+        u32 cnt = 0;
+        for (u32 w = 0; w < W; ++w) cnt += __popcll(act[w]);
+        bytes += (unsigned long long)W * 8 + (unsigned long long)cnt * g.cell_bytes;
+      }
+    }
+    for (int o = 16; o; o >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, o);
+    bytes += 12 + (unsigned long long)Wi * 8;
+    unsigned long long base = 0;
+    if (lane == 0) {
+      base = atomicAdd(total, bytes);
+      atomicAdd(n_roots, 1ull);
+    }
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (!out) continue;
+    // pass 2: write. Children are laid out in ascending index: running offset over rounds of 32 children.
+    u8* dst = out + base;
+    if (lane == 0) put_bytes(dst, node, 12);
+    if (lane < Wi * 2) put_bytes(dst + 12 + lane * 4, node + 4 + lane, 4);
+    for (u32 k = lane + 32; k < Wi * 2; k += 32) put_bytes(dst + 12 + k * 4, node + 4 + k, 4);
+    unsigned long long run = 12 + (unsigned long long)Wi * 8;
+    for (u32 c0 = 0; c0 < children; c0 += 32) {
+      const u32 c = c0 + lane;
+      u32 leaf = NONE, cnt = 0;
+      if (c < children) {
+        const u32 v = node[g.inner_child_off + c];
+        if (v >= 2u) {
+          leaf = v - 2u;
+          const u64* act = leaf_active(g, leaf);
+          for (u32 w = 0; w < W; ++w) cnt += __popcll(act[w]);
+        }
+      }
+      const unsigned long long mine = leaf != NONE ? (unsigned long long)W * 8 + (unsigned long long)cnt * g.cell_bytes : 0ull;
+      unsigned long long incl = mine;
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (u32)o) incl += t;
+      }
+      if (leaf != NONE) {
+        u8* d = dst + run + (incl - mine);
+        const u64* act = leaf_active(g, leaf);
+        put_bytes(d, act, W * 8);
+        d += W * 8;
+        const u8* cells = leaf_cells(g, leaf);
+        for (u32 w = 0; w < W; ++w) {
+          u64 m = act[w];
+          while (m) {
+            const u32 bit = __ffsll((long long)m) - 1;
+            m &= m - 1;
+            put_bytes(d, cells + (size_t)(w * 64 + bit) * g.cell_bytes, g.cell_bytes);
+            d += g.cell_bytes;
+          }
+        }
+      }
+      run += __shfl_sync(0xffffffffu, incl, 31);
     }
   }
 }
@@ -999,13 +1082,137 @@ int Grid::stats(i64 out[8]) {
   return BNX_OK;
 }
 
-int Grid::serialize(const char*, u8*, i64, i64*) {
-  set_error("serialize: not implemented yet");
-  return BNX_ERR_UNSUPPORTED;
+int Grid::serialize(const char* type_name, u8* buffer, i64 cap, i64* size) {
+  BNX_REQUIRE(type_name && size, "serialize: null argument");
+  GridCounters c;
+  BNX_TRY(read_counters(&c));
+  const u32 n_inner = std::min(c.n_inner, dev_.inner_cap);
+  const u32 children = 1u << (3 * inner_bits), Wi = std::max(1u, children / 64u);
+  char header[256];
+  std::snprintf(header, sizeof(header), "Bonxai::VoxelGrid<%s,%d,%d>(%lf)\n", type_name, inner_bits, leaf_bits, resolution);  // serialization.hpp:84-88
+  const size_t hlen = std::strlen(header);
+  const int blocks = std::max(1, std::min<int>((int)ceil_div(std::max(1u, n_inner), TPB / 32), sm_count() * 8));
+  auto run = [&](u8* d_out) -> int {
+    BNX_CUDA(cudaMemsetAsync(d_count_, 0, 16, stream_));
+    if (n_inner) {
+      note_launch(), k_serialize<<<blocks, TPB, 0, stream_>>>(dev_, n_inner, children, Wi, d_out, reinterpret_cast<unsigned long long*>(d_count_),
+                                                       reinterpret_cast<unsigned long long*>(d_count_) + 1);
+      BNX_CUDA(cudaGetLastError());
+    }
+    BNX_CUDA(cudaMemcpyAsync(h_count_, d_count_, 16, cudaMemcpyDeviceToHost, stream_));
+    return sync();
+  };
+  BNX_TRY(run(nullptr));
+  const u64 body = h_count_[0];
+  const u32 roots = (u32)h_count_[1];
+  *size = (i64)(hlen + 4 + body);
+  if (!buffer) return BNX_OK;
+  if (cap < *size) {
+    set_error("serialize: output capacity too small");
+    return BNX_ERR_CAPACITY;
+  }
+  std::memcpy(buffer, header, hlen);
+  std::memcpy(buffer + hlen, &roots, 4);  // serialization.hpp:91
+  if (body) {
+    BNX_TRY(b_out_.reserve(body));
+    BNX_TRY(run(b_out_.as<u8>()));
+    BNX_CUDA(cudaMemcpyAsync(buffer + hlen + 4, b_out_.p, body, cudaMemcpyDeviceToHost, stream_));
+    BNX_TRY(sync());
+  }
+  return BNX_OK;
 }
-int Grid::deserialize(const u8*, i64, int, const char*, Grid**) {
-  set_error("deserialize: not implemented yet");
-  return BNX_ERR_UNSUPPORTED;
+
+// Deserialize, serialization.hpp:118-199: header "Bonxai::VoxelGrid<TYPE,IB,LB>(RES)\n", u32 root count, root bodies.
+// The stream is decoded on the host into (coord, value) pairs of the ON cells and inserted with the batched
+// setValue path (a leaf whose mask is all OFF leaves no trace, which no API can observe).
+int Grid::deserialize(const u8* data, i64 len, int cell_bytes, const char* expect_type, Grid** out) {
+  BNX_REQUIRE(data && out && len > 0, "deserialize: null argument");
+  const char* txt = reinterpret_cast<const char*>(data);
+  const void* nl = std::memchr(txt, '\n', (size_t)len);
+  BNX_REQUIRE(nl != nullptr, "Header wasn't recognized");
+  const std::string header(txt, static_cast<const char*>(nl));
+  const std::string prefix = "Bonxai::VoxelGrid<";
+  BNX_REQUIRE(header.rfind(prefix, 0) == 0, "Header wasn't recognized");  // serialization.hpp:127-130
+  const size_t gt = header.rfind(">(");
+  BNX_REQUIRE(gt != std::string::npos && header.back() == ')', "Header wasn't recognized");
+  const std::string inside = header.substr(prefix.size(), gt - prefix.size());  // TYPE,IB,LB (TYPE may contain commas)
+  const size_t c2 = inside.rfind(','), c1 = inside.rfind(',', c2 == std::string::npos ? 0 : c2 - 1);
+  BNX_REQUIRE(c2 != std::string::npos && c1 != std::string::npos, "Header wasn't recognized");
+  const std::string type_name = inside.substr(0, c1);
+  const int ib = std::atoi(inside.substr(c1 + 1, c2 - c1 - 1).c_str()), lb = std::atoi(inside.substr(c2 + 1).c_str());
+  const double res = std::atof(header.substr(gt + 2, header.size() - gt - 3).c_str());
+  if (expect_type && type_name != expect_type) {
+    set_error("DataT does not match");  // serialization.hpp:155-158
+    return BNX_ERR_INVALID;
+  }
+  Grid* g = new Grid();
+  int st = g->init(res, ib, lb, cell_bytes);
+  if (st != BNX_OK) {
+    delete g;
+    return st;
+  }
+  const u8* p = static_cast<const u8*>(nl) + 1;
+  const u8* end = data + len;
+  auto fail = [&](const char* msg) {
+    delete g;
+    set_error(msg);
+    return BNX_ERR_INVALID;
+  };
+  if (end - p < 4) return fail("deserialize: truncated stream");
+  u32 roots;
+  std::memcpy(&roots, p, 4);
+  p += 4;
+  const u32 children = 1u << (3 * ib), Wi = std::max(1u, children / 64u);
+  const u32 cells = 1u << (3 * lb), W = std::max(1u, cells / 64u);
+  const i32 lmask = (1 << lb) - 1, imask = (1 << ib) - 1;
+  std::vector<i32> xyz;
+  std::vector<u8> vals;
+  auto flush = [&]() -> int {
+    if (xyz.empty()) return BNX_OK;
+    const int r = g->set_values(xyz.data(), vals.data(), (i64)(xyz.size() / 3), nullptr, BNX_HOST);
+    xyz.clear();
+    vals.clear();
+    return r;
+  };
+  std::vector<u64> imaskw(Wi), lmaskw(W);
+  for (u32 r = 0; r < roots; ++r) {
+    if (end - p < (ptrdiff_t)(12 + Wi * 8)) return fail("deserialize: truncated stream");
+    i32 key[3];
+    std::memcpy(key, p, 12);
+    p += 12;
+    std::memcpy(imaskw.data(), p, Wi * 8);
+    p += Wi * 8;
+    for (u32 ci = 0; ci < children; ++ci) {
+      if (!((imaskw[ci >> 6] >> (ci & 63)) & 1ull)) continue;
+      if (end - p < (ptrdiff_t)(W * 8)) return fail("deserialize: truncated stream");
+      std::memcpy(lmaskw.data(), p, W * 8);
+      p += W * 8;
+      const i32 bx = key[0] | ((i32)(ci & imask) << lb), by = key[1] | ((i32)((ci >> ib) & imask) << lb), bz = key[2] | ((i32)((ci >> (2 * ib)) & imask) << lb);
+      for (u32 li = 0; li < cells; ++li) {
+        if (!((lmaskw[li >> 6] >> (li & 63)) & 1ull)) continue;
+        if (end - p < cell_bytes) return fail("deserialize: truncated stream");
+        xyz.push_back(bx | (i32)(li & lmask));
+        xyz.push_back(by | (i32)((li >> lb) & lmask));
+        xyz.push_back(bz | (i32)((li >> (2 * lb)) & lmask));
+        vals.insert(vals.end(), p, p + cell_bytes);
+        p += cell_bytes;
+      }
+    }
+    if (xyz.size() >= (size_t)3 << 21) {
+      st = flush();
+      if (st != BNX_OK) {
+        delete g;
+        return st;
+      }
+    }
+  }
+  st = flush();
+  if (st != BNX_OK) {
+    delete g;
+    return st;
+  }
+  *out = g;
+  return BNX_OK;
 }
 
 }  // namespace bnx

@@ -95,8 +95,7 @@ __global__ void __launch_bounds__(TPB) k_classify(const unsigned char* __restric
   if (PACKED) {
     const unsigned long long key = pack_key(e);
     for (;;) {
-      unsigned long long k = b.keys[slot];
-      if (k == 0ull) k = atomicCAS(&b.keys[slot], 0ull, key);
+      const unsigned long long k = atomicCAS(&b.keys[slot], 0ull, key);  // one L2 round trip, hit or claim
       if (k == 0ull || k == key) break;
       slot = (slot + 1) & p.hash_mask;
     }
@@ -383,6 +382,7 @@ __device__ __forceinline__ void mark_bits(const GridDev& G, u32 leaf, u32 w, uns
 template <bool SHARD>
 __global__ void __launch_bounds__(TPB) k_mark(GridDev g, GridDev gs, ScanParams p, ScanBuffers b) {
   __shared__ unsigned long long s_bits[CHUNK][TPB];
+  __shared__ u32 s_leaf[CHUNK][TPB];
   __shared__ unsigned char s_key[CHUNK][TPB];
   const unsigned long long rc = b.sc->ray_chunk;
   const u32 n_rays = (u32)(rc >> 40);
@@ -417,7 +417,8 @@ __global__ void __launch_bounds__(TPB) k_mark(GridDev g, GridDev gs, ScanParams 
       nseg = rg.m < (1u << 29) ? walk_chunk<int>(p, rg, k0, k1, lx0, ly0, lz0, s_bits, s_key)
                                : walk_chunk<i64>(p, rg, k0, k1, lx0, ly0, lz0, s_bits, s_key);
     }
-    // ---- flush, segment ordinal by segment ordinal (segments with the same leaf are consecutive)
+    // ---- flush A: resolve every segment's leaf (segments of one leaf are consecutive) and prefetch its touched word
+    // into L1; all lanes walk their stacks in lock step. The pointer replaces the mask's slot partner in smem.
     const u32 nmax = __reduce_max_sync(0xffffffffu, nseg);
     u32 cur_q = 0xFFu, leaf = NONE, inner = NONE;
     int rrx = 0, rry = 0, rrz = 0;
@@ -425,7 +426,6 @@ __global__ void __launch_bounds__(TPB) k_mark(GridDev g, GridDev gs, ScanParams 
     for (u32 sgi = 0; sgi < nmax; ++sgi) {
       if (sgi < nseg) {
         const u32 key = s_key[sgi][threadIdx.x];
-        const unsigned long long bits = s_bits[sgi][threadIdx.x];
         const u32 q = key >> 3, w = key & 7u;
         if (q != cur_q) {
           cur_q = q;
@@ -441,11 +441,36 @@ __global__ void __launch_bounds__(TPB) k_mark(GridDev g, GridDev gs, ScanParams 
           }
           leaf = (!SHARD || own) ? mark_leaf(g, inner, new_root, lx, ly, lz) : mark_leaf(gs, inner, new_root, lx, ly, lz);
         }
+        s_leaf[sgi][threadIdx.x] = leaf;
+        if (SHARD) s_key[sgi][threadIdx.x] = (unsigned char)(w | (own ? 0u : 0x80u));
         if (leaf != NONE) {
-          if (!SHARD || own) {
-            mark_bits(g, leaf, w, bits, p.seq, &b.sc->n_touched, b.touched, p.touched_cap);
+          const u64* t = ((!SHARD || own) ? leaf_touched(g, leaf) : leaf_touched(gs, leaf)) + w;
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(t));
+        }
+      }
+    }
+    // ---- flush B: test, then OR only what adds bits. A word seen non-zero can never be the leaf's first touch, so
+    // only writers of an (apparently) empty word need the old value back (stamp + list the leaf once per scan).
+    for (u32 sgi = 0; sgi < nmax; ++sgi) {
+      if (sgi < nseg) {
+        const u32 lf = s_leaf[sgi][threadIdx.x];
+        if (lf == NONE) continue;
+        const u32 key = s_key[sgi][threadIdx.x];
+        const unsigned long long bits = s_bits[sgi][threadIdx.x];
+        const bool mine = !SHARD || !(key & 0x80u);
+        const GridDev& G = mine ? g : gs;
+        unsigned long long* t = reinterpret_cast<unsigned long long*>(leaf_touched(G, lf)) + (key & 7u);
+        const unsigned long long cur = *t;
+        if ((cur & bits) == bits) continue;
+        if (cur != 0ull) {
+          atomicOr(t, bits);  // result unused: a fire-and-forget reduction
+        } else if (atomicOr(t, bits) == 0ull && atomicExch(leaf_stamp(G, lf), p.seq) != p.seq) {
+          if (mine) {
+            const u32 at = atomicAdd(&b.sc->n_touched, 1u);
+            if (at < p.touched_cap) b.touched[at] = lf;
           } else {
-            mark_bits(gs, leaf, w, bits, p.seq, &b.sc->n_touched2, b.touched2, p.touched2_cap);
+            const u32 at = atomicAdd(&b.sc->n_touched2, 1u);
+            if (at < p.touched2_cap) b.touched2[at] = lf;
           }
         }
       }
@@ -494,15 +519,24 @@ __global__ void __launch_bounds__(TPB) k_apply_leaves(GridDev g, ScanParams p, S
   const u32 lane = threadIdx.x & 31;
   const u32 warps = gridDim.x * (TPB / 32);
   u32 changed = 0;
-  for (u32 t = blockIdx.x * (TPB / 32) + (threadIdx.x >> 5); t < n; t += warps) {
-    const u32 leaf = b.touched[t];
+  // the masks of the NEXT leaf of this warp are loaded while the current leaf's cells are in flight
+  u32 t = blockIdx.x * (TPB / 32) + (threadIdx.x >> 5);
+  u32 leaf_n = t < n ? b.touched[t] : NONE;
+  unsigned long long tw_n = 0, aw_n = 0;
+  if (leaf_n != NONE && lane < 8) {
+    tw_n = reinterpret_cast<const unsigned long long*>(leaf_touched(g, leaf_n))[lane];
+    aw_n = reinterpret_cast<const unsigned long long*>(leaf_active(g, leaf_n))[lane];
+  }
+  for (; t < n; t += warps) {
+    const u32 leaf = leaf_n;
+    const unsigned long long tw = tw_n, aw = aw_n;
     unsigned long long* touched = reinterpret_cast<unsigned long long*>(leaf_touched(g, leaf));
     unsigned long long* active = reinterpret_cast<unsigned long long*>(leaf_active(g, leaf));
     u32* cells = reinterpret_cast<u32*>(leaf_cells(g, leaf));
-    unsigned long long tw = 0, aw = 0;
-    if (lane < 8) {
-      tw = touched[lane];
-      aw = active[lane];
+    leaf_n = t + warps < n ? b.touched[t + warps] : NONE;
+    if (leaf_n != NONE && lane < 8) {
+      tw_n = reinterpret_cast<const unsigned long long*>(leaf_touched(g, leaf_n))[lane];
+      aw_n = reinterpret_cast<const unsigned long long*>(leaf_active(g, leaf_n))[lane];
     }
     // lane owns cells it*32 + lane, it = 0..15 (coalesced 128-B rows); bit `it` of mine/on = that cell touched/ON
     u32 mine = 0, on = 0;

@@ -99,6 +99,8 @@ class VoxelGrid {
   uint32_t leafBits() const { return LEAF_BITS; }
   double voxelSize() const { return resolution; }
   bnx_grid_t* handle() const { return handle_; }
+  // take ownership of a handle passed to the view constructor (used by Deserialize)
+  void adopt() { owned_ = true; }
 
   [[nodiscard]] size_t memUsage() const {
     int64_t b = 0;

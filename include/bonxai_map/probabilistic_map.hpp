@@ -151,15 +151,7 @@ class ProbabilisticMap {
       const float of[3] = {(float)o.x, (float)o.y, (float)o.z};  // exact: the origin is a PointT of floats
       detail::check(bnx_map_insert_f32(_map, base, (int64_t)sizeof(PointT), n, of, max_range, BNX_HOST));
     } else {
-      std::vector<double> xyz(points.size() * 3);
-      for (size_t i = 0; i < points.size(); ++i) {
-        const Point3D p = ConvertPoint<Point3D>(points[i]);
-        xyz[3 * i] = p.x;
-        xyz[3 * i + 1] = p.y;
-        xyz[3 * i + 2] = p.z;
-      }
-      const double od[3] = {o.x, o.y, o.z};
-      detail::check(bnx_map_insert_f64(_map, xyz.data(), 24, n, od, max_range, BNX_HOST));
+      insertConverted(points, o, max_range);
     }
   }
 
@@ -214,6 +206,24 @@ class ProbabilisticMap {
     coords.resize((size_t)n);
     if (n) detail::check(bnx_map_get_voxels(_map, kind, &coords[0].x, n, &n, BNX_HOST));
     coords.resize((size_t)n);
+  }
+
+  // point types without an in-place xyz layout: converted to double triplets first (ConvertPoint, like the reference)
+  template <typename PointT, typename Allocator>
+#if defined(__GNUC__)
+  __attribute__((noinline))
+#endif
+  void insertConverted(const std::vector<PointT, Allocator>& points, const Point3D& o, double max_range) {
+    std::vector<double> xyz;
+    xyz.reserve(points.size() * 3);
+    for (const auto& pt : points) {
+      const Point3D p = ConvertPoint<Point3D>(pt);
+      xyz.push_back(p.x);
+      xyz.push_back(p.y);
+      xyz.push_back(p.z);
+    }
+    const double od[3] = {o.x, o.y, o.z};
+    detail::check(bnx_map_insert_f64(_map, xyz.data(), 24, (int64_t)points.size(), od, max_range, BNX_HOST));
   }
 
   // x,y,z as three consecutive floats/doubles inside PointT?

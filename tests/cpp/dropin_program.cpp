@@ -10,7 +10,10 @@
 #include <cstring>
 #include <vector>
 
+#include <sstream>
+
 #include "bonxai/bonxai.hpp"
+#include "bonxai/serialization.hpp"
 #include "bonxai_map/probabilistic_map.hpp"
 
 struct PointXYZ {  // pcl::PointXYZ layout
@@ -162,6 +165,38 @@ int main() {
     long acc = 0;
     for (const auto& c : ray) acc = acc * 31 + c.x * 7 + c.y * 3 + c.z;
     std::printf("ray2 cells=%zu hash=%ld\n", ray.size(), acc);
+  }
+  // ---------------------------------------------------------------- Serialize / Deserialize (examples/test_serialization.cpp)
+  {
+    Bonxai::VoxelGrid<int> grid(0.1);
+    auto accessor = grid.createAccessor();
+    int count = 0;
+    for (double x = -0.5; x < 0.5; x += 0.1)
+      for (double y = -0.5; y < 0.5; y += 0.1)
+        for (double z = -0.5; z < 0.5; z += 0.1) accessor.setValue(grid.posToCoord(x, y, z), count++);
+    accessor.setCellOff(grid.posToCoord(0.2, 0.2, 0.2));
+    std::ostringstream ofile(std::ios::binary);
+    Bonxai::Serialize(ofile, grid);
+    const std::string msg = ofile.str();
+    std::istringstream ifile(msg, std::ios::binary);
+    char header[256];
+    ifile.getline(header, 256);
+    Bonxai::HeaderInfo info = Bonxai::GetHeaderInfo(header);
+    std::printf("stream: %zu bytes, header '%s' -> type %s bits %d/%d res %.3f\n", msg.size(), header, info.type_name.c_str(), info.inner_bits,
+                info.leaf_bits, info.resolution);
+    auto new_grid = Bonxai::Deserialize<int>(ifile, info);
+    std::printf("cells %zu -> %zu\n", grid.activeCellsCount(), new_grid.activeCellsCount());
+    printDigest("original", grid);
+    printDigest("deserialized", new_grid);
+    bool threw = false;
+    try {
+      std::istringstream again(msg, std::ios::binary);
+      again.getline(header, 256);
+      auto wrong = Bonxai::Deserialize<float>(again, info);
+    } catch (const std::runtime_error&) {
+      threw = true;
+    }
+    std::printf("type mismatch throws: %d\n", (int)threw);
   }
   return 0;
 }
