@@ -311,13 +311,14 @@ __device__ __forceinline__ u32 walk_chunk(const ScanParams& p, const RayGeom& r,
   lz0 = z >> 3;
   u32 nseg = 0, key = 0xFFFFFFFFu;
   unsigned long long bits = 0;
-  const E em = (E)r.m;
+  const E em = (E)r.m, half = (E)((r.m + 1u) >> 1);  // (e << 1) >= m  <=>  e >= ceil(m / 2)
+  const E dax = (E)r.ax, day = (E)r.ay, daz = (E)r.az;
 #pragma unroll
   for (u32 c = 0; c < CHUNK; ++c) {
     if (k0 + c < k1) {
-      // quadrant = which minor axes have crossed into the neighbouring leaf; word = z & 7
-      const u32 q = (u32)((x >> 3) != lx0) | ((u32)((y >> 3) != ly0) << 1) | ((u32)((z >> 3) != lz0) << 2);
-      const u32 kc = (q << 3) | ((u32)z & 7u);
+      // segment key: mask word (z & 7) + the leaf-parity bit of every axis. Inside a chunk a coordinate crosses at
+      // most one leaf boundary, so equal keys <=> same leaf and same word.
+      const u32 kc = ((u32)z & 7u) | ((u32)x & 8u) | (((u32)y & 8u) << 1) | (((u32)z & 8u) << 2);
       if (kc != key) {
         if (bits) {
           s_bits[nseg][threadIdx.x] = bits;
@@ -328,18 +329,18 @@ __device__ __forceinline__ u32 walk_chunk(const ScanParams& p, const RayGeom& r,
         bits = 0;
       }
       bits |= 1ull << (((u32)x & 7u) | (((u32)y & 7u) << 3));
-      ex += (E)r.ax;
-      ey += (E)r.ay;
-      ez += (E)r.az;
-      if ((ex << 1) >= em) {
+      ex += dax;
+      ey += day;
+      ez += daz;
+      if (ex >= half) {
         x += r.sx;
         ex -= em;
       }
-      if ((ey << 1) >= em) {
+      if (ey >= half) {
         y += r.sy;
         ey -= em;
       }
-      if ((ez << 1) >= em) {
+      if (ez >= half) {
         z += r.sz;
         ez -= em;
       }
@@ -353,27 +354,32 @@ __device__ __forceinline__ u32 walk_chunk(const ScanParams& p, const RayGeom& r,
   return nseg;
 }
 
-// leaf of (lx,ly,lz) [leaf coordinates] in grid G, creating root / inner / leaf as needed
+// leaf (lx,ly,lz) [leaf coordinates, default bits 2/3] in grid G, creating root / inner / leaf as needed
 __device__ __forceinline__ u32 mark_leaf(const GridDev& G, u32& inner, bool new_root, int lx, int ly, int lz) {
   if (new_root) {
     const int kx = (lx >> 2) << 5, ky = (ly >> 2) << 5, kz = (lz >> 2) << 5;
     inner = root_find(G, kx, ky, kz);
     if (inner == NONE) inner = root_find_or_insert(G, kx, ky, kz);
   }
-  return inner == NONE ? NONE : leaf_in_inner_or_create(G, inner, lx << 3, ly << 3, lz << 3);
+  if (inner == NONE) return NONE;
+  const u32 ii = ((u32)lx & 3u) | (((u32)ly & 3u) << 2) | (((u32)lz & 3u) << 4);  // getInnerIndex, bonxai.hpp:431-438
+  const u32 v = inner_ptr(G, inner)[G.inner_child_off + ii];
+  return v >= 2u ? v - 2u : leaf_create_in_inner(G, inner, ii, lx << 3, ly << 3, lz << 3);
 }
 
-// OR `bits` into word w of the leaf's touched mask; the thread that turns the word non-zero stamps the leaf and,
-// if nobody stamped it in this scan yet, appends it to the touched list
+// OR `bits` into word w of the leaf's touched mask. Test first (a stale L1 line only costs a redundant atomic):
+// the leaves around the sensor are hit by every ray. A word seen non-zero can never be the leaf's first touch, so
+// only writers of an (apparently) empty word need the old value back; the thread that really turns a word
+// non-zero stamps the leaf and, if nobody stamped it in this scan yet, appends it to the touched list.
 __device__ __forceinline__ void mark_bits(const GridDev& G, u32 leaf, u32 w, unsigned long long bits, u32 seq, u32* n_list, u32* list, u32 cap) {
   unsigned long long* t = reinterpret_cast<unsigned long long*>(leaf_touched(G, leaf)) + w;
-  // test first (a stale L1 line only costs a redundant atomic): the leaves around the sensor are hit by every ray
-  if ((*t & bits) != bits) {
-    const unsigned long long old = atomicOr(t, bits);
-    if (old == 0ull && atomicExch(leaf_stamp(G, leaf), seq) != seq) {
-      const u32 at = atomicAdd(n_list, 1u);
-      if (at < cap) list[at] = leaf;
-    }
+  const unsigned long long cur = *t;
+  if ((cur & bits) == bits) return;
+  if (cur != 0ull) {
+    atomicOr(t, bits);  // result unused: a fire-and-forget reduction
+  } else if (atomicOr(t, bits) == 0ull && atomicExch(leaf_stamp(G, leaf), seq) != seq) {
+    const u32 at = atomicAdd(n_list, 1u);
+    if (at < cap) list[at] = leaf;
   }
 }
 
@@ -382,7 +388,6 @@ __device__ __forceinline__ void mark_bits(const GridDev& G, u32 leaf, u32 w, uns
 template <bool SHARD>
 __global__ void __launch_bounds__(TPB) k_mark(GridDev g, GridDev gs, ScanParams p, ScanBuffers b) {
   __shared__ unsigned long long s_bits[CHUNK][TPB];
-  __shared__ u32 s_leaf[CHUNK][TPB];
   __shared__ unsigned char s_key[CHUNK][TPB];
   const unsigned long long rc = b.sc->ray_chunk;
   const u32 n_rays = (u32)(rc >> 40);
@@ -417,16 +422,17 @@ __global__ void __launch_bounds__(TPB) k_mark(GridDev g, GridDev gs, ScanParams 
       nseg = rg.m < (1u << 29) ? walk_chunk<int>(p, rg, k0, k1, lx0, ly0, lz0, s_bits, s_key)
                                : walk_chunk<i64>(p, rg, k0, k1, lx0, ly0, lz0, s_bits, s_key);
     }
-    // ---- flush A: resolve every segment's leaf (segments of one leaf are consecutive) and prefetch its touched word
-    // into L1; all lanes walk their stacks in lock step. The pointer replaces the mask's slot partner in smem.
+    // ---- flush: all lanes walk their segment stacks in lock step (segments of one leaf are consecutive)
     const u32 nmax = __reduce_max_sync(0xffffffffu, nseg);
+    const u32 par0 = ((u32)lx0 & 1u) | (((u32)ly0 & 1u) << 1) | (((u32)lz0 & 1u) << 2);
     u32 cur_q = 0xFFu, leaf = NONE, inner = NONE;
     int rrx = 0, rry = 0, rrz = 0;
     bool have_root = false, own = true;
     for (u32 sgi = 0; sgi < nmax; ++sgi) {
       if (sgi < nseg) {
         const u32 key = s_key[sgi][threadIdx.x];
-        const u32 q = key >> 3, w = key & 7u;
+        const unsigned long long bits = s_bits[sgi][threadIdx.x];
+        const u32 q = (key >> 3) ^ par0, w = key & 7u;  // q: which axes have crossed into the neighbouring leaf
         if (q != cur_q) {
           cur_q = q;
           const int lx = lx0 + ((q & 1u) ? sx : 0), ly = ly0 + ((q & 2u) ? sy : 0), lz = lz0 + ((q & 4u) ? sz : 0);
@@ -441,36 +447,11 @@ __global__ void __launch_bounds__(TPB) k_mark(GridDev g, GridDev gs, ScanParams 
           }
           leaf = (!SHARD || own) ? mark_leaf(g, inner, new_root, lx, ly, lz) : mark_leaf(gs, inner, new_root, lx, ly, lz);
         }
-        s_leaf[sgi][threadIdx.x] = leaf;
-        if (SHARD) s_key[sgi][threadIdx.x] = (unsigned char)(w | (own ? 0u : 0x80u));
         if (leaf != NONE) {
-          const u64* t = ((!SHARD || own) ? leaf_touched(g, leaf) : leaf_touched(gs, leaf)) + w;
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(t));
-        }
-      }
-    }
-    // ---- flush B: test, then OR only what adds bits. A word seen non-zero can never be the leaf's first touch, so
-    // only writers of an (apparently) empty word need the old value back (stamp + list the leaf once per scan).
-    for (u32 sgi = 0; sgi < nmax; ++sgi) {
-      if (sgi < nseg) {
-        const u32 lf = s_leaf[sgi][threadIdx.x];
-        if (lf == NONE) continue;
-        const u32 key = s_key[sgi][threadIdx.x];
-        const unsigned long long bits = s_bits[sgi][threadIdx.x];
-        const bool mine = !SHARD || !(key & 0x80u);
-        const GridDev& G = mine ? g : gs;
-        unsigned long long* t = reinterpret_cast<unsigned long long*>(leaf_touched(G, lf)) + (key & 7u);
-        const unsigned long long cur = *t;
-        if ((cur & bits) == bits) continue;
-        if (cur != 0ull) {
-          atomicOr(t, bits);  // result unused: a fire-and-forget reduction
-        } else if (atomicOr(t, bits) == 0ull && atomicExch(leaf_stamp(G, lf), p.seq) != p.seq) {
-          if (mine) {
-            const u32 at = atomicAdd(&b.sc->n_touched, 1u);
-            if (at < p.touched_cap) b.touched[at] = lf;
+          if (!SHARD || own) {
+            mark_bits(g, leaf, w, bits, p.seq, &b.sc->n_touched, b.touched, p.touched_cap);
           } else {
-            const u32 at = atomicAdd(&b.sc->n_touched2, 1u);
-            if (at < p.touched2_cap) b.touched2[at] = lf;
+            mark_bits(gs, leaf, w, bits, p.seq, &b.sc->n_touched2, b.touched2, p.touched2_cap);
           }
         }
       }
