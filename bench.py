@@ -45,6 +45,24 @@ def load_peaks():
         return {"hbm_gbs": 6650.0}, "fallback"
 
 
+def ncu_traffic(phase: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the phase's kernel, from the committed ncu --set full
+    capture (profiles/r1_ncu_summary.json); None if that file has no entry."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_ncu_summary.json")) as f:
+            k = json.load(f)["kernels"]
+        name = {"classify": "k_classify<0, 1, 1>", "resolve": "k_resolve<0>", "mark": "k_mark<0>", "apply": "k_apply_leaves"}[phase]
+        e = k[name]
+        scale = {"Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Gbyte": 1e9}
+        tot = 0.0
+        for key, v in e.items():
+            if key.startswith("dram_read") or key.startswith("dram_write"):
+                tot += v * scale[key.split("[")[1].rstrip("]")]
+        return tot
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """SM clock + throttle reasons DURING the timed region. NVML (what nvidia-smi reads) polled every 2 ms from a
     thread, because the timed region lasts tens of milliseconds — shorter than one `nvidia-smi -lms` period."""
@@ -228,8 +246,10 @@ def run_gpu(args):
     sampler.start()
     launches0 = capi.launch_count()
     e0.record(stream)
+    th0 = time.perf_counter()
     for i in range(W, total):
         m.insert_async(capi.DevPtr(dev_scans[i].data_ptr()), scans[i][1], MAX_RANGE, n=N_PTS, stride_bytes=16)
+    enqueue_us = 1e6 * (time.perf_counter() - th0) / K  # host time to enqueue one scan: must stay below the GPU time
     e1.record(stream)
     m.sync()
     barrier()
@@ -254,8 +274,23 @@ def run_gpu(args):
     t0 = time.perf_counter()
     for i in range(W, total):
         m2.insert_async(pinned[i], scans[i][1], MAX_RANGE)
+    enqueue_e2e_us = 1e6 * (time.perf_counter() - t0) / K
     m2.sync()
     e2e_s = time.perf_counter() - t0
+    e2e_runs = [e2e_s]
+    if world == 1:
+        # the host side of this pass (a Python loop on a shared VM core) is noisy: repeat once on a fresh map, keep both
+        del m2
+        m2 = capi.ProbabilisticMap(RES)
+        for i in range(W):
+            m2.insert_async(pinned[i], scans[i][1], MAX_RANGE)
+        m2.sync()
+        t0 = time.perf_counter()
+        for i in range(W, total):
+            m2.insert_async(pinned[i], scans[i][1], MAX_RANGE)
+        m2.sync()
+        e2e_runs.append(time.perf_counter() - t0)
+        e2e_s = min(e2e_runs)
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -301,12 +336,13 @@ def run_gpu(args):
                           "note": "one synchronous bnx_map_insert_f32 per scan (the drop-in C++ insertPointCloud); value/e2e use the pipelined call"},
             "roofline": {"bound": "hbm", "kernel": {"classify": "k_classify", "resolve": "k_resolve", "mark": "k_mark", "apply": "k_apply_endpoints+k_apply_leaves"}[dom],
                          "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "algorithmic_bytes_per_launch": alg_bytes, "kernel_us": dom_us,
+                         "traffic": ncu_traffic(dom), "algorithmic_bytes_per_launch": alg_bytes, "kernel_us": dom_us,
                          "kernel_share_of_step": phases[dom] / max(phases["total"], 1e-9),
                          "step_achieved_gbs": alg_bytes * K / secs / 1e9},
             "e2e": {"value": world * K * N_PTS / e2e_s, "unit": "points/s", "h2d_bytes_per_step": N_PTS * 16, "d2h_bytes_per_step": 64,
-                    "ms_per_step": 1e3 * e2e_s / K},
+                    "ms_per_step": 1e3 * e2e_s / K, "runs_ms_per_step": [1e3 * r / K for r in e2e_runs], "reported": "min of the runs"},
             "gpu_launches": int(launches_all),
+            "host_enqueue_us_per_scan": {"device_buffers": enqueue_us, "host_buffers": enqueue_e2e_us},
             "clocks": clocks,
         }
         # CPU baseline beside it: the unmodified reference on one host core, bounded sample of the same sequence

@@ -22,6 +22,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace bnx {
@@ -30,6 +31,9 @@ namespace {
 
 constexpr int TPB = 256;
 constexpr u32 CHUNK = 8;  // ray cells per work item
+#ifndef MARK_MIN_BLOCKS
+#define MARK_MIN_BLOCKS 8
+#endif
 constexpr unsigned long long CHUNK_FIELD = (1ull << 40) - 1ull;
 constexpr u32 RING_SIZE = 1024;  // entries of the pipelined-insert record ring (Map::RING)
 constexpr u32 OVF_TILES = 1u, OVF_CHUNKS = 2u, OVF_RECORDS = 4u, OVF_LEAVES = 8u;
@@ -183,11 +187,10 @@ __global__ void __launch_bounds__(TPB) k_resolve(GridDev g, ScanParams p, ScanBu
   if (MODE == 0 && *b.poison) return;  // an earlier pipelined scan ran short: freeze until the host recovers
   if (threadIdx.x == 0) s_m = 0;
 
-  bool is_end = false;
+  bool is_end = false, winner = false;
   int4 e = make_int4(0, 0, 0, 0);
   u32 leaf = NONE, ci = 0, m = 0, chunks = 0;
   if (i < count) {
-    bool winner;
     if (MODE == 1) {
       e = b.pending[i];
       winner = true;
@@ -203,25 +206,36 @@ __global__ void __launch_bounds__(TPB) k_resolve(GridDev g, ScanParams p, ScanBu
       winner = b.table[b.slot_of[i]] == (p.packed ? ~i : i + 1u);
       if (winner) e = b.ep[i];
     }
+  }
+  if (!PENDING) {
+    // Accessor::value(coord, true), bonxai.hpp:469-494 — warp-aggregated: neighbouring points of a scan mostly fall
+    // into the same few leaves, so ONE lane per distinct leaf walks (and, if needed, creates) it and broadcasts the
+    // index; nobody spins on a slot that a lane of its own warp holds locked.
+    const u32 want = __ballot_sync(0xffffffffu, winner);
     if (winner) {
-      bool stale = false;
-      if (!PENDING) {
-        leaf = leaf_find_or_create(g, e.x, e.y, e.z);  // Accessor::value(coord, true), bonxai.hpp:469-494
-        if (leaf != NONE) {
-          ci = ((u32)e.x & 7u) | (((u32)e.y & 7u) << 3) | (((u32)e.z & 7u) << 6);
-          const bool on = (leaf_active(g, leaf)[ci >> 6] >> (ci & 63)) & 1ull;
-          const u32 word = on ? reinterpret_cast<const u32*>(leaf_cells(g, leaf))[ci] : 0u;
-          stale = (word & 0xFu) == p.c;  // probabilistic_map.cpp:34 / :47 — skipped AND no ray is cast
-        } else {
-          stale = true;  // pool exhausted: the scan will be repeated
-        }
+      const u32 peers = __match_any_sync(want, e.x >> 3) & __match_any_sync(want, e.y >> 3) & __match_any_sync(want, e.z >> 3);
+      const int leader = __ffs(peers) - 1;
+      if ((int)lane == leader) leaf = leaf_find_or_create(g, e.x, e.y, e.z);
+      leaf = __shfl_sync(peers, leaf, leader);
+    }
+  }
+  if (winner) {
+    bool stale = false;
+    if (!PENDING) {
+      if (leaf != NONE) {
+        ci = ((u32)e.x & 7u) | (((u32)e.y & 7u) << 3) | (((u32)e.z & 7u) << 6);
+        const bool on = (leaf_active(g, leaf)[ci >> 6] >> (ci & 63)) & 1ull;
+        const u32 word = on ? reinterpret_cast<const u32*>(leaf_cells(g, leaf))[ci] : 0u;
+        stale = (word & 0xFu) == p.c;  // probabilistic_map.cpp:34 / :47 — skipped AND no ray is cast
+      } else {
+        stale = true;  // pool exhausted: the scan will be repeated
       }
-      if (!stale) {
-        is_end = true;
-        const RayGeom rg = ray_geom(p, e.x, e.y, e.z);
-        m = rg.m;  // probabilistic_map.hpp:180; the ray has exactly m cells (end excluded)
-        chunks = rg.chunks;
-      }
+    }
+    if (!stale) {
+      is_end = true;
+      const RayGeom rg = ray_geom(p, e.x, e.y, e.z);
+      m = rg.m;  // probabilistic_map.hpp:180; the ray has exactly m cells (end excluded)
+      chunks = rg.chunks;
     }
   }
   if (chunks > p.max_chunks) {  // would overflow the packed counter: refuse the scan (BNX_ERR_UNSUPPORTED)
@@ -282,6 +296,13 @@ __global__ void __launch_bounds__(TPB) k_resolve(GridDev g, ScanParams p, ScanBu
 // ------------------------------------------------------------------------------------------------
 // phase 3: mark ray cells
 // ------------------------------------------------------------------------------------------------
+// cells [k0, k1) of chunk j. (Chunks of several leaf blocks with the segment flushed as soon as its key changes
+// were measured too: 1.6-2x slower — fewer, longer, more divergent work items. profiles/r1_notes.md)
+__device__ __forceinline__ void chunk_range(const RayGeom& r, u32 j, u32& k0, u32& k1) {
+  k0 = j == 0u ? 0u : r.len0 + 8u * (j - 1u);
+  k1 = min(r.m, j == 0u ? r.len0 : k0 + 8u);
+}
+
 // One lane = one chunk of one ray.
 //   walk   exact integer DDA restarted from the closed form at the chunk's first cell (cell k of RayIterator,
 //          probabilistic_map.hpp:162-203, is origin + sign * floor((2*k*|d| + m) / (2*m)) per axis with residual
@@ -386,7 +407,7 @@ __device__ __forceinline__ void mark_bits(const GridDev& G, u32 leaf, u32 w, uns
 // SHARD: cells whose root this rank does not own are marked in the scratch grid gs (same code, other pools);
 // their (leaf, mask) records travel to the owner after the kernel.
 template <bool SHARD>
-__global__ void __launch_bounds__(TPB) k_mark(GridDev g, GridDev gs, ScanParams p, ScanBuffers b) {
+__global__ void __launch_bounds__(TPB, MARK_MIN_BLOCKS) k_mark(GridDev g, GridDev gs, ScanParams p, ScanBuffers b) {
   __shared__ unsigned long long s_bits[CHUNK][TPB];
   __shared__ unsigned char s_key[CHUNK][TPB];
   const unsigned long long rc = b.sc->ray_chunk;
@@ -413,9 +434,8 @@ __global__ void __launch_bounds__(TPB) k_mark(GridDev g, GridDev gs, ScanParams 
       const u32 r = r_first + __popc(starts & ((2u << lane) - 1u));
       const int4 ray = b.rays[r];
       const RayGeom rg = ray_geom(p, ray.x, ray.y, ray.z);
-      const u32 j = chunk - (u32)ray.w;
-      const u32 k0 = j == 0u ? 0u : rg.len0 + 8u * (j - 1u);
-      const u32 k1 = min(rg.m, j == 0u ? rg.len0 : k0 + 8u);
+      u32 k0, k1;
+      chunk_range(rg, chunk - (u32)ray.w, k0, k1);
       sx = rg.sx;
       sy = rg.sy;
       sz = rg.sz;
