@@ -35,7 +35,7 @@ SYMBOLS = [
     "bnx_map_get_options", "bnx_map_insert_f32", "bnx_map_insert_f64", "bnx_map_add_hit", "bnx_map_add_miss",
     "bnx_map_query", "bnx_map_get_voxels", "bnx_map_get_voxel_points", "bnx_map_counters", "bnx_map_update_count",
     "bnx_map_set_profiling", "bnx_map_phase_times",
-    "bnx_map_insert_async_f32", "bnx_map_insert_async_f64", "bnx_map_totals",
+    "bnx_map_publish_occupied_f32", "bnx_map_insert_async_f32", "bnx_map_insert_async_f64", "bnx_map_totals",
     "bnx_map_shard_config", "bnx_map_shard_begin", "bnx_map_shard_resolve_mark", "bnx_map_shard_merge", "bnx_map_shard_finish",
 ]
 
@@ -384,6 +384,16 @@ class ProbabilisticMap:
         if cnt.value:
             _check(self.lib.bnx_map_get_voxel_points(self.h, int(kind), C.c_void_p(xyz.ctypes.data), C.c_int64(cnt.value), C.byref(cnt), BNX_HOST))
         return xyz
+
+    def publish_occupied(self, z_min: float, z_max: float, stride_floats: int = 3):
+        """occupied voxels as float32 points coord*resolution within [z_min, z_max] (the ROS node's publishAll)"""
+        cnt = C.c_int64()
+        _check(self.lib.bnx_map_publish_occupied_f32(self.h, C.c_double(z_min), C.c_double(z_max), None, C.c_int64(stride_floats), C.c_int64(0), C.byref(cnt), BNX_HOST))
+        out = np.empty((cnt.value, stride_floats), np.float32)
+        if cnt.value:
+            _check(self.lib.bnx_map_publish_occupied_f32(self.h, C.c_double(z_min), C.c_double(z_max), C.c_void_p(out.ctypes.data), C.c_int64(stride_floats),
+                                                         C.c_int64(cnt.value), C.byref(cnt), BNX_HOST))
+        return out
 
     def active_count(self) -> int:
         return self._grid.active_count()

@@ -320,6 +320,13 @@ int bnx_map_shard_finish(bnx_map_t* h, const void* flags_reduced, int* retry) {
   DeviceGuard dg(h->m.grid.device);
   return h->m.shard_finish(flags_reduced, retry);
 }
+int bnx_map_publish_occupied_f32(bnx_map_t* h, double z_min, double z_max, float* points, int64_t stride_floats, int64_t cap, int64_t* count,
+                                 int where) {
+  BNX_HANDLE(h);
+  DeviceGuard dg(h->m.grid.device);
+  BNX_TRY(h->m.drain());
+  return h->m.grid.dump_points_f32(points, stride_floats, 1, z_min, z_max, cap, count, where, h->m.options[4]);
+}
 int bnx_map_counters(bnx_map_t* h, int64_t out[8]) {
   BNX_HANDLE(h);
   BNX_TRY(h->m.drain());

@@ -256,9 +256,18 @@ __global__ void __launch_bounds__(TPB) k_count_active(GridDev g, u32 n_leaves, u
 // forEachCell (bonxai.hpp:704-743) / getOccupiedVoxels / getFreeVoxels (probabilistic_map.cpp:108-126)
 // as a compaction: per-leaf predicate masks -> popcount -> block prefix -> one atomicAdd per block.
 // pred < 0: every ON cell. pred 0/2: CellT word with probability_log > / < thr.
+// fpos: the publisher post-step of the ROS caller fused in (bonxai_ros/src/bonxai_server.cpp:217-251): voxel corner
+// coord*resolution in fp64, kept if zmin <= z <= zmax, stored as float xyz (+ w = 1.0f for a 16-byte pcl::PointXYZ).
+struct DumpFilter {
+  float* fpos;
+  u32 fstride;  // floats per output point: 3 or 4
+  int zfilter;
+  double zmin, zmax;
+};
+
 __global__ void __launch_bounds__(TPB) k_dump(GridDev g, u32 n_leaves, int pred, i32 thr, double res, i32* __restrict__ xyz,
                                                double* __restrict__ pos, u8* __restrict__ vals, unsigned long long cap,
-                                               unsigned long long* total) {
+                                               unsigned long long* total, DumpFilter flt) {
   __shared__ u32 s_cnt[TPB / 32];
   __shared__ unsigned long long s_base;
   const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -286,6 +295,11 @@ __global__ void __launch_bounds__(TPB) k_dump(GridDev g, u32 n_leaves, int pred,
             if ((m >> bit) & 1ull) {
               const i32 prob = (i32)cells[w * 64 + bit] >> 4;
               p = pred == BNX_OCCUPIED ? prob > thr : prob < thr;
+              if (p && flt.zfilter) {
+                const u32 ci = w * 64 + bit;
+                const double z = __dmul_rn((double)(hdr.z | (i32)((ci >> (2 * g.lb)) & ((1u << g.lb) - 1u))), res);
+                p = z >= flt.zmin && z <= flt.zmax;
+              }
             }
             pm |= (u64)__ballot_sync(0xffffffffu, p) << (half * 32);
           }
@@ -312,7 +326,7 @@ __global__ void __launch_bounds__(TPB) k_dump(GridDev g, u32 n_leaves, int pred,
       s_base = sum ? atomicAdd(total, (unsigned long long)sum) : 0ull;
     }
     __syncthreads();
-    if (leaf_total && (xyz || pos || vals)) {
+    if (leaf_total && (xyz || pos || vals || flt.fpos)) {
       // output order inside a leaf is lane-major (word l, word l+32, word l+1, ...): the order of a dump
       // is unspecified, only the set of (coord, value) pairs matters.
       const unsigned long long base = s_base + s_cnt[warp];
@@ -339,6 +353,13 @@ __global__ void __launch_bounds__(TPB) k_dump(GridDev g, u32 n_leaves, int pred,
             pos[3 * o] = __dmul_rn((double)cx, res);
             pos[3 * o + 1] = __dmul_rn((double)cy, res);
             pos[3 * o + 2] = __dmul_rn((double)cz, res);
+          }
+          if (flt.fpos) {  // PCLPoint(voxel.x(), voxel.y(), voxel.z()): double -> float, round to nearest
+            float* q = flt.fpos + (size_t)o * flt.fstride;
+            q[0] = __double2float_rn(__dmul_rn((double)cx, res));
+            q[1] = __double2float_rn(__dmul_rn((double)cy, res));
+            q[2] = __double2float_rn(__dmul_rn((double)cz, res));
+            if (flt.fstride == 4) q[3] = 1.0f;
           }
           if (vals) copy_cell(vals + (size_t)o * g.cell_bytes, leaf_cells(g, leaf) + (size_t)ci * g.cell_bytes, g.cell_bytes);
         }
@@ -952,6 +973,48 @@ int Grid::active_count(i64* count) {
   return BNX_OK;
 }
 
+int Grid::dump_points_f32(float* out, i64 stride_floats, int zfilter, double zmin, double zmax, i64 cap, i64* count, int where, i32 thr) {
+  BNX_REQUIRE(count != nullptr && cap >= 0, "occupied points: bad argument");
+  BNX_REQUIRE(stride_floats == 3 || stride_floats == 4, "occupied points: stride must be 3 or 4 floats");
+  GridCounters c;
+  BNX_TRY(read_counters(&c));
+  const u32 n_leaves = std::min(c.n_leaves, dev_.leaf_cap);
+  const int blocks = std::max(1, std::min<int>((int)ceil_div(n_leaves, TPB / 32), sm_count() * 8));
+  auto run = [&](float* dout, u64 dcap) -> int {
+    BNX_CUDA(cudaMemsetAsync(d_count_, 0, 8, stream_));
+    if (n_leaves) {
+      const DumpFilter f = {dout, (u32)stride_floats, zfilter, zmin, zmax};
+      note_launch(), k_dump<<<blocks, TPB, 0, stream_>>>(dev_, n_leaves, BNX_OCCUPIED, thr, resolution, nullptr, nullptr, nullptr, dcap,
+                                                  reinterpret_cast<unsigned long long*>(d_count_), f);
+      BNX_CUDA(cudaGetLastError());
+    }
+    BNX_CUDA(cudaMemcpyAsync(h_count_, d_count_, 8, cudaMemcpyDeviceToHost, stream_));
+    return sync();
+  };
+  if (where == BNX_DEVICE && out && cap > 0) {
+    BNX_TRY(run(out, (u64)cap));
+    *count = (i64)h_count_[0];
+    if (*count > cap) {
+      set_error("occupied points: output capacity too small");
+      return BNX_ERR_CAPACITY;
+    }
+    return BNX_OK;
+  }
+  BNX_TRY(run(nullptr, 0));
+  const i64 total = (i64)h_count_[0];
+  *count = total;
+  if (!out || cap == 0) return BNX_OK;
+  if (total > cap) {
+    set_error("occupied points: output capacity too small");
+    return BNX_ERR_CAPACITY;
+  }
+  if (total == 0) return BNX_OK;
+  BNX_TRY(b_out_.reserve((size_t)total * stride_floats * 4));
+  BNX_TRY(run(b_out_.as<float>(), (u64)total));
+  BNX_CUDA(cudaMemcpyAsync(out, b_out_.p, (size_t)total * stride_floats * 4, cudaMemcpyDeviceToHost, stream_));
+  return sync();
+}
+
 int Grid::dump(i32* xyz, double* pos, void* values, i64 cap, i64* count, int where, int pred, i32 thr) {
   BNX_REQUIRE(count != nullptr, "dump: null count");
   BNX_REQUIRE(cap >= 0, "dump: negative capacity");
@@ -962,7 +1025,8 @@ int Grid::dump(i32* xyz, double* pos, void* values, i64 cap, i64* count, int whe
   auto run = [&](i32* dxyz, double* dpos, u8* dval, u64 dcap) -> int {
     BNX_CUDA(cudaMemsetAsync(d_count_, 0, 8, stream_));
     if (n_leaves) {
-      note_launch(), k_dump<<<blocks, TPB, 0, stream_>>>(dev_, n_leaves, pred, thr, resolution, dxyz, dpos, dval, dcap, reinterpret_cast<unsigned long long*>(d_count_));
+      const DumpFilter nofilter = {nullptr, 3, 0, 0.0, 0.0};
+      note_launch(), k_dump<<<blocks, TPB, 0, stream_>>>(dev_, n_leaves, pred, thr, resolution, dxyz, dpos, dval, dcap, reinterpret_cast<unsigned long long*>(d_count_), nofilter);
       BNX_CUDA(cudaGetLastError());
     }
     BNX_CUDA(cudaMemcpyAsync(h_count_, d_count_, 8, cudaMemcpyDeviceToHost, stream_));

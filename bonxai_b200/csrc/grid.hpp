@@ -66,6 +66,8 @@ class Grid {
   // pred: -1 all ON cells; BNX_OCCUPIED/BNX_FREE: CellT probability_log >/< thr (map grids only).
   // xyz_out (int32 triplets) or pos_out (double triplets, coord*resolution); values optional.
   int dump(i32* xyz, double* pos, void* values, i64 cap, i64* count, int where, int pred, i32 thr);
+  // occupied voxels of a map grid as float points coord*resolution with an optional z window (publisher post-step)
+  int dump_points_f32(float* out, i64 stride_floats, int zfilter, double zmin, double zmax, i64 cap, i64* count, int where, i32 thr);
   int clear(int option);
   int release_unused();
   int mem_usage(i64* bytes);

@@ -179,6 +179,12 @@ BNX_API int bnx_map_query(bnx_map_t* m, const int32_t* xyz, int64_t n, int kind,
 BNX_API int bnx_map_get_voxels(bnx_map_t* m, int kind, int32_t* xyz, int64_t cap, int64_t* count, int where);
 /* getOccupiedVoxels<PointT>, probabilistic_map.hpp:115-124: coord * resolution (voxel corner), doubles */
 BNX_API int bnx_map_get_voxel_points(bnx_map_t* m, int kind, double* xyz, int64_t cap, int64_t* count, int where);
+/* The publisher post-step of the reference's ROS node fused into the compaction (bonxai_ros/src/bonxai_server.cpp:
+ * 217-251): every occupied voxel as the point coord*resolution (fp64 product, voxel corner), kept when
+ * z_min <= z <= z_max, written as float x,y,z every stride_floats floats (3 = packed, 4 = pcl::PointXYZ with
+ * w = 1.0f). Same cap/count protocol as bnx_grid_dump; order unspecified. */
+BNX_API int bnx_map_publish_occupied_f32(bnx_map_t* m, double z_min, double z_max, float* points, int64_t stride_floats,
+                                         int64_t cap, int64_t* count, int where);
 /* counters of the last insert: {N points, E endpoint voxels updated (= rays cast), V = sum of ray
  * cells + N, U cells whose word changed, leaves touched, retries after pool growth, 0, 0} */
 BNX_API int bnx_map_counters(bnx_map_t* m, int64_t out[8]);
