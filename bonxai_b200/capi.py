@@ -35,7 +35,7 @@ SYMBOLS = [
     "bnx_map_get_options", "bnx_map_insert_f32", "bnx_map_insert_f64", "bnx_map_add_hit", "bnx_map_add_miss",
     "bnx_map_query", "bnx_map_get_voxels", "bnx_map_get_voxel_points", "bnx_map_counters", "bnx_map_update_count",
     "bnx_map_set_profiling", "bnx_map_phase_times",
-    "bnx_map_publish_occupied_f32", "bnx_map_insert_async_f32", "bnx_map_insert_async_f64", "bnx_map_totals",
+    "bnx_map_publish_occupied_f32", "bnx_map_insert_transformed_f32", "bnx_map_insert_async_f32", "bnx_map_insert_async_f64", "bnx_map_totals",
     "bnx_map_shard_config", "bnx_map_shard_begin", "bnx_map_shard_resolve_mark", "bnx_map_shard_merge", "bnx_map_shard_finish",
 ]
 
@@ -347,6 +347,15 @@ class ProbabilisticMap:
         else:
             o = np.ascontiguousarray(origin, dtype=np.float32)
             _check(self.lib.bnx_map_insert_async_f32(self.h, p, C.c_int64(stride_bytes), C.c_int64(n), C.c_void_p(o.ctypes.data), C.c_double(max_range), where))
+
+    def insert_transformed(self, pts, sensor_to_world, origin, max_range, use_async=False):
+        """fused ROS pre-step: drop non-finite points, apply the 4x4 float transform, insert (float32 points only)"""
+        arr = pts if use_async else np.ascontiguousarray(pts)
+        assert arr.dtype == np.float32 and arr.ndim == 2 and arr.flags["C_CONTIGUOUS"]
+        T = np.ascontiguousarray(sensor_to_world, dtype=np.float32).reshape(16)
+        o = np.ascontiguousarray(origin, dtype=np.float32)
+        _check(self.lib.bnx_map_insert_transformed_f32(self.h, C.c_void_p(arr.ctypes.data), C.c_int64(arr.shape[1] * 4), C.c_int64(len(arr)),
+                                                       C.c_void_p(T.ctypes.data), C.c_void_p(o.ctypes.data), C.c_double(max_range), BNX_HOST, int(use_async)))
 
     def totals(self):
         a = (C.c_int64 * 4)()

@@ -256,6 +256,16 @@ int bnx_map_insert_async_f64(bnx_map_t* h, const void* points, int64_t stride_by
   DeviceGuard dg(h->m.grid.device);
   return h->m.insert_async(points, stride_bytes, n, true, origin, max_range, where);
 }
+int bnx_map_insert_transformed_f32(bnx_map_t* h, const void* points, int64_t stride_bytes, int64_t n, const float sensor_to_world[16],
+                                   const float origin[3], double max_range, int where, int async) {
+  BNX_HANDLE(h);
+  BNX_REQUIRE(origin != nullptr && sensor_to_world != nullptr, "null origin / transform");
+  DeviceGuard dg(h->m.grid.device);
+  const double o[3] = {(double)origin[0], (double)origin[1], (double)origin[2]};
+  if (!async) BNX_TRY(h->m.drain());
+  h->m.set_next_transform(sensor_to_world);
+  return async ? h->m.insert_async(points, stride_bytes, n, false, o, max_range, where) : h->m.insert(points, stride_bytes, n, false, o, max_range, where);
+}
 int bnx_map_totals(bnx_map_t* h, int64_t out[4]) {
   BNX_HANDLE(h);
   DeviceGuard dg(h->m.grid.device);

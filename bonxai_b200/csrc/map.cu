@@ -82,16 +82,39 @@ __global__ void __launch_bounds__(TPB) k_classify(const unsigned char* __restric
     px = q[0];
     py = q[1];
     pz = q[2];
-  } else if (VEC4) {
-    const float4 q = *reinterpret_cast<const float4*>(pts + (size_t)i * 16);  // pcl::PointXYZ
-    px = (double)q.x;
-    py = (double)q.y;
-    pz = (double)q.z;
   } else {
-    const float* q = reinterpret_cast<const float*>(pts + (size_t)i * stride);
-    px = (double)q[0];
-    py = (double)q[1];
-    pz = (double)q[2];
+    float fx, fy, fz;
+    if (VEC4) {
+      const float4 q = *reinterpret_cast<const float4*>(pts + (size_t)i * 16);  // pcl::PointXYZ
+      fx = q.x;
+      fy = q.y;
+      fz = q.z;
+    } else {
+      const float* q = reinterpret_cast<const float*>(pts + (size_t)i * stride);
+      fx = q[0];
+      fy = q[1];
+      fz = q[2];
+    }
+    if (p.use_transform) {
+      // the ROS caller's pre-step (bonxai_ros/src/bonxai_server.cpp:148-171): non-finite points leave the cloud, the
+      // rest goes through pcl::transformPointCloud in float. Association of PCL's SSE kernel on x86-64:
+      // x*c0 + (y*c1 + (z*c2 + c3)), every product and sum rounded on its own (no FMA).
+      if (!(isfinite(fx) && isfinite(fy) && isfinite(fz))) {
+        b.ep[i] = make_int4(0, 0, 0, 2);
+        b.slot_of[i] = NONE;
+        atomicAdd(&b.sc->n_dropped, 1u);
+        return;
+      }
+      const float tx = __fadd_rn(__fmul_rn(fx, p.T[0]), __fadd_rn(__fmul_rn(fy, p.T[1]), __fadd_rn(__fmul_rn(fz, p.T[2]), p.T[3])));
+      const float ty = __fadd_rn(__fmul_rn(fx, p.T[4]), __fadd_rn(__fmul_rn(fy, p.T[5]), __fadd_rn(__fmul_rn(fz, p.T[6]), p.T[7])));
+      const float tz = __fadd_rn(__fmul_rn(fx, p.T[8]), __fadd_rn(__fmul_rn(fy, p.T[9]), __fadd_rn(__fmul_rn(fz, p.T[10]), p.T[11])));
+      fx = tx;
+      fy = ty;
+      fz = tz;
+    }
+    px = (double)fx;
+    py = (double)fy;
+    pz = (double)fz;
   }
   const int4 e = classify_point(px, py, pz, p);
   b.ep[i] = e;
@@ -203,7 +226,8 @@ __global__ void __launch_bounds__(TPB) k_resolve(GridDev g, ScanParams p, ScanBu
         e.w &= 1;
       }
     } else {
-      winner = b.table[b.slot_of[i]] == (p.packed ? ~i : i + 1u);
+      const u32 slot = b.slot_of[i];  // NONE: the point was dropped by the fused pre-step
+      winner = slot != NONE && b.table[slot] == (p.packed ? ~i : i + 1u);
       if (winner) e = b.ep[i];
     }
   }
@@ -596,6 +620,7 @@ __global__ void __launch_bounds__(TPB) k_apply_leaves(GridDev g, ScanParams p, S
   r->n_changed = sc->n_changed;
   r->n_touched = sc->n_touched;
   r->n_points = p.n;
+  r->n_dropped = sc->n_dropped;
   r->sum_m = sc->sum_m;
   r->ray_chunk = sc->ray_chunk;
   __threadfence_system();
@@ -617,7 +642,8 @@ __global__ void __launch_bounds__(TPB) k_begin_scan(ScanBuffers b, uint4* base, 
 __global__ void __launch_bounds__(TPB) k_shard_bucket(ScanParams p, ScanBuffers b, u32 index_base, int4* send, u32 cap) {
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.n) return;
-  if (b.table[b.slot_of[i]] != ~i) return;  // not the lowest local index of its voxel
+  const u32 slot = b.slot_of[i];
+  if (slot == NONE || b.table[slot] != ~i) return;  // dropped, or not the lowest local index of its voxel
   const int4 e = b.ep[i];
   const u32 o = shard_owner(e.x >> 5, e.y >> 5, e.z >> 5, p.world);
   int4* block = send + (size_t)o * cap;
@@ -855,6 +881,9 @@ int Map::build_params(i64 n, const double origin[3], double max_range, ScanParam
   p.n = (u32)n;
   p.world = 1;
   p.async_id = NONE;
+  p.use_transform = use_next_T_ ? 1u : 0u;
+  for (int k = 0; k < 12; ++k) p.T[k] = next_T_[k];
+  use_next_T_ = false;
   p.max_chunks = (u32)std::min<u64>(((1ull << 40) - 1) / (u64)std::max<i64>(n + n_pending_, 1), 1ull << 28);
   // every endpoint lies within max_range of the origin (hits by the range test, misses by truncation): if that
   // ball fits 21 bits per axis the dedupe table can use packed keys
@@ -959,6 +988,7 @@ int Map::launch_scan(const void* d_points, i64 stride_bytes, bool f64, ScanParam
 }
 
 void Map::account(const ScanCounters& st, i64 n, i64 pending, i64 retries) {
+  n -= st.n_dropped;  // the reference's caller removes non-finite points before insertPointCloud sees the cloud
   counters[0] = n;
   counters[1] = (i64)st.n_endpoints + pending;
   counters[2] = (i64)st.sum_m + n;
@@ -1097,6 +1127,7 @@ int Map::drain() {
     st.n_endpoints = r.n_endpoints;
     st.n_changed = r.n_changed;
     st.n_touched = r.n_touched;
+    st.n_dropped = r.n_dropped;
     st.sum_m = r.sum_m;
     st.ray_chunk = r.ray_chunk;
     account(st, q[k].p.n, 0, 0);

@@ -25,6 +25,8 @@ struct ScanParams {
   u32 leaf_cap2;               // sharded: slots per peer block of the leaf-mask exchange
   u32 touched2_cap;            // sharded: entries of the scratch-grid touched list
   u32 async_id;                // pipelined insert: serial of this scan (NONE for the synchronous path)
+  u32 use_transform;           // fused ROS pre-step: drop non-finite points, then T * p in float before classifying
+  float T[12];                 // rows 0..2 of the 4x4 sensor->world matrix
 };
 
 struct ScanCounters {
@@ -35,7 +37,7 @@ struct ScanCounters {
   u32 n_changed;                 // cells changed by the free-space apply pass
   u32 overflow;                  // scan scratch overflow bits
   u32 n_touched2;                // sharded: scratch-grid leaves touched (cells owned by other ranks)
-  u32 pad_;
+  u32 n_dropped;                 // fused pre-step: non-finite points removed from the scan
   GridCounters gc;               // snapshot of the grid counters taken by the last kernel of the scan
 };
 
@@ -44,7 +46,8 @@ struct AsyncRecord {
   u32 error, n_leaves, n_inner, n_roots;
   u32 n_endpoints, n_changed, n_touched, n_points;
   unsigned long long sum_m, ray_chunk;
-  u32 pad[3];
+  u32 n_dropped;
+  u32 pad[2];
   volatile u32 id;  // written last
 };
 static_assert(sizeof(AsyncRecord) == 64, "one record per 64 bytes");
@@ -75,6 +78,11 @@ class Map {
 
   int insert(const void* points, i64 stride_bytes, i64 n, bool f64, const double origin[3], double max_range, int where);
   int add_point(const double p[3], bool miss);
+  // the next insert / insert_async first drops non-finite points and applies this 4x4 (row-major, float) to the rest
+  void set_next_transform(const float T16[16]) {
+    for (int k = 0; k < 12; ++k) next_T_[k] = T16[k];
+    use_next_T_ = true;
+  }
 
   // ---- root-key sharding across processes (one map shard per GPU). The caller runs the two exchanges
   // (all-to-all of the staged device buffers) between the stages; see bonxai_b200/sharded.py.
@@ -108,6 +116,8 @@ class Map {
   ScanCounters* d_sc_ = nullptr;    // head of b_table_: counters + dedupe table are cleared by ONE memset
   ScanCounters* h_status_ = nullptr;  // pinned
   u32 n_pending_ = 0;
+  float next_T_[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+  bool use_next_T_ = false;
   int rank_ = 0, world_ = 1;
   Grid* scratch_ = nullptr;  // sharded: staging grid for cells whose root another rank owns (masks only)
   ScanParams sp_ = {};       // sharded: parameters of the scan in flight

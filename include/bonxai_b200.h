@@ -165,6 +165,15 @@ BNX_API int bnx_map_insert_async_f32(bnx_map_t* m, const void* points, int64_t s
                                      const float origin[3], double max_range, int where);
 BNX_API int bnx_map_insert_async_f64(bnx_map_t* m, const void* points, int64_t stride_bytes, int64_t n,
                                      const double origin[3], double max_range, int where);
+/* insertPointCloud with the pre-step of the reference's ROS caller fused into the classify kernel
+ * (bonxai_ros/src/bonxai_server.cpp:148-171): points with a non-finite coordinate leave the cloud, the others are
+ * transformed by the row-major 4x4 float matrix sensor_to_world exactly like pcl::transformPointCloud's SSE kernel
+ * (x*c0 + (y*c1 + (z*c2 + c3)), one rounding per operation), then inserted. `points` are in the SENSOR frame,
+ * origin (= the matrix translation in the ROS node) in the world frame. async != 0: pipelined like
+ * bnx_map_insert_async_f32. Counter N of the scan excludes the dropped points. */
+BNX_API int bnx_map_insert_transformed_f32(bnx_map_t* m, const void* points, int64_t stride_bytes, int64_t n,
+                                           const float sensor_to_world[16], const float origin[3], double max_range,
+                                           int where, int async);
 /* cumulative {N, E, V, U} over every scan inserted so far (completes the queue) */
 BNX_API int bnx_map_totals(bnx_map_t* m, int64_t out[4]);
 /* addHitPoint / addMissPoint, probabilistic_map.cpp:30-54: the endpoint cell is updated now, its
