@@ -583,9 +583,10 @@ int Grid::init(double voxel_size, int ib, int lb, int cbytes) {
   d.cell_bytes = (u32)cbytes;
   d.mask_words = W;
   d.off_active = 64;
+  d.off_stamp = 16;
   d.off_touched = 64 + (u32)round_up(W * 8, 64);
-  d.off_stamp = d.off_touched + W * 8;
-  d.off_cells = (u32)round_up(d.off_stamp + 4, 128);
+  d.off_hit = d.off_touched + W * 8;
+  d.off_cells = (u32)round_up(d.off_hit + W * 8, 128);
   d.leaf_stride = (u32)round_up(d.off_cells + (size_t)cells * cbytes, 128);
   d.inner_child_off = 4 + 2 * Wi;
   d.inner_stride = (u32)round_up(d.inner_child_off + children, 4);

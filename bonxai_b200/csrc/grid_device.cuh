@@ -14,8 +14,8 @@
 //   inner pool   node = {int32 key[3]; u32 flags; u64 mask[Wi]; u32 child[8^ib]}; child 0 = EMPTY,
 //                1 = LOCKED, v >= 2 -> leaf (v-2). mask bit i mirrors child[i] >= 2 (kept for iteration
 //                and the Serialize stream).
-//   leaf pool    node = line0 {int32 origin[3]; u32 flags; pad; u64 active[W] @64}
-//                       line1 {u64 touched[W] @off_touched; u32 stamp @off_stamp}   (per-scan scratch of the map)
+//   leaf pool    node = line0 {int32 origin[3]; u32 flags; u32 stamp @16; pad; u64 active[W] @64}
+//                       line1 {u64 touched[W] @off_touched; u64 hit[W] @off_hit}   (per-scan scratch of the map)
 //                       cells[8^lb] @off_cells, cell_bytes each.
 //                Default bits (2,3), 4-byte cells: 2304 B per leaf = 18 x 128-B lines.
 //
@@ -57,7 +57,7 @@ struct GridDev {
   int ib, lb;  // INNER_BITS, LEAF_BITS
   u32 cell_bytes;
   u32 mask_words;  // u64 words of a leaf mask
-  u32 off_active, off_touched, off_stamp, off_cells;
+  u32 off_active, off_touched, off_hit, off_stamp, off_cells;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -98,6 +98,9 @@ __device__ __forceinline__ u64* leaf_active(const GridDev& g, u32 leaf) {
 }
 __device__ __forceinline__ u64* leaf_touched(const GridDev& g, u32 leaf) {
   return reinterpret_cast<u64*>(leaf_ptr(g, leaf) + g.off_touched);
+}
+__device__ __forceinline__ u64* leaf_hit(const GridDev& g, u32 leaf) {
+  return reinterpret_cast<u64*>(leaf_ptr(g, leaf) + g.off_hit);
 }
 __device__ __forceinline__ u32* leaf_stamp(const GridDev& g, u32 leaf) {
   return reinterpret_cast<u32*>(leaf_ptr(g, leaf) + g.off_stamp);

@@ -188,6 +188,10 @@ __device__ __forceinline__ unsigned long long warp_incl_scan(unsigned long long 
   return v;
 }
 
+// OR `bits` into word w of a per-scan leaf mask (touched or hit); defined with the mark kernel below
+__device__ __forceinline__ void mark_bits(const GridDev& G, u32 leaf, unsigned long long* word, unsigned long long bits, u32 seq, u32* n_list, u32* list,
+                                          u32 cap);
+
 // which root does which rank own (map sharding)? Uses the upper hash bits: the root table slot uses the lower.
 __host__ __device__ __forceinline__ u32 shard_owner(int rx, int ry, int rz, u32 world) {
   return (u32)((hash3(rx, ry, rz) >> 34) % world);
@@ -294,7 +298,13 @@ __global__ void __launch_bounds__(TPB) k_resolve(GridDev g, ScanParams p, ScanBu
   }
   __syncthreads();
   if (threadIdx.x == 0 && s_m) atomicAdd(&b.sc->sum_m, s_m);
-  if (is_end && !PENDING) b.ends[s_base_e + s_warp_e[warp] + e_excl_w] = make_uint2(leaf, ci | ((u32)e.w << 16));
+  if (is_end && !PENDING) {
+    // addHitPoint / addMissPoint (probabilistic_map.cpp:30-54) deferred to the apply pass: a hit endpoint sets its bit in
+    // the leaf's HIT mask; a miss endpoint gets exactly the update of a ray cell (max(p + miss, clamp_min), stamp), so
+    // it simply joins the touched mask. Either way the leaf is listed for the apply pass.
+    unsigned long long* word = reinterpret_cast<unsigned long long*>(e.w ? leaf_touched(g, leaf) : leaf_hit(g, leaf)) + (ci >> 6);
+    mark_bits(g, leaf, word, 1ull << (ci & 63), p.seq, &b.sc->n_touched, b.touched, p.touched_cap);
+  }
   if (mine) {
     const unsigned long long at = s_base + s_warp[warp] + (incl - mine);
     const u32 ray = (u32)(at >> 40);
@@ -412,17 +422,17 @@ __device__ __forceinline__ u32 mark_leaf(const GridDev& G, u32& inner, bool new_
   return v >= 2u ? v - 2u : leaf_create_in_inner(G, inner, ii, lx << 3, ly << 3, lz << 3);
 }
 
-// OR `bits` into word w of the leaf's touched mask. Test first (a stale L1 line only costs a redundant atomic):
-// the leaves around the sensor are hit by every ray. A word seen non-zero can never be the leaf's first touch, so
-// only writers of an (apparently) empty word need the old value back; the thread that really turns a word
-// non-zero stamps the leaf and, if nobody stamped it in this scan yet, appends it to the touched list.
-__device__ __forceinline__ void mark_bits(const GridDev& G, u32 leaf, u32 w, unsigned long long bits, u32 seq, u32* n_list, u32* list, u32 cap) {
-  unsigned long long* t = reinterpret_cast<unsigned long long*>(leaf_touched(G, leaf)) + w;
-  const unsigned long long cur = *t;
+// OR `bits` into one 64-bit word of a leaf's per-scan mask (touched, or hit). Test first (a stale L1 line only costs a
+// redundant atomic): the leaves around the sensor are hit by every ray. A word seen non-zero can never be the leaf's
+// first touch, so only writers of an (apparently) empty word need the old value back; the thread that really turns
+// a word non-zero stamps the leaf and, if nobody stamped it in this scan yet, appends it to the touched list.
+__device__ __forceinline__ void mark_bits(const GridDev& G, u32 leaf, unsigned long long* word, unsigned long long bits, u32 seq, u32* n_list, u32* list,
+                                          u32 cap) {
+  const unsigned long long cur = *word;
   if ((cur & bits) == bits) return;
   if (cur != 0ull) {
-    atomicOr(t, bits);  // result unused: a fire-and-forget reduction
-  } else if (atomicOr(t, bits) == 0ull && atomicExch(leaf_stamp(G, leaf), seq) != seq) {
+    atomicOr(word, bits);  // result unused: a fire-and-forget reduction
+  } else if (atomicOr(word, bits) == 0ull && atomicExch(leaf_stamp(G, leaf), seq) != seq) {
     const u32 at = atomicAdd(n_list, 1u);
     if (at < cap) list[at] = leaf;
   }
@@ -493,9 +503,10 @@ __global__ void __launch_bounds__(TPB, MARK_MIN_BLOCKS) k_mark(GridDev g, GridDe
         }
         if (leaf != NONE) {
           if (!SHARD || own) {
-            mark_bits(g, leaf, w, bits, p.seq, &b.sc->n_touched, b.touched, p.touched_cap);
+            mark_bits(g, leaf, reinterpret_cast<unsigned long long*>(leaf_touched(g, leaf)) + w, bits, p.seq, &b.sc->n_touched, b.touched, p.touched_cap);
           } else {
-            mark_bits(gs, leaf, w, bits, p.seq, &b.sc->n_touched2, b.touched2, p.touched2_cap);
+            mark_bits(gs, leaf, reinterpret_cast<unsigned long long*>(leaf_touched(gs, leaf)) + w, bits, p.seq, &b.sc->n_touched2, b.touched2,
+                      p.touched2_cap);
           }
         }
       }
@@ -508,34 +519,16 @@ __global__ void __launch_bounds__(TPB) k_clear_touched(GridDev g, ScanBuffers b,
   const u32 lane = threadIdx.x & 31;
   const u32 warps = gridDim.x * (TPB / 32);
   for (u32 t = blockIdx.x * (TPB / 32) + (threadIdx.x >> 5); t < n; t += warps) {
-    if (lane < 8) reinterpret_cast<unsigned long long*>(leaf_touched(g, b.touched[t]))[lane] = 0ull;
+    if (lane < 16) reinterpret_cast<unsigned long long*>(leaf_touched(g, b.touched[t]))[lane] = 0ull;  // touched[8] + hit[8] are contiguous
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // phase 4 / 5: apply
 // ------------------------------------------------------------------------------------------------
-// addHitPoint / addMissPoint on the winning endpoint voxels, probabilistic_map.cpp:30-54
-__global__ void __launch_bounds__(TPB) k_apply_endpoints(GridDev g, ScanParams p, ScanBuffers b) {
-  if (g.ctr->error | b.sc->overflow) return;
-  if (b.gate && (b.gate[0] | b.gate[1])) return;  // some rank of a sharded map must repeat the scan
-  const u32 n = b.sc->n_endpoints;
-  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const uint2 rec = b.ends[i];
-    const u32 leaf = rec.x, ci = rec.y & 0xFFFFu, type = rec.y >> 16;
-    u32* cell = reinterpret_cast<u32*>(leaf_cells(g, leaf)) + ci;
-    unsigned long long* act = reinterpret_cast<unsigned long long*>(leaf_active(g, leaf)) + (ci >> 6);
-    const unsigned long long bit = 1ull << (ci & 63);
-    const bool on = (*act & bit) != 0;
-    const u32 word = on ? *cell : 0u;  // a missing cell is created as CellT{}: id 0, probability 0
-    i32 prob = (i32)word >> 4;
-    prob = type ? max(prob + p.miss, p.cmin) : min(prob + p.hit, p.cmax);
-    *cell = ((u32)prob << 4) | p.c;
-    if (!on) atomicOr(act, bit);
-  }
-}
-
-// clearPoint over the union of all rays, probabilistic_map.cpp:81-89: one warp per touched leaf
+// One warp per listed leaf: hit endpoints (addHitPoint, probabilistic_map.cpp:30-41) and the union of all rays + miss
+// endpoints (clearPoint / addMissPoint, :43-54,81-89). Hit endpoints are never stale (resolve filtered them) and win
+// over ray cells, like the reference where they are stamped before any ray is cast.
 __global__ void __launch_bounds__(TPB) k_apply_leaves(GridDev g, ScanParams p, ScanBuffers b) {
   // last kernel of the scan: the host reads counters + grid counters with one copy
   if (blockIdx.x == 0 && threadIdx.x == 0) b.sc->gc = *g.ctr;
@@ -547,46 +540,57 @@ __global__ void __launch_bounds__(TPB) k_apply_leaves(GridDev g, ScanParams p, S
   // the masks of the NEXT leaf of this warp are loaded while the current leaf's cells are in flight
   u32 t = blockIdx.x * (TPB / 32) + (threadIdx.x >> 5);
   u32 leaf_n = t < n ? b.touched[t] : NONE;
-  unsigned long long tw_n = 0, aw_n = 0;
+  unsigned long long tw_n = 0, aw_n = 0, hw_n = 0;
   if (leaf_n != NONE && lane < 8) {
     tw_n = reinterpret_cast<const unsigned long long*>(leaf_touched(g, leaf_n))[lane];
+    hw_n = reinterpret_cast<const unsigned long long*>(leaf_hit(g, leaf_n))[lane];
     aw_n = reinterpret_cast<const unsigned long long*>(leaf_active(g, leaf_n))[lane];
   }
   for (; t < n; t += warps) {
     const u32 leaf = leaf_n;
-    const unsigned long long tw = tw_n, aw = aw_n;
+    const unsigned long long tw = tw_n, aw = aw_n, hw = hw_n;
     unsigned long long* touched = reinterpret_cast<unsigned long long*>(leaf_touched(g, leaf));
+    unsigned long long* hitm = reinterpret_cast<unsigned long long*>(leaf_hit(g, leaf));
     unsigned long long* active = reinterpret_cast<unsigned long long*>(leaf_active(g, leaf));
     u32* cells = reinterpret_cast<u32*>(leaf_cells(g, leaf));
     leaf_n = t + warps < n ? b.touched[t + warps] : NONE;
     if (leaf_n != NONE && lane < 8) {
       tw_n = reinterpret_cast<const unsigned long long*>(leaf_touched(g, leaf_n))[lane];
+      hw_n = reinterpret_cast<const unsigned long long*>(leaf_hit(g, leaf_n))[lane];
       aw_n = reinterpret_cast<const unsigned long long*>(leaf_active(g, leaf_n))[lane];
     }
     // lane owns cells it*32 + lane, it = 0..15 (coalesced 128-B rows); bit `it` of mine/on = that cell touched/ON
-    u32 mine = 0, on = 0;
+    u32 mine = 0, on = 0, hit = 0;
 #pragma unroll
     for (u32 w = 0; w < 8; ++w) {
       const unsigned long long t64 = __shfl_sync(0xffffffffu, tw, w);
       const unsigned long long a64 = __shfl_sync(0xffffffffu, aw, w);
+      const unsigned long long h64 = __shfl_sync(0xffffffffu, hw, w);
       mine |= (u32)((t64 >> lane) & 1ull) << (2 * w) | (u32)((t64 >> (32 + lane)) & 1ull) << (2 * w + 1);
       on |= (u32)((a64 >> lane) & 1ull) << (2 * w) | (u32)((a64 >> (32 + lane)) & 1ull) << (2 * w + 1);
+      hit |= (u32)((h64 >> lane) & 1ull) << (2 * w) | (u32)((h64 >> (32 + lane)) & 1ull) << (2 * w + 1);
     }
+    mine |= hit;
     // all loads of this leaf are issued before the first use (memory-level parallelism)
     u32 word[16];
 #pragma unroll
     for (u32 it = 0; it < 16; ++it) word[it] = ((mine & on) >> it) & 1u ? cells[it * 32 + lane] : 0u;
 #pragma unroll
     for (u32 it = 0; it < 16; ++it) {
-      if (((mine >> it) & 1u) && (word[it] & 0xFu) != p.c) {
+      if ((hit >> it) & 1u) {
+        const i32 prob = min(((i32)word[it] >> 4) + p.hit, p.cmax);
+        cells[it * 32 + lane] = ((u32)prob << 4) | p.c;
+        ++changed;
+      } else if (((mine >> it) & 1u) && (word[it] & 0xFu) != p.c) {
         const i32 prob = max(((i32)word[it] >> 4) + p.miss, p.cmin);
         cells[it * 32 + lane] = ((u32)prob << 4) | p.c;
         ++changed;
       }
     }
-    if (lane < 8 && tw) {
-      active[lane] = aw | tw;
+    if (lane < 8 && (tw | hw)) {
+      active[lane] = aw | tw | hw;
       touched[lane] = 0ull;
+      hitm[lane] = 0ull;
     }
   }
   for (int o = 16; o; o >>= 1) changed += __shfl_xor_sync(0xffffffffu, changed, o);
@@ -719,7 +723,7 @@ __global__ void __launch_bounds__(TPB) k_shard_merge(GridDev g, ScanParams p, Sc
     if (leaf == NONE) continue;
     if (lane < 8) {
       const unsigned long long bits = reinterpret_cast<const unsigned long long*>(block + (size_t)j * 5 + 1)[lane];
-      if (bits) mark_bits(g, leaf, lane, bits, p.seq, &b.sc->n_touched, b.touched, p.touched_cap);
+      if (bits) mark_bits(g, leaf, reinterpret_cast<unsigned long long*>(leaf_touched(g, leaf)) + lane, bits, p.seq, &b.sc->n_touched, b.touched, p.touched_cap);
     }
   }
 }
@@ -837,7 +841,6 @@ int Map::reserve_scan(i64 n, i64 stride_bytes, double max_range) {
   const size_t np = (size_t)n + n_pending_ + 32;
   BNX_TRY(b_ep_.reserve(np * sizeof(int4)));
   BNX_TRY(b_slot_.reserve(np * 4));
-  BNX_TRY(b_ends_.reserve(np * sizeof(uint2)));
   BNX_TRY(b_rays_.reserve(np * sizeof(int4)));
   // [ScanCounters | table u32[slots] | keys u64[slots]] — contiguous so that one memset clears all of it
   const u64 slots = table_slots(n);
@@ -854,7 +857,6 @@ int Map::reserve_scan(i64 n, i64 stride_bytes, double max_range) {
   buf_.keys = reinterpret_cast<unsigned long long*>(b_table_.as<unsigned char>() + SC_BYTES + slots * 4);
   buf_.ep = b_ep_.as<int4>();
   buf_.slot_of = b_slot_.as<u32>();
-  buf_.ends = b_ends_.as<uint2>();
   buf_.rays = b_rays_.as<int4>();
   buf_.tile_first = b_tiles_.as<u32>();
   buf_.touched = b_touched_.as<u32>();
@@ -980,7 +982,6 @@ int Map::launch_scan(const void* d_points, i64 stride_bytes, bool f64, ScanParam
   if (profiling && first_attempt) cudaEventRecord(ev_[3], s);
   note_launch(), k_mark<false><<<persistent, TPB, 0, s>>>(g, g, p, buf_);
   if (profiling && first_attempt) cudaEventRecord(ev_[4], s);
-  note_launch(), k_apply_endpoints<<<std::min(persistent, blocks_for(n + n_pending_ + 1)), TPB, 0, s>>>(g, p, buf_);
   note_launch(), k_apply_leaves<<<persistent, TPB, 0, s>>>(g, p, buf_);
   BNX_CUDA(cudaGetLastError());
   if (profiling && first_attempt) cudaEventRecord(ev_[5], s);
@@ -992,7 +993,7 @@ void Map::account(const ScanCounters& st, i64 n, i64 pending, i64 retries) {
   counters[0] = n;
   counters[1] = (i64)st.n_endpoints + pending;
   counters[2] = (i64)st.sum_m + n;
-  counters[3] = (i64)st.n_endpoints + st.n_changed;
+  counters[3] = (i64)st.n_changed;  // endpoints are applied (and counted) by the leaf pass too
   counters[4] = st.n_touched;
   counters[5] = retries;
   counters[6] = (i64)(st.ray_chunk >> 40);
@@ -1296,7 +1297,6 @@ int Map::shard_finish(const void* flags_reduced, int* retry) {
   const int persistent = sm_count() * 8;
   const GridDev g = grid.dev();
   buf_.gate = static_cast<const u32*>(flags_reduced);
-  note_launch(), k_apply_endpoints<<<persistent, TPB, 0, s>>>(g, sp_, buf_);
   note_launch(), k_apply_leaves<<<persistent, TPB, 0, s>>>(g, sp_, buf_);
   BNX_CUDA(cudaGetLastError());
   u32* h_flags = reinterpret_cast<u32*>(reinterpret_cast<unsigned char*>(h_status_) + sizeof(ScanCounters));
@@ -1338,7 +1338,7 @@ int Map::shard_finish(const void* flags_reduced, int* retry) {
   counters[0] = sp_.n;
   counters[1] = st.n_endpoints;
   counters[2] = (i64)st.sum_m;  // ray cells of the rays this rank cast; the caller adds N once over all ranks
-  counters[3] = (i64)st.n_endpoints + st.n_changed;
+  counters[3] = (i64)st.n_changed;
   counters[4] = st.n_touched;
   counters[5] = shard_retries_;
   counters[6] = (i64)(st.ray_chunk >> 40);

@@ -57,7 +57,6 @@ struct ScanBuffers {
   u32* slot_of;      // per point: its slot in the dedupe table
   u32* table;        // endpoint dedupe table: lowest point index per voxel
   unsigned long long* keys;  // packed-key flavour of the table
-  uint2* ends;       // per updated endpoint: {leaf, cell index | type << 16}
   int4* rays;        // per ray with >= 1 cell: end voxel xyz + first chunk
   u32* tile_first;   // per 32-chunk tile: ray that owns the tile's first chunk
   u32* touched;      // leaves first touched in this scan
@@ -112,7 +111,7 @@ class Map {
   int run_scan(const void* d_points, i64 stride_bytes, bool f64, const ScanParams& base, bool reuse_classify);
 
   ScanBuffers buf_ = {};
-  DevBuf b_pts_, b_ep_, b_slot_, b_table_, b_ends_, b_rays_, b_tiles_, b_touched_, b_pending_, b_q_xyz_, b_q_out_;
+  DevBuf b_pts_, b_ep_, b_slot_, b_table_, b_rays_, b_tiles_, b_touched_, b_pending_, b_q_xyz_, b_q_out_;
   ScanCounters* d_sc_ = nullptr;    // head of b_table_: counters + dedupe table are cleared by ONE memset
   ScanCounters* h_status_ = nullptr;  // pinned
   u32 n_pending_ = 0;
