@@ -448,6 +448,12 @@ __global__ void __launch_bounds__(TPB, MARK_MIN_BLOCKS) k_mark(GridDev g, GridDe
   const u32 n_rays = (u32)(rc >> 40);
   const u32 total = (u32)(rc & CHUNK_FIELD);
   if (b.sc->overflow | *b.poison) return;
+  // pipelined insert: the dedupe table was last read by k_resolve; leave it zeroed for the next scan's k_classify
+  // (saves a clearing launch per scan). Skipped when the pipeline is frozen, like every other write.
+  if (p.clean16) {
+    uint4* tab = reinterpret_cast<uint4*>(b.table);
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < p.clean16; i += gridDim.x * blockDim.x) tab[i] = make_uint4(0, 0, 0, 0);
+  }
   const u32 lane = threadIdx.x & 31;
   const u32 warps = gridDim.x * (TPB / 32);
   for (u32 tile = blockIdx.x * (TPB / 32) + (threadIdx.x >> 5); (u64)tile * 32 < total; tile += warps) {
@@ -629,6 +635,10 @@ __global__ void __launch_bounds__(TPB) k_apply_leaves(GridDev g, ScanParams p, S
   r->ray_chunk = sc->ray_chunk;
   __threadfence_system();
   r->id = p.async_id;
+  if (!err) {  // healthy: hand zeroed counters to the next scan (a failed scan's counters stay for the host)
+    uint4* z = reinterpret_cast<uint4*>(b.sc);
+    for (u32 k = 0; k < sizeof(ScanCounters) / 16; ++k) z[k] = make_uint4(0, 0, 0, 0);
+  }
 }
 
 // pipelined insert: clears the scan counters + dedupe table like the memset of the synchronous path, unless the
@@ -844,7 +854,9 @@ int Map::reserve_scan(i64 n, i64 stride_bytes, double max_range) {
   BNX_TRY(b_rays_.reserve(np * sizeof(int4)));
   // [ScanCounters | table u32[slots] | keys u64[slots]] — contiguous so that one memset clears all of it
   const u64 slots = table_slots(n);
+  const void* table_before = b_table_.p;
   BNX_TRY(b_table_.reserve(SC_BYTES + slots * 12));
+  if (b_table_.p != table_before) clean_slots_ = 0;  // fresh allocation: nothing is known to be zero
   // 32-chunk tiles: estimated from the longest possible ray, grown on overflow
   double cells = std::isfinite(max_range) ? std::ceil(max_range * grid.inv_resolution) + 2.0 : 512.0;
   cells = std::min(cells, 4096.0);
@@ -883,6 +895,7 @@ int Map::build_params(i64 n, const double origin[3], double max_range, ScanParam
   p.n = (u32)n;
   p.world = 1;
   p.async_id = NONE;
+  p.clean16 = 0;
   p.use_transform = use_next_T_ ? 1u : 0u;
   for (int k = 0; k < 12; ++k) p.T[k] = next_T_[k];
   use_next_T_ = false;
@@ -959,8 +972,13 @@ int Map::launch_scan(const void* d_points, i64 stride_bytes, bool f64, ScanParam
     const size_t bytes = n > 0 ? SC_BYTES + slots * (p.packed ? 12 : 4) : SC_BYTES;
     if (p.async_id == NONE) {
       BNX_CUDA(cudaMemsetAsync(d_sc_, 0, bytes, s));
+      clean_slots_ = 0;  // the synchronous path leaves a used table behind
     } else {
-      note_launch(), k_begin_scan<<<std::min<int>(persistent, blocks_for((i64)(bytes / 16))), TPB, 0, s>>>(buf_, reinterpret_cast<uint4*>(d_sc_), (u32)(bytes / 16));
+      if (slots > clean_slots_) {
+        note_launch(), k_begin_scan<<<std::min<int>(persistent, blocks_for((i64)(bytes / 16))), TPB, 0, s>>>(buf_, reinterpret_cast<uint4*>(d_sc_), (u32)(bytes / 16));
+      }
+      p.clean16 = (u32)(slots * 12 / 16);  // k_mark zeroes table + keys again, the epilogue the counters
+      clean_slots_ = slots;
     }
     if (n > 0) {
       const unsigned char* pts = static_cast<const unsigned char*>(d_points);
@@ -1006,6 +1024,7 @@ int Map::run_scan(const void* d_points, i64 stride_bytes, bool f64, const ScanPa
   cudaStream_t s = grid.stream();
   ScanParams p = base;
   p.async_id = NONE;
+  p.clean16 = 0;  // a retry re-reads the dedupe table: the synchronous path clears it with its own memset
   const int persistent = sm_count() * 8;
   i64 retries = 0;
   for (;; ++retries) {
@@ -1060,13 +1079,37 @@ int Map::insert_async(const void* points, i64 stride_bytes, i64 n, bool f64, con
   if (n_pending_ || world_ > 1) return insert(points, stride_bytes, n, f64, origin, max_range, where);  // rare paths stay synchronous
   cudaStream_t s = grid.stream();
   if (queue_.size() >= RING / 2) BNX_TRY(drain());
-  // head-room check on the newest record the device has published (no synchronisation): grow early
+  // Flow control without a CUDA sync: at most MAX_IN_FLIGHT scans are queued ahead of the newest record the device
+  // has published in the host ring; that bounds how stale the pool head-room information below can be.
+  if (queue_.size() > done_upto_ + MAX_IN_FLIGHT) {
+    const u32 wait_id = queue_[queue_.size() - 1 - MAX_IN_FLIGHT].p.async_id;
+    const volatile AsyncRecord* r = &h_ring_[wait_id & (RING - 1)];
+    unsigned spins = 0;
+    while (r->id != wait_id) {
+      if (++spins > (1u << 14)) {  // never spin on a wedged device: fall back to a real synchronisation
+        if (cudaStreamQuery(s) != cudaErrorNotReady) break;
+        spins = 0;
+      }
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    }
+  }
+  // head-room check on the newest published record: grow early, so that a queued scan (almost) never runs short
   if (!queue_.empty()) {
-    for (size_t k = queue_.size(); k-- > 0;) {
+    for (size_t k = queue_.size(); k-- > done_upto_;) {
       const AsyncRecord& r = h_ring_[queue_[k].p.async_id & (RING - 1)];
       if (r.id != queue_[k].p.async_id) continue;
+      done_upto_ = k + 1;
       const GridDev g = grid.dev();
-      if (r.error || (u64)r.n_leaves * 2 > g.leaf_cap || (u64)r.n_inner * 2 > g.inner_cap || (u64)r.n_roots * 2 > (u64)g.root_mask + 1) BNX_TRY(drain());
+      const u64 ahead = queue_.size() - k;  // scans that may still allocate before we look again
+      const u64 leaves_ahead = (u64)r.n_leaves + ahead * max_leaf_growth_, inner_ahead = (u64)r.n_inner + ahead * 64;
+      if (r.error || leaves_ahead * 2 > g.leaf_cap || inner_ahead * 2 > g.inner_cap || (u64)(r.n_roots + ahead * 64) * 2 > (u64)g.root_mask + 1) {
+        BNX_TRY(drain());
+      } else if (k > 0) {
+        const AsyncRecord& q = h_ring_[queue_[k - 1].p.async_id & (RING - 1)];
+        if (q.id == queue_[k - 1].p.async_id && r.n_leaves > q.n_leaves) max_leaf_growth_ = std::max<u64>(max_leaf_growth_, r.n_leaves - q.n_leaves);
+      }
       break;
     }
   }
@@ -1116,6 +1159,7 @@ int Map::drain() {
   BNX_TRY(grid.read_counters(&gc));  // synchronises the stream
   std::vector<Queued> q;
   q.swap(queue_);
+  done_upto_ = 0;
   size_t done = q.size();
   if (gc.error) {
     // frozen at the first scan that ran short: everything before it is applied, nothing after it is

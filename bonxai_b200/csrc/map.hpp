@@ -25,6 +25,7 @@ struct ScanParams {
   u32 leaf_cap2;               // sharded: slots per peer block of the leaf-mask exchange
   u32 touched2_cap;            // sharded: entries of the scratch-grid touched list
   u32 async_id;                // pipelined insert: serial of this scan (NONE for the synchronous path)
+  u32 clean16;                 // pipelined insert: 16-byte units of dedupe table k_mark zeroes for the next scan
   u32 use_transform;           // fused ROS pre-step: drop non-finite points, then T * p in float before classifying
   float T[12];                 // rows 0..2 of the 4x4 sensor->world matrix
 };
@@ -134,6 +135,10 @@ class Map {
   AsyncRecord* h_ring_ = nullptr;  // pinned + mapped
   AsyncRecord* d_ring_ = nullptr;
   u32 async_next_ = 0;
+  static constexpr size_t MAX_IN_FLIGHT = 32;  // scans queued ahead of the newest published record
+  size_t done_upto_ = 0;                       // queue_ entries whose record has been seen
+  u64 max_leaf_growth_ = 2048;                 // largest per-scan leaf allocation seen so far (head-room estimate)
+  u64 clean_slots_ = 0;  // dedupe-table slots known to be zero (left clean by the previous pipelined scan)
   cudaStream_t copy_stream_ = nullptr;
   cudaEvent_t ev_copied_[2] = {nullptr, nullptr}, ev_consumed_[2] = {nullptr, nullptr};
   bool stage_used_[2] = {false, false};
