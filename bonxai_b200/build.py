@@ -56,7 +56,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}")
-    link = [_nvcc(), "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs]
+    link = [_nvcc(), "-shared", "-cudart", "static", "-Xlinker", "-ldl", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs]
     subprocess.run(link, check=True)
     return LIB
 

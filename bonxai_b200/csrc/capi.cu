@@ -337,6 +337,22 @@ int bnx_map_publish_occupied_f32(bnx_map_t* h, double z_min, double z_max, float
   BNX_TRY(h->m.drain());
   return h->m.grid.dump_points_f32(points, stride_floats, 1, z_min, z_max, cap, count, where, h->m.options[4]);
 }
+int bnx_nccl_unique_id(const char* nccl_library_path, void* out128) {
+  BNX_REQUIRE(out128 != nullptr, "null output");
+  return Map::nccl_unique_id(nccl_library_path, out128);
+}
+int bnx_map_shard_comm_init(bnx_map_t* h, const char* nccl_library_path, const void* unique_id128, int rank, int world) {
+  BNX_HANDLE(h);
+  DeviceGuard dg(h->m.grid.device);
+  return h->m.shard_comm_init(nccl_library_path, unique_id128, rank, world);
+}
+int bnx_map_shard_insert(bnx_map_t* h, const void* points, int64_t stride_bytes, int64_t n, int is_f64, uint32_t index_base, int64_t n_max,
+                         const double origin[3], double max_range, int where, int async) {
+  BNX_HANDLE(h);
+  BNX_REQUIRE(origin != nullptr, "null origin");
+  DeviceGuard dg(h->m.grid.device);
+  return h->m.shard_insert(points, stride_bytes, n, is_f64 != 0, index_base, n_max, origin, max_range, where, async != 0);
+}
 int bnx_map_counters(bnx_map_t* h, int64_t out[8]) {
   BNX_HANDLE(h);
   BNX_TRY(h->m.drain());

@@ -667,6 +667,7 @@ int Grid::recover(const GridCounters& seen) {
   fix.n_inner = std::min(seen.n_inner, dev_.inner_cap);
   fix.error = 0;
   fix.failed_id = NONE;
+  fix.failed_ovf = 0;
   fix.done_blocks = 0;
   if (fix.n_free < 0) fix.n_free = 0;
   *h_ctr_ = fix;

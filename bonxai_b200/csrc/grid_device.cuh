@@ -39,7 +39,7 @@ struct GridCounters {
   int n_free;    // entries on the leaf free list
   u32 failed_id;    // async pipeline: id of the first scan that failed (NONE when healthy)
   u32 done_blocks;  // last-block ticket of the scan epilogue
-  u32 pad;
+  u32 failed_ovf;   // sharded pipeline: the all-reduced overflow bits of the scan that failed
 };
 
 struct GridDev {

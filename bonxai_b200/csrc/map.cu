@@ -20,6 +20,8 @@
 // pools have grown; phases 4-5 cannot fail.
 #include "map.hpp"
 
+#include "nccl_dyn.hpp"
+
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -211,7 +213,7 @@ __global__ void __launch_bounds__(TPB) k_resolve(GridDev g, ScanParams p, ScanBu
   __shared__ u32 s_base_e;
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (MODE == 0 && *b.poison) return;  // an earlier pipelined scan ran short: freeze until the host recovers
+  if (MODE != 1 && *b.poison) return;  // an earlier pipelined scan ran short: freeze until the host recovers
   if (threadIdx.x == 0) s_m = 0;
 
   bool is_end = false, winner = false;
@@ -616,10 +618,12 @@ __global__ void __launch_bounds__(TPB) k_apply_leaves(GridDev g, ScanParams p, S
   __threadfence();
   const volatile ScanCounters* sc = b.sc;
   u32 err = g.ctr->error;
-  if (sc->overflow && !err) {
+  const u32 gate_ovf = b.gate ? b.gate[1] : 0u;
+  if ((sc->overflow || (b.gate && (b.gate[0] | gate_ovf))) && !err) {  // this rank, or (sharded) any rank, ran short
     err = ERR_SCAN;
     atomicOr(&g.ctr->error, ERR_SCAN);
   }
+  if (err && g.ctr->failed_id == NONE) g.ctr->failed_ovf = gate_ovf | sc->overflow;
   if (err && g.ctr->failed_id == NONE) g.ctr->failed_id = p.async_id;
   AsyncRecord* r = b.ring + (p.async_id & (RING_SIZE - 1u));
   r->error = err;
@@ -655,7 +659,7 @@ __global__ void __launch_bounds__(TPB) k_begin_scan(ScanBuffers b, uint4* base, 
 // record = {x, y, z, global point index << 1 | type}; slot 0 of a peer block carries the count
 __global__ void __launch_bounds__(TPB) k_shard_bucket(ScanParams p, ScanBuffers b, u32 index_base, int4* send, u32 cap) {
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= p.n) return;
+  if (i >= p.n || *b.poison) return;
   const u32 slot = b.slot_of[i];
   if (slot == NONE || b.table[slot] != ~i) return;  // dropped, or not the lowest local index of its voxel
   const int4 e = b.ep[i];
@@ -672,7 +676,7 @@ __global__ void __launch_bounds__(TPB) k_shard_bucket(ScanParams p, ScanBuffers 
 // exchange 1, receiver: lowest global index per endpoint voxel over the records of all ranks
 __global__ void __launch_bounds__(TPB) k_shard_dedupe(ScanParams p, ScanBuffers b, u32 count) {
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= count) return;
+  if (i >= count || *b.poison) return;
   const u32 j = i % p.rec_cap;
   if (j == 0u || j > (u32)b.recs[i - j].x) return;
   const int4 e = b.recs[i];
@@ -722,6 +726,7 @@ __global__ void __launch_bounds__(TPB) k_shard_merge(GridDev g, ScanParams p, Sc
   const u32 lane = threadIdx.x & 31;
   const u32 warps = gridDim.x * (TPB / 32);
   const u32 slots = p.world * cap;
+  if (*b.poison) return;
   for (u32 t = blockIdx.x * (TPB / 32) + (threadIdx.x >> 5); t < slots; t += warps) {
     const u32 j = t % cap;
     const int4* block = recv + (size_t)(t - j) * 5;
@@ -803,6 +808,7 @@ Map::~Map() {
     if (ev_consumed_[k]) cudaEventDestroy(ev_consumed_[k]);
   }
   if (h_ring_) cudaFreeHost(h_ring_);
+  if (comm_) nccl_api(nullptr).CommDestroy(static_cast<ncclComm_t>(comm_));
   delete scratch_;
   if (h_status_) cudaFreeHost(h_status_);
   for (auto& e : ev_)
@@ -1152,6 +1158,7 @@ int Map::insert_async(const void* points, i64 stride_bytes, i64 n, bool f64, con
 }
 
 int Map::drain() {
+  if (!squeue_.empty()) return shard_drain();
   if (queue_.empty()) return BNX_OK;
   cudaStream_t s = grid.stream();
   BNX_CUDA(cudaMemcpyAsync(h_status_, d_sc_, sizeof(ScanCounters), cudaMemcpyDeviceToHost, s));
@@ -1235,7 +1242,7 @@ int Map::shard_begin(const void* points, i64 stride_bytes, i64 n, bool f64, u32 
   BNX_REQUIRE(n_pending_ == 0, "shard_begin: addHitPoint/addMissPoint queues are not supported on a sharded map");
   BNX_REQUIRE(origin && send_records && cap_records >= 2, "shard_begin: null argument");
   BNX_REQUIRE(f64 ? (stride_bytes >= 24 && stride_bytes % 8 == 0) : (stride_bytes >= 12 && stride_bytes % 4 == 0), "shard_begin: bad stride");
-  BNX_TRY(drain());
+  if (!queue_.empty()) BNX_TRY(drain());  // single-GPU pipeline first; the sharded queue is drained collectively
   cudaStream_t s = grid.stream();
   scratch_->set_stream(s);
   const i64 slots = (i64)world_ * cap_records;
@@ -1392,6 +1399,178 @@ int Map::shard_finish(const void* flags_reduced, int* retry) {
   BNX_TRY(scratch_->read_counters(&sgc));
   BNX_TRY(scratch_->maintain(sgc));
   return grid.maintain(st.gc);
+}
+
+// ---- native driver of the sharded protocol (NCCL resolved at run time)
+int Map::nccl_unique_id(const char* nccl_path, void* out128) {
+  const NcclApi& api = nccl_api(nccl_path);
+  if (!api.ok) {
+    set_error("NCCL could not be loaded (libnccl.so.2)");
+    return BNX_ERR_UNSUPPORTED;
+  }
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId id;
+  BNX_NCCL(api, api.GetUniqueId(&id));
+  std::memcpy(out128, &id, 128);
+  return BNX_OK;
+}
+
+int Map::shard_comm_init(const char* nccl_path, const void* unique_id128, int rank, int world) {
+  BNX_REQUIRE(unique_id128 != nullptr, "shard_comm_init: null id");
+  const NcclApi& api = nccl_api(nccl_path);
+  if (!api.ok) {
+    set_error("NCCL could not be loaded (libnccl.so.2)");
+    return BNX_ERR_UNSUPPORTED;
+  }
+  BNX_TRY(shard_config(rank, world));
+  ncclUniqueId id;
+  std::memcpy(&id, unique_id128, 128);
+  ncclComm_t comm = nullptr;
+  BNX_NCCL(api, api.CommInitRank(&comm, world, id, rank));
+  comm_ = comm;
+  BNX_TRY(x_flags_.reserve(64));
+  return BNX_OK;
+}
+
+// block o of `send` goes to rank o, block r of `recv` comes from rank r: grouped ncclSend/ncclRecv over NVLink
+int Map::all_to_all(const void* send, void* recv, size_t block_bytes) {
+  const NcclApi& api = nccl_api(nullptr);
+  ncclComm_t comm = static_cast<ncclComm_t>(comm_);
+  cudaStream_t s = grid.stream();
+  BNX_NCCL(api, api.GroupStart());
+  for (int peer = 0; peer < world_; ++peer) {
+    BNX_NCCL(api, api.Send(static_cast<const char*>(send) + (size_t)peer * block_bytes, block_bytes, ncclChar, peer, comm, s));
+    BNX_NCCL(api, api.Recv(static_cast<char*>(recv) + (size_t)peer * block_bytes, block_bytes, ncclChar, peer, comm, s));
+  }
+  BNX_NCCL(api, api.GroupEnd());
+  return BNX_OK;
+}
+
+int Map::shard_insert(const void* points, i64 stride_bytes, i64 n, bool f64, u32 index_base, i64 n_max, const double origin[3], double max_range,
+                      int where, bool async) {
+  BNX_REQUIRE(comm_ != nullptr && world_ > 1, "shard_insert: call shard_comm_init first");
+  BNX_REQUIRE(n_max >= n, "shard_insert: n_max must be the largest slice of the scan over all ranks");
+  const NcclApi& api = nccl_api(nullptr);
+  cudaStream_t s = grid.stream();
+  if (!async) BNX_TRY(drain());
+  if (async && squeue_.size() >= 64) BNX_TRY(drain());  // same count on every rank: draining stays collective
+  // equal-split exchange buffers (all ranks compute the same capacities from n_max)
+  const i64 want_rec = std::max<i64>(cap_rec_, n_max + 2);
+  if (want_rec != cap_rec_ || !x_send1_.p) {
+    if (async) BNX_TRY(drain());
+    cap_rec_ = want_rec;
+    BNX_TRY(x_send1_.reserve((size_t)world_ * cap_rec_ * 16));
+    BNX_TRY(x_recv1_.reserve((size_t)world_ * cap_rec_ * 16));
+  }
+  if ((size_t)world_ * cap_leaf_ * 80 > x_send2_.bytes) {
+    if (async) BNX_TRY(drain());
+    BNX_TRY(x_send2_.reserve((size_t)world_ * cap_leaf_ * 80));
+    BNX_TRY(x_recv2_.reserve((size_t)world_ * cap_leaf_ * 80));
+  }
+  u32* flags = x_flags_.as<u32>();
+  const u32 my_async = async ? async_next_++ : NONE;
+  BNX_TRY(shard_begin(points, stride_bytes, n, f64, index_base, origin, max_range, x_send1_.p, cap_rec_, where));
+  sp_.async_id = my_async;
+  BNX_TRY(all_to_all(x_send1_.p, x_recv1_.p, (size_t)cap_rec_ * 16));
+  for (;;) {
+    BNX_TRY(shard_resolve_mark(x_recv1_.p, x_send2_.p, cap_leaf_));
+    BNX_TRY(all_to_all(x_send2_.p, x_recv2_.p, (size_t)cap_leaf_ * 80));
+    BNX_TRY(shard_merge(x_recv2_.p, flags));
+    BNX_NCCL(api, api.AllReduce(flags, flags, 4, ncclUint32, ncclMax, static_cast<ncclComm_t>(comm_), s));
+    if (async) {
+      buf_.gate = flags;
+      note_launch(), k_apply_leaves<<<sm_count() * 8, TPB, 0, s>>>(grid.dev(), sp_, buf_);
+      BNX_CUDA(cudaGetLastError());
+      buf_.gate = nullptr;
+      ShardQueued q;
+      q.points = points;
+      q.stride = stride_bytes;
+      q.n = n;
+      q.n_max = n_max;
+      q.f64 = f64;
+      q.index_base = index_base;
+      q.async_id = my_async;
+      q.c = sp_.c;
+      std::memcpy(q.origin, origin, sizeof(q.origin));
+      q.max_range = max_range;
+      q.where = where;
+      squeue_.push_back(q);
+      if (++update_count == 4) update_count = 1;
+      return BNX_OK;
+    }
+    int retry = 0;
+    BNX_TRY(shard_finish(flags, &retry));
+    if (!retry) return BNX_OK;
+    if (retry & (int)(OVF_LEAVES << 8)) {  // every rank saw the same reduced flags: same growth everywhere
+      cap_leaf_ *= 4;
+      BNX_TRY(x_send2_.reserve((size_t)world_ * cap_leaf_ * 80));
+      BNX_TRY(x_recv2_.reserve((size_t)world_ * cap_leaf_ * 80));
+    }
+    if (retry & (int)(OVF_RECORDS << 8)) {
+      set_error("sharded insert: endpoint record exchange overflowed (n_max too small)");
+      return BNX_ERR_INVALID;
+    }
+  }
+}
+
+int Map::shard_drain() {
+  cudaStream_t s = grid.stream();
+  BNX_CUDA(cudaMemcpyAsync(h_status_, d_sc_, sizeof(ScanCounters), cudaMemcpyDeviceToHost, s));
+  GridCounters gc;
+  BNX_TRY(grid.read_counters(&gc));  // synchronises the stream
+  std::vector<ShardQueued> q;
+  q.swap(squeue_);
+  size_t done = q.size();
+  if (gc.error) {
+    done = 0;
+    while (done < q.size() && q[done].async_id != gc.failed_id) ++done;
+  }
+  for (size_t k = 0; k < done; ++k) {
+    const AsyncRecord& r = h_ring_[q[k].async_id & (RING - 1)];
+    counters[0] = q[k].n;
+    counters[1] = r.n_endpoints;
+    counters[2] = (i64)r.sum_m;
+    counters[3] = r.n_changed;
+    counters[4] = r.n_touched;
+    counters[5] = 0;
+    counters[6] = (i64)(r.ray_chunk >> 40);
+    counters[7] = (i64)(r.ray_chunk & CHUNK_FIELD);
+    for (int j = 0; j < 4; ++j) totals[j] += counters[j];
+  }
+  GridCounters sgc;
+  BNX_TRY(scratch_->read_counters(&sgc));
+  if (!gc.error) {
+    BNX_TRY(scratch_->maintain(sgc));
+    return grid.maintain(gc);
+  }
+  // every rank is frozen at the same scan (the flags were all-reduced): drop its marks, grow what was short on
+  // this rank, then replay the rest of the queue with synchronous (collective) inserts
+  const ScanCounters st = *h_status_;
+  if ((st.overflow | gc.failed_ovf) & OVF_CHUNKS) {
+    set_error("insert: more than 2^32 ray chunks in one scan");
+    return BNX_ERR_UNSUPPORTED;
+  }
+  if (st.n_touched) {
+    note_launch(), k_clear_touched<<<sm_count() * 8, TPB, 0, s>>>(grid.dev(), buf_, std::min<u32>(st.n_touched, (u32)(b_touched_.bytes / 4)));
+    BNX_CUDA(cudaGetLastError());
+    BNX_CUDA(cudaStreamSynchronize(s));
+  }
+  BNX_TRY(grid.recover(gc));
+  if (sgc.error) BNX_TRY(scratch_->recover(sgc));
+  if ((st.overflow | gc.failed_ovf) & OVF_TILES) {
+    const u64 chunks = st.ray_chunk & CHUNK_FIELD;
+    BNX_TRY(b_tiles_.reserve((size_t)(std::max<u64>(chunks, b_tiles_.bytes / 4 * 32) * 2 / 32 + 64) * 4));
+    buf_.tile_first = b_tiles_.as<u32>();
+  }
+  if (gc.failed_ovf & OVF_LEAVES) cap_leaf_ *= 4;
+  const u32 resume = update_count;
+  for (size_t k = done; k < q.size(); ++k) {
+    const ShardQueued& e = q[k];
+    update_count = e.c;
+    BNX_TRY(shard_insert(e.points, e.stride, e.n, e.f64, e.index_base, e.n_max, e.origin, e.max_range, e.where, false));
+  }
+  update_count = resume;
+  return BNX_OK;
 }
 
 int Map::add_point(const double pt[3], bool miss) {

@@ -92,6 +92,12 @@ class Map {
   int shard_resolve_mark(const void* recv_records, void* send_leaves, i64 cap_leaves);
   int shard_merge(const void* recv_leaves, void* flags);
   int shard_finish(const void* flags_reduced, int* retry);
+  // the same protocol driven natively: NCCL send/recv all-to-all + all-reduce issued by the library on the map's
+  // stream (NCCL is resolved with dlopen). async: nothing synchronises; failures freeze all ranks at the same scan.
+  static int nccl_unique_id(const char* nccl_path, void* out128);
+  int shard_comm_init(const char* nccl_path, const void* unique_id128, int rank, int world);
+  int shard_insert(const void* points, i64 stride_bytes, i64 n, bool f64, u32 index_base, i64 n_max, const double origin[3], double max_range,
+                   int where, bool async);
 
   // ---- pipelined insert: enqueue a scan and return; drain() completes everything queued (growing pools and
   // replaying from the first scan that ran short, if any). Input buffers must stay valid until drain().
@@ -122,6 +128,20 @@ class Map {
   Grid* scratch_ = nullptr;  // sharded: staging grid for cells whose root another rank owns (masks only)
   ScanParams sp_ = {};       // sharded: parameters of the scan in flight
   i64 shard_retries_ = 0;
+  void* comm_ = nullptr;  // ncclComm_t
+  DevBuf x_send1_, x_recv1_, x_send2_, x_recv2_, x_flags_;
+  i64 cap_rec_ = 0, cap_leaf_ = 1 << 13;
+  struct ShardQueued {
+    const void* points;
+    i64 stride, n, n_max;
+    bool f64;
+    u32 index_base, async_id, c;
+    double origin[3], max_range;
+    int where;
+  };
+  std::vector<ShardQueued> squeue_;
+  int all_to_all(const void* send, void* recv, size_t block_bytes);
+  int shard_drain();
   // pipelined insert
   static constexpr u32 RING = 1024;
   struct Queued {

@@ -12,6 +12,7 @@ Bit-exactness: the union of the shards' forEachCell dumps equals the unsharded m
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -92,45 +93,63 @@ class _Shard:
             self._alloc_leaves(self.cap_leaves * 4)
 
 
-class ShardedMap:
-    """one rank of a map sharded over torch.distributed ranks (NCCL, one process per GPU)"""
+def nccl_library_path():
+    """torch's bundled NCCL (already loaded by the process once torch.distributed uses it), else the system one"""
+    try:
+        import torch
+        cand = os.path.join(os.path.dirname(os.path.dirname(torch.__file__)), "nvidia", "nccl", "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            return cand
+    except Exception:
+        pass
+    return "libnccl.so.2"
 
-    def __init__(self, resolution: float, group=None, cap_leaves: int = 1 << 13):
+
+class ShardedMap:
+    """one rank of a map sharded over torch.distributed ranks (one process per GPU). torch.distributed is only used to
+    hand the NCCL unique id around; the per-scan exchanges are issued by the library itself (bnx_map_shard_insert)."""
+
+    def __init__(self, resolution: float, group=None):
         import torch
         import torch.distributed as dist
         self.torch, self.dist, self.group = torch, dist, group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         assert self.world > 1, "use capi.ProbabilisticMap for a single GPU"
-        self.shard = _Shard(resolution, self.rank, self.world, torch.device("cuda", torch.cuda.current_device()), cap_leaves=cap_leaves)
-        self.shard.set_stream(torch.cuda.current_stream().cuda_stream)
-        self.map = self.shard.map
-        self.attempts = 0
+        self.map = capi.ProbabilisticMap(resolution)
+        self.lib = self.map.lib
+        self.map.set_stream(torch.cuda.current_stream().cuda_stream)
+        path = nccl_library_path().encode()
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if self.rank == 0:
+            buf = (C.c_uint8 * 128)()
+            capi._check(self.lib.bnx_nccl_unique_id(path, buf))
+            uid = torch.tensor(list(buf), dtype=torch.uint8)
+        uid = uid.cuda()
+        dist.broadcast(uid, src=0, group=group)
+        raw = bytes(uid.cpu().tolist())
+        capi._check(self.lib.bnx_map_shard_comm_init(self.map.h, path, raw, self.rank, self.world))
 
-    def insert(self, pts_local, n_local, stride_bytes, index_base, origin, max_range, f64=False):
-        """this rank's slice of the scan: points [index_base, index_base + n_local) of the global cloud"""
-        s, dist = self.shard, self.dist
-        n_max = self.torch.tensor([n_local], dtype=self.torch.int64, device=s.device)
-        if n_local + 2 > s.cap_records:  # keep record capacities equal on all ranks (equal-split all-to-all)
-            pass
-        dist.all_reduce(n_max, op=dist.ReduceOp.MAX, group=self.group)
-        need = int(n_max.item()) + 2
-        if need > s.cap_records:
-            s._alloc_records(max(need, s.cap_records * 2))
-        s.begin(pts_local, n_local, stride_bytes, f64, index_base, origin, max_range)
-        dist.all_to_all_single(s.recv1.view(-1), s.send1.view(-1), group=self.group)
-        while True:
-            self.attempts += 1
-            s.resolve_mark()
-            dist.all_to_all_single(s.recv2.view(-1), s.send2.view(-1), group=self.group)
-            s.merge()
-            dist.all_reduce(s.flags, op=dist.ReduceOp.MAX, group=self.group)
-            retry = s.finish()
-            if not retry:
-                return
-            s.grow_after(retry)  # the flags are all-reduced: every rank takes the same branch
+    def insert(self, pts_local, n_local, stride_bytes, index_base, n_max, origin, max_range, f64=False, use_async=False):
+        """this rank's slice of the scan: points [index_base, index_base + n_local) of the global cloud; n_max = the
+        largest slice over all ranks (every rank must pass the same value)"""
+        o = np.ascontiguousarray(origin, dtype=np.float64)
+        if isinstance(pts_local, capi.DevPtr):
+            p, where = C.c_void_p(pts_local.address), capi.BNX_DEVICE
+        else:
+            assert pts_local.flags["C_CONTIGUOUS"]
+            p, where = C.c_void_p(pts_local.ctypes.data), capi.BNX_HOST
+        capi._check(self.lib.bnx_map_shard_insert(self.map.h, p, C.c_int64(stride_bytes), C.c_int64(n_local), int(bool(f64)), C.c_uint32(index_base),
+                                                  C.c_int64(n_max), C.c_void_p(o.ctypes.data), C.c_double(max_range), where, int(use_async)))
+
+    def sync(self):
+        """completes the pipelined scans; collective: every rank must call it at the same point"""
+        self.map.sync()
 
     def counters(self):
         return self.map.counters()
+
+    def totals(self):
+        return self.map.totals()
 
 
 class LocalShardGroup:

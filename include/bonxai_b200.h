@@ -230,6 +230,20 @@ BNX_API int bnx_map_shard_resolve_mark(bnx_map_t* m, const void* recv_records, v
 BNX_API int bnx_map_shard_merge(bnx_map_t* m, const void* recv_leaves, void* flags);
 BNX_API int bnx_map_shard_finish(bnx_map_t* m, const void* flags_reduced, int* retry);
 
+/* The same protocol driven by the library itself: the two all-to-alls (grouped ncclSend/ncclRecv) and the flag
+ * all-reduce are issued on the map's stream through NCCL, which is resolved with dlopen at run time
+ * (nccl_library_path may be NULL: "libnccl.so.2"; a copy already loaded by the process, e.g. torch's, is shared).
+ *   rank 0: bnx_nccl_unique_id -> 128 bytes, broadcast them by any means -> every rank: bnx_map_shard_comm_init.
+ *   every rank, in lock step: bnx_map_shard_insert(points of its slice, index_base = global index of its first
+ *   point, n_max = the largest slice over all ranks, ...). async != 0: pipelined, nothing synchronises; a scan that
+ *   runs short on ANY rank freezes ALL ranks at that scan (the flags are all-reduced) and the next bnx_map_sync /
+ *   query on every rank grows and replays it — so synchronising calls must be made by all ranks together. */
+BNX_API int bnx_nccl_unique_id(const char* nccl_library_path, void* out128);
+BNX_API int bnx_map_shard_comm_init(bnx_map_t* m, const char* nccl_library_path, const void* unique_id128, int rank, int world);
+BNX_API int bnx_map_shard_insert(bnx_map_t* m, const void* points, int64_t stride_bytes, int64_t n, int is_f64,
+                                 uint32_t index_base, int64_t n_max, const double origin[3], double max_range, int where,
+                                 int async);
+
 #ifdef __cplusplus
 }
 #endif

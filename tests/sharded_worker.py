@@ -19,15 +19,24 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    mode = os.environ.get("BNX_SHARD_TEST_MODE", "sync")
     sm = ShardedMap(0.1)
     if rank == 0:
         import oracle
         om = oracle.load("port").map(0.1)
-    for scan in range(3):
+    keep = []
+    for scan in range(6 if mode == "async" else 3):
         pts, origin = synth.lidar_scan(scan * 2, beams=32, azimuths=1024)
-        lo, hi = split_points(len(pts), world)[rank]
+        parts = split_points(len(pts), world)
+        lo, hi = parts[rank]
+        n_max = max(h - l for l, h in parts)
         dev = torch.from_numpy(pts[lo:hi]).cuda()
-        sm.insert(capi.DevPtr(dev.data_ptr()), hi - lo, 16, lo, origin, 40.0)
+        keep.append(dev)
+        sm.insert(capi.DevPtr(dev.data_ptr()), hi - lo, 16, lo, n_max, origin, 40.0, use_async=(mode == "async"))
+        if mode == "async" and scan % 3 != 2:
+            if rank == 0:
+                om.insert(pts, origin, 40.0)
+            continue  # compare only every third scan: the others stay in the pipeline
         xyz, w = sm.map.dump(sort=False)
         gathered = [None] * world
         dist.all_gather_object(gathered, (xyz, w))

@@ -62,10 +62,16 @@ def test_local_shard_group_growth_and_small_exchange_buffers(bnx, port, monkeypa
     assert g.attempts > 2  # pools and the leaf exchange buffer had to grow
 
 
-def test_nccl_two_ranks(bnx):
+@pytest.mark.parametrize("mode,tiny", [("sync", False), ("async", False), ("async", True)])
+def test_nccl_two_ranks(bnx, mode, tiny):
+    """the native NCCL driver (bnx_map_shard_insert) on 2 GPUs: synchronous, pipelined, and pipelined with pools so
+    small that a queued scan runs short and all ranks freeze + replay"""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
+    env = dict(os.environ, BNX_SHARD_TEST_MODE=mode)
+    if tiny:
+        env.update(BNX_INIT_LEAF_MB="2", BNX_INIT_INNER_MB="0")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29611", os.path.join(ROOT, "tests", "sharded_worker.py")], capture_output=True, text=True, timeout=900)
+                        "--master-port", "29611", os.path.join(ROOT, "tests", "sharded_worker.py")], capture_output=True, text=True, timeout=900, env=env)
     assert r.returncode == 0 and "SHARDED_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
