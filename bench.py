@@ -445,6 +445,7 @@ def run_gpu_sharded(args):
     active = torch.tensor([sm.map.active_count()], dtype=torch.float64, device="cuda")
     dist.all_reduce(active, op=dist.ReduceOp.SUM)
     attempts = 0
+    exchange = sm.exchange_kind()
     del sm
 
     pinned = [torch.from_numpy(p).pin_memory().numpy() for p, _ in slices]
@@ -477,7 +478,11 @@ def run_gpu_sharded(args):
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64+int32", "data": "synthetic",
             "config": {"workload": f"lidar64x{az}_seq({n_scan} pts/scan = {world} x 131072, res 0.1 m, max_range 50 m, 1 m/scan)",
                        "points_per_scan": n_scan, "points_per_gpu_per_scan": n_local,
-                       "parallelism": f"one map sharded by root key over {world} GPUs; per scan 2 all-to-all (grouped ncclSend/Recv) + 1 all-reduce(16 B), pipelined (no host sync per scan)",
+                       "parallelism": f"one map sharded by root key over {world} GPUs, pipelined (no host sync per scan); " + (
+                           "per scan two record exchanges + one flag exchange as NVLink peer-memory stores from the producing kernels into the owners' "
+                           "mailboxes (CUDA IPC), arrival flags instead of collectives; NCCL only bootstraps" if exchange == "p2p" else
+                           "per scan 2 all-to-all (grouped ncclSend/Recv) + 1 all-reduce(16 B)"),
+                       "exchange": exchange,
                        "l2": f"{total} distinct 2 MiB scan slices per GPU resident in HBM, each read once", "active_cells_end": int(active.item()),
                        "attempts": attempts},
             "voxel_updates_per_s": U_all / secs, "ray_visits_per_s": V_all / secs, "rays_per_s": E_all / secs,

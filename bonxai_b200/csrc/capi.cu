@@ -353,6 +353,22 @@ int bnx_map_shard_insert(bnx_map_t* h, const void* points, int64_t stride_bytes,
   DeviceGuard dg(h->m.grid.device);
   return h->m.shard_insert(points, stride_bytes, n, is_f64 != 0, index_base, n_max, origin, max_range, where, async != 0);
 }
+int bnx_map_shard_p2p_alloc(bnx_map_t* h, int64_t cap_records, int64_t cap_leaves, void* ipc_handle64, void** device_ptr) {
+  BNX_HANDLE(h);
+  DeviceGuard dg(h->m.grid.device);
+  return h->m.p2p_alloc(cap_records, cap_leaves, ipc_handle64, device_ptr);
+}
+int bnx_map_shard_p2p_attach(bnx_map_t* h, const void* ipc_handles, void* const* device_ptrs) {
+  BNX_HANDLE(h);
+  DeviceGuard dg(h->m.grid.device);
+  return h->m.p2p_attach(ipc_handles, device_ptrs);
+}
+int bnx_map_shard_exchange(const bnx_map_t* h, int* kind) {
+  BNX_HANDLE(h);
+  BNX_REQUIRE(kind != nullptr, "null output");
+  *kind = h->m.exchange_kind();
+  return BNX_OK;
+}
 int bnx_map_counters(bnx_map_t* h, int64_t out[8]) {
   BNX_HANDLE(h);
   BNX_TRY(h->m.drain());

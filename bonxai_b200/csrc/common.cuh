@@ -66,6 +66,7 @@ enum : u32 {
   ERR_ROOT_TABLE = 4u,  // root hash table full
   ERR_RAY_LIST = 8u,    // scan scratch overflow (should not happen: sized from n)
   ERR_SCAN = 16u,       // async pipeline: a scan's scratch lists overflowed; sticky until the host recovers
+  ERR_PEER = 32u,       // sharded map, peer-memory exchange: a peer's arrival stamp did not show up in time (fatal)
 };
 
 }  // namespace bnx

@@ -43,6 +43,74 @@ constexpr u32 OVF_TILES = 1u, OVF_CHUNKS = 2u, OVF_RECORDS = 4u, OVF_LEAVES = 8u
 inline int blocks_for(i64 n, int tpb = TPB) { return (int)std::max<i64>(1, ceil_div(n, tpb)); }
 
 // ------------------------------------------------------------------------------------------------
+// peer-memory exchange primitives (sharded map)
+// ------------------------------------------------------------------------------------------------
+constexpr unsigned long long PEER_TIMEOUT_NS = 8000000000ull;  // a dead peer becomes ERR_PEER, never a hang
+
+__device__ __forceinline__ u32 ld_acquire_sys(const u32* p) {
+  u32 v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(u32* p, u32 v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Consumer side: threads 0..world-1 of the block spin on the arrival stamps flags[t * stride] that the peers store
+// into THIS rank's mailbox (acquire, system scope), then the block synchronises. Everything a peer wrote before its
+// stamp is visible afterwards (read it with __ldcg: the lines were never in this SM's L1 during this kernel).
+// Stamps only grow, so ">= seq" is the test. A peer that never arrives sets ERR_PEER (sticky: later waits return at once).
+__device__ __forceinline__ void wait_arrivals(const u32* flags, u32 stride, u32 world, u32 seq, u32* err) {
+  if (flags == nullptr) return;
+  if (threadIdx.x < world) {
+    const u32* f = flags + threadIdx.x * stride;
+    if ((int)(ld_acquire_sys(f) - seq) < 0) {
+      const unsigned long long t0 = global_ns();
+      while ((int)(ld_acquire_sys(f) - seq) < 0) {
+        if (*reinterpret_cast<volatile u32*>(err) & ERR_PEER) break;
+        if (global_ns() - t0 > PEER_TIMEOUT_NS) {
+          atomicOr(err, ERR_PEER);
+          break;
+        }
+        __nanosleep(128);
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// Producer side, called by every block at the end of a kernel that stored records into the owners' inboxes: the
+// LAST block writes the record count of every block header and then the arrival stamp into every owner's flag area
+// (release, system scope; each block fenced its own stores before taking its ticket).
+__device__ __forceinline__ void publish_blocks(const PeerBoxes* px, bool leaves, const u32* cnt, u32* done, u32 flag_off, u32 rank, u32 seq, u32 world,
+                                               u32 cap) {
+  __shared__ bool s_last;
+  const bool remote = px->flag[0] != nullptr;
+  if (remote) {
+    __threadfence_system();
+  } else {
+    __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(done, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  if (threadIdx.x < world) {
+    const u32 o = threadIdx.x;
+    const u32 c = min(*reinterpret_cast<const volatile u32*>(cnt + o), cap - 1u);
+    int4* block = leaves ? px->leaf[o] : px->rec[o];
+    block[0] = make_int4((int)c, 0, 0, 0);
+    if (remote) {
+      __threadfence_system();
+      st_release_sys(px->flag[o] + flag_off + rank, seq);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // phase 1: classify + endpoint dedupe
 // ------------------------------------------------------------------------------------------------
 // The per-point body of insertPointCloud (probabilistic_map.hpp:146-158) followed by posToCoord
@@ -534,13 +602,43 @@ __global__ void __launch_bounds__(TPB) k_clear_touched(GridDev g, ScanBuffers b,
 // ------------------------------------------------------------------------------------------------
 // phase 4 / 5: apply
 // ------------------------------------------------------------------------------------------------
+// the reduced flags as seen by the apply pass (block-uniform; ends with a __syncthreads in the peer-memory flavour)
+__device__ __forceinline__ void read_gate(const ScanParams& p, const ScanBuffers& b, u32& pool, u32& ovf) {
+  __shared__ u32 s_gate[2];
+  pool = 0;
+  ovf = 0;
+  if (!b.gate) return;
+  if (!b.my_flags) {  // all-reduced by the caller or by NCCL
+    pool = b.gate[0];
+    ovf = b.gate[1];
+    return;
+  }
+  const u32* base = b.gate + (p.xseq2 & 1u) * (MAX_PEERS * 4);
+  if (threadIdx.x < 2) s_gate[threadIdx.x] = 0;
+  wait_arrivals(base + 3, 4, p.world, p.xseq2, const_cast<u32*>(b.poison));
+  if (threadIdx.x < p.world) {
+    const uint4 v = __ldcg(reinterpret_cast<const uint4*>(base) + threadIdx.x);
+    if (v.x) atomicOr(&s_gate[0], v.x);
+    if (v.y) atomicOr(&s_gate[1], v.y);
+  }
+  __syncthreads();
+  pool = s_gate[0];
+  ovf = s_gate[1];
+}
+
 // One warp per listed leaf: hit endpoints (addHitPoint, probabilistic_map.cpp:30-41) and the union of all rays + miss
 // endpoints (clearPoint / addMissPoint, :43-54,81-89). Hit endpoints are never stale (resolve filtered them) and win
 // over ray cells, like the reference where they are stamped before any ray is cast.
 __global__ void __launch_bounds__(TPB) k_apply_leaves(GridDev g, ScanParams p, ScanBuffers b) {
   // last kernel of the scan: the host reads counters + grid counters with one copy
-  if (blockIdx.x == 0 && threadIdx.x == 0) b.sc->gc = *g.ctr;
-  const bool skip = (g.ctr->error | b.sc->overflow) || (b.gate && (b.gate[0] | b.gate[1]));
+  u32 gate_pool, gate_ovf;
+  read_gate(p, b, gate_pool, gate_ovf);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    b.sc->gc = *g.ctr;
+    b.sc->gate_pool = gate_pool;
+    b.sc->gate_ovf = gate_ovf;
+  }
+  const bool skip = (g.ctr->error | b.sc->overflow | gate_pool | gate_ovf) != 0u;
   const u32 n = skip ? 0u : min(b.sc->n_touched, p.touched_cap);
   const u32 lane = threadIdx.x & 31;
   const u32 warps = gridDim.x * (TPB / 32);
@@ -618,8 +716,7 @@ __global__ void __launch_bounds__(TPB) k_apply_leaves(GridDev g, ScanParams p, S
   __threadfence();
   const volatile ScanCounters* sc = b.sc;
   u32 err = g.ctr->error;
-  const u32 gate_ovf = b.gate ? b.gate[1] : 0u;
-  if ((sc->overflow || (b.gate && (b.gate[0] | gate_ovf))) && !err) {  // this rank, or (sharded) any rank, ran short
+  if ((sc->overflow | gate_pool | gate_ovf) && !err) {  // this rank, or (sharded) any rank, ran short
     err = ERR_SCAN;
     atomicOr(&g.ctr->error, ERR_SCAN);
   }
@@ -655,31 +752,51 @@ __global__ void __launch_bounds__(TPB) k_begin_scan(ScanBuffers b, uint4* base, 
 // ------------------------------------------------------------------------------------------------
 // sharded map: staging kernels around the two exchanges
 // ------------------------------------------------------------------------------------------------
-// exchange 1, sender: every locally winning endpoint goes to the rank that owns its root:
-// record = {x, y, z, global point index << 1 | type}; slot 0 of a peer block carries the count
-__global__ void __launch_bounds__(TPB) k_shard_bucket(ScanParams p, ScanBuffers b, u32 index_base, int4* send, u32 cap) {
+// exchange 1, sender: every locally winning endpoint goes to the rank that owns its root, straight into block [rank] of
+// the owner's inbox (peer memory) or of the caller's send buffer: record = {x, y, z, global point index << 1 | type};
+// slot 0 of a block carries the count. Slots are handed out per owner by a warp-aggregated atomic on a LOCAL counter.
+__global__ void __launch_bounds__(TPB) k_shard_bucket(ScanParams p, ScanBuffers b, u32 index_base) {
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= p.n || *b.poison) return;
-  const u32 slot = b.slot_of[i];
-  if (slot == NONE || b.table[slot] != ~i) return;  // dropped, or not the lowest local index of its voxel
-  const int4 e = b.ep[i];
-  const u32 o = shard_owner(e.x >> 5, e.y >> 5, e.z >> 5, p.world);
-  int4* block = send + (size_t)o * cap;
-  const u32 at = atomicAdd(reinterpret_cast<u32*>(&block[0].x), 1u) + 1u;
-  if (at < cap) {
-    block[at] = make_int4(e.x, e.y, e.z, (int)(((index_base + i) << 1) | (u32)e.w));
-  } else {
-    atomicOr(&b.sc->overflow, OVF_RECORDS);
+  const u32 lane = threadIdx.x & 31;
+  const u32 cap = p.rec_cap;
+  bool win = false;
+  int4 e = make_int4(0, 0, 0, 0);
+  u32 o = 0;
+  if (i < p.n && !*b.poison) {
+    const u32 slot = b.slot_of[i];
+    win = slot != NONE && b.table[slot] == ~i;  // not dropped, and the lowest local index of its voxel
+    if (win) {
+      e = b.ep[i];
+      o = shard_owner(e.x >> 5, e.y >> 5, e.z >> 5, p.world);
+    }
   }
+  const u32 act = __ballot_sync(0xffffffffu, win);
+  if (win) {
+    const u32 peers = __match_any_sync(act, o);
+    const int leader = __ffs(peers) - 1;
+    u32 base = 0;
+    if ((int)lane == leader) base = atomicAdd(&b.sc->cnt1[o], (u32)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    const u32 at = base + __popc(peers & ((1u << lane) - 1u)) + 1u;
+    if (at < cap) {
+      b.px->rec[o][at] = make_int4(e.x, e.y, e.z, (int)(((index_base + i) << 1) | (u32)e.w));
+    } else {
+      atomicOr(&b.sc->overflow, OVF_RECORDS);
+    }
+  }
+  publish_blocks(b.px, false, b.sc->cnt1, &b.sc->done1, MBOX_FLAG1, p.rank, p.xseq1, p.world, cap);
 }
 
 // exchange 1, receiver: lowest global index per endpoint voxel over the records of all ranks
 __global__ void __launch_bounds__(TPB) k_shard_dedupe(ScanParams p, ScanBuffers b, u32 count) {
+  // peer-memory exchange: the records of every rank must have arrived (the wait happens even when the pipeline is
+  // frozen, so that no rank ever runs ahead of an exchange point)
+  wait_arrivals(b.my_flags ? b.my_flags + MBOX_FLAG1 : nullptr, 1, p.world, p.xseq1, const_cast<u32*>(b.poison));
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count || *b.poison) return;
   const u32 j = i % p.rec_cap;
-  if (j == 0u || j > (u32)b.recs[i - j].x) return;
-  const int4 e = b.recs[i];
+  if (j == 0u || j > (u32)__ldcg(&b.recs[i - j]).x) return;
+  const int4 e = __ldcg(&b.recs[i]);
   const unsigned long long key = pack_key(e);
   u32 slot = (u32)hash3(e.x, e.y, e.z) & p.hash_mask;
   for (;;) {
@@ -692,10 +809,11 @@ __global__ void __launch_bounds__(TPB) k_shard_dedupe(ScanParams p, ScanBuffers 
   b.slot_of[i] = slot;
 }
 
-// exchange 2, sender: one warp per scratch leaf touched in this scan -> {leaf origin, 512-bit mask} to the owner
-// of its root; the scratch mask is cleared for the next scan. Record = 5 x int4 (80 B).
-__global__ void __launch_bounds__(TPB) k_shard_emit(GridDev gs, ScanParams p, ScanBuffers b, int4* send, u32 cap) {
+// exchange 2, sender: one warp per scratch leaf touched in this scan -> {leaf origin, 512-bit mask} into block [rank] of
+// the inbox of the rank that owns its root; the scratch mask is cleared for the next scan. Record = 5 x int4 (80 B).
+__global__ void __launch_bounds__(TPB) k_shard_emit(GridDev gs, ScanParams p, ScanBuffers b) {
   const u32 n = min(b.sc->n_touched2, p.touched2_cap);
+  const u32 cap = p.leaf_cap2;
   const u32 lane = threadIdx.x & 31;
   const u32 warps = gridDim.x * (TPB / 32);
   for (u32 t = blockIdx.x * (TPB / 32) + (threadIdx.x >> 5); t < n; t += warps) {
@@ -703,9 +821,9 @@ __global__ void __launch_bounds__(TPB) k_shard_emit(GridDev gs, ScanParams p, Sc
     const int4 hdr = *reinterpret_cast<const int4*>(leaf_ptr(gs, leaf));
     unsigned long long* touched = reinterpret_cast<unsigned long long*>(leaf_touched(gs, leaf));
     const u32 o = shard_owner(hdr.x >> 5, hdr.y >> 5, hdr.z >> 5, p.world);
-    int4* block = send + (size_t)o * cap * 5;
+    int4* block = b.px->leaf[o];
     u32 at = 0;
-    if (lane == 0) at = atomicAdd(reinterpret_cast<u32*>(&block[0].x), 1u) + 1u;
+    if (lane == 0) at = atomicAdd(&b.sc->cnt2[o], 1u) + 1u;
     at = __shfl_sync(0xffffffffu, at, 0);
     unsigned long long m = 0;
     if (lane < 8) {
@@ -719,6 +837,7 @@ __global__ void __launch_bounds__(TPB) k_shard_emit(GridDev gs, ScanParams p, Sc
       atomicOr(&b.sc->overflow, OVF_LEAVES);
     }
   }
+  publish_blocks(b.px, true, b.sc->cnt2, &b.sc->done2, MBOX_FLAG2, p.rank, p.xseq2, p.world, cap);
 }
 
 // exchange 2, receiver: OR the remote masks into this rank's leaves (one warp per record)
@@ -726,29 +845,45 @@ __global__ void __launch_bounds__(TPB) k_shard_merge(GridDev g, ScanParams p, Sc
   const u32 lane = threadIdx.x & 31;
   const u32 warps = gridDim.x * (TPB / 32);
   const u32 slots = p.world * cap;
+  wait_arrivals(b.my_flags ? b.my_flags + MBOX_FLAG2 : nullptr, 1, p.world, p.xseq2, const_cast<u32*>(b.poison));
   if (*b.poison) return;
   for (u32 t = blockIdx.x * (TPB / 32) + (threadIdx.x >> 5); t < slots; t += warps) {
     const u32 j = t % cap;
     const int4* block = recv + (size_t)(t - j) * 5;
-    if (j == 0u || j > min((u32)block[0].x, cap - 1u)) continue;
-    const int4 hdr = block[(size_t)j * 5];
+    if (j == 0u || j > min((u32)__ldcg(&block[0]).x, cap - 1u)) continue;
+    const int4 hdr = __ldcg(&block[(size_t)j * 5]);
     u32 leaf = NONE;
     if (lane == 0) leaf = leaf_find_or_create(g, hdr.x, hdr.y, hdr.z);
     leaf = __shfl_sync(0xffffffffu, leaf, 0);
     if (leaf == NONE) continue;
     if (lane < 8) {
-      const unsigned long long bits = reinterpret_cast<const unsigned long long*>(block + (size_t)j * 5 + 1)[lane];
+      const unsigned long long bits = __ldcg(reinterpret_cast<const unsigned long long*>(block + (size_t)j * 5 + 1) + lane);
       if (bits) mark_bits(g, leaf, reinterpret_cast<unsigned long long*>(leaf_touched(g, leaf)) + lane, bits, p.seq, &b.sc->n_touched, b.touched, p.touched_cap);
     }
   }
 }
 
-// flags of this rank for the all-reduce(MAX) that gates the apply phases on every rank
-__global__ void k_shard_flags(GridDev g, GridDev gs, ScanBuffers b, u32* flags) {
-  flags[0] = g.ctr->error | (gs.ctr->error << 8);
-  flags[1] = b.sc->overflow;
-  flags[2] = 0;
-  flags[3] = 0;
+// flags of this rank for the reduction (MAX / OR) that gates the apply phase on every rank. Caller-run exchange and
+// NCCL: written to `flags`, all-reduced afterwards. Peer memory: stored into slot [rank] of every rank's flag table
+// (values first, then the stamp), the apply kernel ORs the table itself. One warp.
+__global__ void k_shard_flags(GridDev g, GridDev gs, ScanParams p, ScanBuffers b, u32* flags) {
+  const u32 f0 = g.ctr->error | (gs.ctr->error << 8), f1 = b.sc->overflow;
+  if (b.px->flag[0] == nullptr) {
+    if (threadIdx.x == 0) {
+      flags[0] = f0;
+      flags[1] = f1;
+      flags[2] = 0;
+      flags[3] = 0;
+    }
+    return;
+  }
+  if (threadIdx.x < p.world) {
+    u32* dst = b.px->flag[threadIdx.x] + MBOX_FLAGS4 + (p.xseq2 & 1u) * (MAX_PEERS * 4) + p.rank * 4;
+    dst[0] = f0;
+    dst[1] = f1;
+    __threadfence_system();
+    st_release_sys(dst + 3, p.xseq2);
+  }
 }
 
 // public addHitPoint / addMissPoint (probabilistic_map.cpp:30-54): update now, queue the ray
@@ -808,6 +943,9 @@ Map::~Map() {
     if (ev_consumed_[k]) cudaEventDestroy(ev_consumed_[k]);
   }
   if (h_ring_) cudaFreeHost(h_ring_);
+  p2p_close_peers();
+  if (mbox_) cudaFree(mbox_);
+  for (void* old : mbox_retired_) cudaFree(old);
   if (comm_) nccl_api(nullptr).CommDestroy(static_cast<ncclComm_t>(comm_));
   delete scratch_;
   if (h_status_) cudaFreeHost(h_status_);
@@ -819,7 +957,7 @@ static i32 logods_host(float prob) {  // probabilistic_map.hpp:34-36
   return (i32)(1e6 * std::log(prob / (1.0 - prob)));
 }
 
-constexpr size_t SC_BYTES = 128;  // ScanCounters header of b_table_
+constexpr size_t SC_BYTES = 256;  // ScanCounters header of b_table_
 static_assert(sizeof(ScanCounters) <= SC_BYTES, "ScanCounters must fit its header");
 
 static u64 table_slots(i64 n) {
@@ -1235,12 +1373,30 @@ int Map::shard_config(int rank, int world) {
   return BNX_OK;
 }
 
+// where do this rank's records go? peer memory: block [rank] of every owner's inbox; otherwise the caller's send buffers
+int Map::upload_boxes() {
+  BNX_TRY(b_px_.reserve(sizeof(PeerBoxes)));
+  buf_.px = b_px_.as<PeerBoxes>();
+  if (px_uploaded_valid_ && std::memcmp(&px_uploaded_, &px_host_, sizeof(PeerBoxes)) == 0) return BNX_OK;
+  px_uploaded_ = px_host_;
+  px_uploaded_valid_ = true;
+  BNX_CUDA(cudaMemcpyAsync(b_px_.p, &px_host_, sizeof(PeerBoxes), cudaMemcpyHostToDevice, grid.stream()));
+  buf_.px = b_px_.as<PeerBoxes>();
+  return BNX_OK;
+}
+
 int Map::shard_begin(const void* points, i64 stride_bytes, i64 n, bool f64, u32 index_base, const double origin[3], double max_range,
                      void* send_records, i64 cap_records, int where) {
   BNX_REQUIRE(world_ > 1 && scratch_, "shard_begin: call shard_config(rank, world > 1) first");
   BNX_REQUIRE(n >= 0 && n < (1ll << 24) && (u64)index_base + (u64)n < (1ull << 31), "shard_begin: point count / index out of range");
   BNX_REQUIRE(n_pending_ == 0, "shard_begin: addHitPoint/addMissPoint queues are not supported on a sharded map");
-  BNX_REQUIRE(origin && send_records && cap_records >= 2, "shard_begin: null argument");
+  staged_p2p_ = send_records == nullptr;
+  if (staged_p2p_) {
+    BNX_REQUIRE(p2p_ready_, "shard_begin: NULL send buffer but no mailboxes attached (bnx_map_shard_p2p_attach)");
+    cap_records = mbox_cap_rec_;
+    BNX_REQUIRE(n + 2 <= cap_records, "shard_begin: the mailbox holds fewer endpoint records than this slice has points");
+  }
+  BNX_REQUIRE(origin && cap_records >= 2, "shard_begin: null argument");
   BNX_REQUIRE(f64 ? (stride_bytes >= 24 && stride_bytes % 8 == 0) : (stride_bytes >= 12 && stride_bytes % 4 == 0), "shard_begin: bad stride");
   if (!queue_.empty()) BNX_TRY(drain());  // single-GPU pipeline first; the sharded queue is drained collectively
   cudaStream_t s = grid.stream();
@@ -1273,6 +1429,7 @@ int Map::shard_begin(const void* points, i64 stride_bytes, i64 n, bool f64, u32 
   p.world = (u32)world_;
   p.async_id = NONE;
   p.rec_cap = (u32)cap_records;
+  p.xseq1 = ++xseq1_;
   p.max_chunks = (u32)std::min<u64>(((1ull << 40) - 1) / (u64)std::max<i64>(slots, 1), 1ull << 28);
   const double reach = std::ceil(max_range * grid.inv_resolution) + 4.0, lim = (double)(1 << 20) - 1.0;
   p.packed = std::isfinite(max_range) && max_range >= 0.0 && std::fabs((double)p.Ox) + reach < lim &&
@@ -1285,11 +1442,19 @@ int Map::shard_begin(const void* points, i64 stride_bytes, i64 n, bool f64, u32 
   p.hash_mask = (u32)(tslots - 1);
   sp_ = p;
   shard_retries_ = 0;
+  if (!staged_p2p_) {
+    BNX_REQUIRE(world_ <= MAX_PEERS, "sharded insert: at most 16 ranks");
+    px_host_ = PeerBoxes{};
+    for (int o = 0; o < world_; ++o) px_host_.rec[o] = static_cast<int4*>(send_records) + (size_t)o * cap_records;
+    BNX_TRY(upload_boxes());
+    buf_.my_flags = nullptr;
+  } else {
+    buf_.my_flags = reinterpret_cast<const u32*>(mbox_);
+  }
   BNX_CUDA(cudaMemsetAsync(d_sc_, 0, SC_BYTES + tslots * 12, s));
-  BNX_CUDA(cudaMemset2DAsync(send_records, (size_t)cap_records * 16, 0, 16, (size_t)world_, s));  // block headers
+  const int blocks = blocks_for(n);
   if (n > 0) {
     const unsigned char* pts = static_cast<const unsigned char*>(d_points);
-    const int blocks = blocks_for(n);
     if (f64) {
       launch_classify<true, false>(true, blocks, s, pts, (u32)stride_bytes, p, buf_);
     } else if (stride_bytes == 16 && (reinterpret_cast<uintptr_t>(pts) & 15u) == 0) {
@@ -1297,14 +1462,24 @@ int Map::shard_begin(const void* points, i64 stride_bytes, i64 n, bool f64, u32 
     } else {
       launch_classify<false, false>(true, blocks, s, pts, (u32)stride_bytes, p, buf_);
     }
-    note_launch(), k_shard_bucket<<<blocks, TPB, 0, s>>>(p, buf_, index_base, static_cast<int4*>(send_records), (u32)cap_records);
-    BNX_CUDA(cudaGetLastError());
   }
+  // always launched: its last block writes the block headers (counts) and, with mailboxes, the arrival stamps
+  note_launch(), k_shard_bucket<<<blocks, TPB, 0, s>>>(p, buf_, index_base);
+  BNX_CUDA(cudaGetLastError());
   return BNX_OK;
 }
 
 int Map::shard_resolve_mark(const void* recv_records, void* send_leaves, i64 cap_leaves) {
-  BNX_REQUIRE(world_ > 1 && scratch_ && recv_records && send_leaves && cap_leaves >= 2, "shard_resolve_mark: bad argument");
+  BNX_REQUIRE(world_ > 1 && scratch_, "shard_resolve_mark: bad argument");
+  if (staged_p2p_) {
+    BNX_REQUIRE(p2p_ready_, "shard_resolve_mark: no mailboxes attached");
+    recv_records = mbox_ + MBOX_HEADER;
+    cap_leaves = mbox_cap_leaf_;
+  } else {
+    BNX_REQUIRE(recv_records && send_leaves && cap_leaves >= 2, "shard_resolve_mark: bad argument");
+    for (int o = 0; o < world_; ++o) px_host_.leaf[o] = static_cast<int4*>(send_leaves) + (size_t)o * cap_leaves * 5;
+    BNX_TRY(upload_boxes());
+  }
   cudaStream_t s = grid.stream();
   ScanParams& p = sp_;
   const u32 slots = p.world * p.rec_cap;
@@ -1316,48 +1491,60 @@ int Map::shard_resolve_mark(const void* recv_records, void* send_leaves, i64 cap
   buf_.recs = static_cast<const int4*>(recv_records);
   buf_.gate = nullptr;
   p.seq = ++seq_;
+  p.xseq2 = ++xseq2_;
   p.tile_cap = (u32)std::min<size_t>(b_tiles_.bytes / 4, 0xFFFFFFFFull);
   p.touched_cap = (u32)std::min<size_t>(b_touched_.bytes / 4, 0xFFFFFFFFull);
   p.touched2_cap = (u32)std::min<size_t>(b_touched2_.bytes / 4, 0xFFFFFFFFull);
   p.leaf_cap2 = (u32)cap_leaves;
   const u64 tslots = (u64)p.hash_mask + 1;
   BNX_CUDA(cudaMemsetAsync(d_sc_, 0, SC_BYTES + tslots * 12, s));
-  BNX_CUDA(cudaMemset2DAsync(send_leaves, (size_t)cap_leaves * 80, 0, 16, (size_t)world_, s));
   const GridDev g = grid.dev(), gs = scratch_->dev();
   note_launch(), k_shard_dedupe<<<blocks_for(slots), TPB, 0, s>>>(p, buf_, slots);
   note_launch(), k_resolve<2><<<blocks_for(slots), TPB, 0, s>>>(g, p, buf_, slots);
   note_launch(), k_mark<true><<<persistent, TPB, 0, s>>>(g, gs, p, buf_);
-  note_launch(), k_shard_emit<<<persistent, TPB, 0, s>>>(gs, p, buf_, static_cast<int4*>(send_leaves), (u32)cap_leaves);
+  note_launch(), k_shard_emit<<<persistent, TPB, 0, s>>>(gs, p, buf_);
   BNX_CUDA(cudaGetLastError());
   return BNX_OK;
 }
 
 int Map::shard_merge(const void* recv_leaves, void* flags) {
-  BNX_REQUIRE(world_ > 1 && scratch_ && recv_leaves && flags, "shard_merge: bad argument");
+  BNX_REQUIRE(world_ > 1 && scratch_, "shard_merge: bad argument");
+  if (staged_p2p_) {
+    recv_leaves = mbox_ + MBOX_HEADER + (size_t)world_ * mbox_cap_rec_ * 16;
+  } else {
+    BNX_REQUIRE(recv_leaves && flags, "shard_merge: bad argument");
+  }
   cudaStream_t s = grid.stream();
   const GridDev g = grid.dev(), gs = scratch_->dev();
   note_launch(), k_shard_merge<<<sm_count() * 8, TPB, 0, s>>>(g, sp_, buf_, static_cast<const int4*>(recv_leaves), sp_.leaf_cap2);
-  note_launch(), k_shard_flags<<<1, 1, 0, s>>>(g, gs, buf_, static_cast<u32*>(flags));
+  note_launch(), k_shard_flags<<<1, 32, 0, s>>>(g, gs, sp_, buf_, static_cast<u32*>(flags));
   BNX_CUDA(cudaGetLastError());
   return BNX_OK;
 }
 
 int Map::shard_finish(const void* flags_reduced, int* retry) {
-  BNX_REQUIRE(world_ > 1 && scratch_ && flags_reduced && retry, "shard_finish: bad argument");
+  BNX_REQUIRE(world_ > 1 && scratch_ && retry, "shard_finish: bad argument");
+  if (staged_p2p_) {
+    flags_reduced = mbox_ + MBOX_FLAGS4 * 4;  // the apply pass reduces the flag table itself
+  } else {
+    BNX_REQUIRE(flags_reduced != nullptr, "shard_finish: bad argument");
+  }
   cudaStream_t s = grid.stream();
   const int persistent = sm_count() * 8;
   const GridDev g = grid.dev();
   buf_.gate = static_cast<const u32*>(flags_reduced);
   note_launch(), k_apply_leaves<<<persistent, TPB, 0, s>>>(g, sp_, buf_);
   BNX_CUDA(cudaGetLastError());
-  u32* h_flags = reinterpret_cast<u32*>(reinterpret_cast<unsigned char*>(h_status_) + sizeof(ScanCounters));
   BNX_CUDA(cudaMemcpyAsync(h_status_, d_sc_, sizeof(ScanCounters), cudaMemcpyDeviceToHost, s));
-  BNX_CUDA(cudaMemcpyAsync(h_flags, flags_reduced, 16, cudaMemcpyDeviceToHost, s));
   BNX_CUDA(cudaStreamSynchronize(s));
   buf_.gate = nullptr;
   const ScanCounters st = *h_status_;
-  const u32 any_pool = h_flags[0], any_ovf = h_flags[1];
+  const u32 any_pool = st.gate_pool, any_ovf = st.gate_ovf;
   *retry = 0;
+  if ((st.gc.error | any_pool) & ERR_PEER) {
+    set_error("sharded insert: a peer rank did not reach an exchange point in time");
+    return BNX_ERR_CUDA;
+  }
   if (any_pool | any_ovf) {
     // some rank ran short: nobody applied. Every rank drops this attempt's marks; the short ones grow.
     if (any_ovf & OVF_CHUNKS) {
@@ -1401,6 +1588,92 @@ int Map::shard_finish(const void* flags_reduced, int* retry) {
   return grid.maintain(st.gc);
 }
 
+// ------------------------------------------------------------------------------------------------
+// peer-memory exchange: mailboxes
+// ------------------------------------------------------------------------------------------------
+void Map::p2p_close_peers() {
+  for (int o = 0; o < MAX_PEERS; ++o) {
+    if (peer_ipc_[o] && peer_base_[o]) cudaIpcCloseMemHandle(peer_base_[o]);
+    peer_base_[o] = nullptr;
+    peer_ipc_[o] = false;
+  }
+  p2p_ready_ = false;
+}
+
+int Map::p2p_alloc(i64 cap_records, i64 cap_leaves, void* ipc_handle64, void** local_ptr) {
+  BNX_REQUIRE(world_ > 1 && world_ <= MAX_PEERS, "p2p_alloc: call shard_config(rank, 2..16) first");
+  BNX_REQUIRE(cap_records >= 2 && cap_leaves >= 2, "p2p_alloc: capacities must be >= 2");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+  BNX_TRY(drain());
+  BNX_CUDA(cudaStreamSynchronize(grid.stream()));
+  p2p_close_peers();
+  if (mbox_) mbox_retired_.push_back(mbox_);
+  mbox_ = nullptr;
+  const size_t bytes = MBOX_HEADER + (size_t)world_ * ((size_t)cap_records * 16 + (size_t)cap_leaves * 80);
+  void* ptr = nullptr;
+  BNX_CUDA(cudaMalloc(&ptr, bytes));
+  BNX_CUDA(cudaMemset(ptr, 0, MBOX_HEADER));
+  BNX_CUDA(cudaDeviceSynchronize());
+  mbox_ = static_cast<unsigned char*>(ptr);
+  mbox_cap_rec_ = cap_records;
+  mbox_cap_leaf_ = cap_leaves;
+  if (ipc_handle64) {
+    cudaIpcMemHandle_t h;
+    BNX_CUDA(cudaIpcGetMemHandle(&h, ptr));
+    std::memcpy(ipc_handle64, &h, 64);
+  }
+  if (local_ptr) *local_ptr = ptr;
+  return BNX_OK;
+}
+
+int Map::p2p_attach(const void* handles, void* const* local_ptrs) {
+  BNX_REQUIRE(mbox_ != nullptr, "p2p_attach: call p2p_alloc first");
+  BNX_REQUIRE(handles != nullptr || local_ptrs != nullptr, "p2p_attach: null handles");
+  p2p_close_peers();
+  for (int o = 0; o < world_; ++o) {
+    if (o == rank_) {
+      peer_base_[o] = mbox_;
+    } else if (local_ptrs) {
+      BNX_REQUIRE(local_ptrs[o] != nullptr, "p2p_attach: null mailbox pointer");
+      peer_base_[o] = local_ptrs[o];
+    } else {
+      cudaIpcMemHandle_t h;
+      std::memcpy(&h, static_cast<const unsigned char*>(handles) + (size_t)o * 64, 64);
+      void* ptr = nullptr;
+      BNX_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+      peer_base_[o] = ptr;
+      peer_ipc_[o] = true;
+    }
+  }
+  px_host_ = PeerBoxes{};
+  for (int o = 0; o < world_; ++o) {
+    unsigned char* base = static_cast<unsigned char*>(peer_base_[o]);
+    px_host_.flag[o] = reinterpret_cast<u32*>(base);
+    px_host_.rec[o] = reinterpret_cast<int4*>(base + MBOX_HEADER) + (size_t)rank_ * mbox_cap_rec_;
+    px_host_.leaf[o] = reinterpret_cast<int4*>(base + MBOX_HEADER + (size_t)world_ * mbox_cap_rec_ * 16) + (size_t)rank_ * mbox_cap_leaf_ * 5;
+  }
+  BNX_TRY(upload_boxes());
+  BNX_CUDA(cudaStreamSynchronize(grid.stream()));
+  p2p_ready_ = true;
+  return BNX_OK;
+}
+
+// native driver: every rank (re)creates its mailbox and the IPC handles travel through one NCCL all-gather.
+// Collective: all ranks call it at the same point of the protocol with the same capacities.
+int Map::p2p_collective_setup(i64 cap_records, i64 cap_leaves) {
+  const NcclApi& api = nccl_api(nullptr);
+  cudaStream_t s = grid.stream();
+  unsigned char mine[64];
+  BNX_TRY(p2p_alloc(cap_records, cap_leaves, mine, nullptr));
+  BNX_TRY(x_handles_.reserve((size_t)world_ * 64));
+  BNX_CUDA(cudaMemcpyAsync(x_handles_.as<unsigned char>() + (size_t)rank_ * 64, mine, 64, cudaMemcpyHostToDevice, s));
+  BNX_NCCL(api, api.AllGather(x_handles_.as<unsigned char>() + (size_t)rank_ * 64, x_handles_.p, 64, ncclChar, static_cast<ncclComm_t>(comm_), s));
+  std::vector<unsigned char> all((size_t)world_ * 64);
+  BNX_CUDA(cudaMemcpyAsync(all.data(), x_handles_.p, all.size(), cudaMemcpyDeviceToHost, s));
+  BNX_CUDA(cudaStreamSynchronize(s));
+  return p2p_attach(all.data(), nullptr);
+}
+
 // ---- native driver of the sharded protocol (NCCL resolved at run time)
 int Map::nccl_unique_id(const char* nccl_path, void* out128) {
   const NcclApi& api = nccl_api(nccl_path);
@@ -1429,6 +1702,9 @@ int Map::shard_comm_init(const char* nccl_path, const void* unique_id128, int ra
   BNX_NCCL(api, api.CommInitRank(&comm, world, id, rank));
   comm_ = comm;
   BNX_TRY(x_flags_.reserve(64));
+  // data path: peer memory over NVLink unless told otherwise; the mailboxes are created by the first insert
+  const char* ex = std::getenv("BNX_SHARD_EXCHANGE");
+  want_p2p_ = !(ex && std::strcmp(ex, "nccl") == 0) && world <= MAX_PEERS;
   return BNX_OK;
 }
 
@@ -1456,29 +1732,39 @@ int Map::shard_insert(const void* points, i64 stride_bytes, i64 n, bool f64, u32
   if (async && squeue_.size() >= 64) BNX_TRY(drain());  // same count on every rank: draining stays collective
   // equal-split exchange buffers (all ranks compute the same capacities from n_max)
   const i64 want_rec = std::max<i64>(cap_rec_, n_max + 2);
-  if (want_rec != cap_rec_ || !x_send1_.p) {
-    if (async) BNX_TRY(drain());
-    cap_rec_ = want_rec;
-    BNX_TRY(x_send1_.reserve((size_t)world_ * cap_rec_ * 16));
-    BNX_TRY(x_recv1_.reserve((size_t)world_ * cap_rec_ * 16));
+  if (want_p2p_) {
+    // mailboxes: created (and, after an overflow, replaced by larger ones) by all ranks together
+    if (!p2p_ready_ || want_rec > mbox_cap_rec_ || cap_leaf_ > mbox_cap_leaf_) {
+      if (async) BNX_TRY(drain());
+      cap_rec_ = want_rec;
+      BNX_TRY(p2p_collective_setup(cap_rec_, cap_leaf_));
+    }
+  } else {
+    if (want_rec != cap_rec_ || !x_send1_.p) {
+      if (async) BNX_TRY(drain());
+      cap_rec_ = want_rec;
+      BNX_TRY(x_send1_.reserve((size_t)world_ * cap_rec_ * 16));
+      BNX_TRY(x_recv1_.reserve((size_t)world_ * cap_rec_ * 16));
+    }
+    if ((size_t)world_ * cap_leaf_ * 80 > x_send2_.bytes) {
+      if (async) BNX_TRY(drain());
+      BNX_TRY(x_send2_.reserve((size_t)world_ * cap_leaf_ * 80));
+      BNX_TRY(x_recv2_.reserve((size_t)world_ * cap_leaf_ * 80));
+    }
   }
-  if ((size_t)world_ * cap_leaf_ * 80 > x_send2_.bytes) {
-    if (async) BNX_TRY(drain());
-    BNX_TRY(x_send2_.reserve((size_t)world_ * cap_leaf_ * 80));
-    BNX_TRY(x_recv2_.reserve((size_t)world_ * cap_leaf_ * 80));
-  }
+  const bool p2p = want_p2p_;
   u32* flags = x_flags_.as<u32>();
   const u32 my_async = async ? async_next_++ : NONE;
-  BNX_TRY(shard_begin(points, stride_bytes, n, f64, index_base, origin, max_range, x_send1_.p, cap_rec_, where));
+  BNX_TRY(shard_begin(points, stride_bytes, n, f64, index_base, origin, max_range, p2p ? nullptr : x_send1_.p, cap_rec_, where));
   sp_.async_id = my_async;
-  BNX_TRY(all_to_all(x_send1_.p, x_recv1_.p, (size_t)cap_rec_ * 16));
+  if (!p2p) BNX_TRY(all_to_all(x_send1_.p, x_recv1_.p, (size_t)cap_rec_ * 16));
   for (;;) {
-    BNX_TRY(shard_resolve_mark(x_recv1_.p, x_send2_.p, cap_leaf_));
-    BNX_TRY(all_to_all(x_send2_.p, x_recv2_.p, (size_t)cap_leaf_ * 80));
-    BNX_TRY(shard_merge(x_recv2_.p, flags));
-    BNX_NCCL(api, api.AllReduce(flags, flags, 4, ncclUint32, ncclMax, static_cast<ncclComm_t>(comm_), s));
+    BNX_TRY(shard_resolve_mark(p2p ? nullptr : x_recv1_.p, p2p ? nullptr : x_send2_.p, cap_leaf_));
+    if (!p2p) BNX_TRY(all_to_all(x_send2_.p, x_recv2_.p, (size_t)cap_leaf_ * 80));
+    BNX_TRY(shard_merge(p2p ? nullptr : x_recv2_.p, flags));
+    if (!p2p) BNX_NCCL(api, api.AllReduce(flags, flags, 4, ncclUint32, ncclMax, static_cast<ncclComm_t>(comm_), s));
     if (async) {
-      buf_.gate = flags;
+      buf_.gate = p2p ? reinterpret_cast<const u32*>(mbox_) + MBOX_FLAGS4 : flags;
       note_launch(), k_apply_leaves<<<sm_count() * 8, TPB, 0, s>>>(grid.dev(), sp_, buf_);
       BNX_CUDA(cudaGetLastError());
       buf_.gate = nullptr;
@@ -1499,16 +1785,20 @@ int Map::shard_insert(const void* points, i64 stride_bytes, i64 n, bool f64, u32
       return BNX_OK;
     }
     int retry = 0;
-    BNX_TRY(shard_finish(flags, &retry));
+    BNX_TRY(shard_finish(p2p ? nullptr : flags, &retry));
     if (!retry) return BNX_OK;
-    if (retry & (int)(OVF_LEAVES << 8)) {  // every rank saw the same reduced flags: same growth everywhere
-      cap_leaf_ *= 4;
-      BNX_TRY(x_send2_.reserve((size_t)world_ * cap_leaf_ * 80));
-      BNX_TRY(x_recv2_.reserve((size_t)world_ * cap_leaf_ * 80));
-    }
     if (retry & (int)(OVF_RECORDS << 8)) {
       set_error("sharded insert: endpoint record exchange overflowed (n_max too small)");
       return BNX_ERR_INVALID;
+    }
+    if (retry & (int)(OVF_LEAVES << 8)) {  // every rank saw the same reduced flags: same growth everywhere
+      cap_leaf_ *= 4;
+      if (p2p) {
+        // the mailboxes are replaced, the received endpoint records with them: start the scan over (nothing was applied)
+        return shard_insert(points, stride_bytes, n, f64, index_base, n_max, origin, max_range, where, false);
+      }
+      BNX_TRY(x_send2_.reserve((size_t)world_ * cap_leaf_ * 80));
+      BNX_TRY(x_recv2_.reserve((size_t)world_ * cap_leaf_ * 80));
     }
   }
 }
@@ -1542,6 +1832,10 @@ int Map::shard_drain() {
   if (!gc.error) {
     BNX_TRY(scratch_->maintain(sgc));
     return grid.maintain(gc);
+  }
+  if (gc.error & ERR_PEER) {
+    set_error("sharded insert: a peer rank did not reach an exchange point in time");
+    return BNX_ERR_CUDA;
   }
   // every rank is frozen at the same scan (the flags were all-reduced): drop its marks, grow what was short on
   // this rank, then replay the rest of the queue with synchronous (collective) inserts

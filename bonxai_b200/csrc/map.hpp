@@ -6,6 +6,21 @@
 
 namespace bnx {
 
+// sharded map, peer-memory exchange: a rank's mailbox is one device allocation that every peer maps
+// (CUDA IPC across processes, the raw pointer inside one process). The producing kernels store their records straight
+// into block [rank] of the OWNER's inbox over NVLink and the kernel's last block stamps an arrival flag there; the
+// consuming kernel spins on its own flags. No collective launch, no staging copy.
+constexpr int MAX_PEERS = 16;
+constexpr size_t MBOX_HEADER = 4096;      // flag area in front of the two inboxes
+constexpr u32 MBOX_FLAG1 = 0;             // u32[MAX_PEERS]  exchange 1: stamp of the scan whose records have arrived
+constexpr u32 MBOX_FLAG2 = 64;            // u32[MAX_PEERS]  exchange 2
+constexpr u32 MBOX_FLAGS4 = 128;          // uint4[2][MAX_PEERS] {pool error bits, overflow bits, 0, stamp}, slot = stamp & 1
+struct PeerBoxes {
+  int4* rec[MAX_PEERS];   // owner o: block of this rank in o's endpoint-record inbox ([0] = {count})
+  int4* leaf[MAX_PEERS];  // owner o: block of this rank in o's leaf-record inbox
+  u32* flag[MAX_PEERS];   // owner o: its flag area (NULL: the caller moves the staged buffers, no flags)
+};
+
 // everything a scan's kernels need besides the grid, passed by value
 struct ScanParams {
   double ox, oy, oz;  // origin promoted to fp64 (ConvertPoint, grid_coord.hpp:134-162)
@@ -24,6 +39,7 @@ struct ScanParams {
   u32 rec_cap;                 // sharded: slots per peer block of the endpoint record exchange
   u32 leaf_cap2;               // sharded: slots per peer block of the leaf-mask exchange
   u32 touched2_cap;            // sharded: entries of the scratch-grid touched list
+  u32 xseq1, xseq2;            // sharded, peer-memory exchange: arrival stamps of this scan's exchange 1 / exchange 2 + flags
   u32 async_id;                // pipelined insert: serial of this scan (NONE for the synchronous path)
   u32 clean16;                 // pipelined insert: 16-byte units of dedupe table k_mark zeroes for the next scan
   u32 use_transform;           // fused ROS pre-step: drop non-finite points, then T * p in float before classifying
@@ -40,7 +56,13 @@ struct ScanCounters {
   u32 n_touched2;                // sharded: scratch-grid leaves touched (cells owned by other ranks)
   u32 n_dropped;                 // fused pre-step: non-finite points removed from the scan
   GridCounters gc;               // snapshot of the grid counters taken by the last kernel of the scan
+  u32 cnt1[MAX_PEERS];           // sharded: endpoint records bucketed for owner o
+  u32 cnt2[MAX_PEERS];           // sharded: leaf records emitted for owner o
+  u32 done1, done2;              // last-block tickets of the two producing kernels
+  u32 gate_pool, gate_ovf;       // sharded: the reduced error flags the apply pass acted on
+  u32 pad_[2];
 };
+static_assert(sizeof(ScanCounters) % 16 == 0, "cleared in 16-byte units");
 
 // one record per pipelined scan, written by the device into pinned host memory (zero copy) when the scan ends
 struct AsyncRecord {
@@ -65,6 +87,8 @@ struct ScanBuffers {
   u32* touched2;     // sharded: scratch-grid leaves touched in this scan
   const int4* recs;  // sharded: received endpoint records, [world][rec_cap], element 0 of a block = {count}
   const u32* gate;   // sharded: all-reduced error flags; the apply kernels skip when any is set (NULL otherwise)
+  const u32* my_flags;  // sharded, peer-memory exchange: this rank's mailbox flag area (NULL: exchanges run by the caller)
+  const PeerBoxes* px;  // sharded: where the records of this rank go (device memory)
   ScanCounters* sc;
   AsyncRecord* ring;  // pipelined insert: mapped pinned host memory, RING entries
   const u32* poison;  // &GridCounters::error of the map's grid: non-zero freezes every scan kernel
@@ -98,6 +122,14 @@ class Map {
   int shard_comm_init(const char* nccl_path, const void* unique_id128, int rank, int world);
   int shard_insert(const void* points, i64 stride_bytes, i64 n, bool f64, u32 index_base, i64 n_max, const double origin[3], double max_range,
                    int where, bool async);
+  // peer-memory exchange. p2p_alloc: (re)creates this rank's mailbox and returns its CUDA IPC handle (64 bytes) and
+  // raw device pointer; p2p_attach: maps the mailboxes of all ranks (handles: [world][64] bytes; local_ptrs != NULL:
+  // the shards live in this process and the raw pointers are used). The staged calls then take NULL buffers.
+  // shard_comm_init does both itself (handles all-gathered through NCCL) unless BNX_SHARD_EXCHANGE=nccl.
+  int p2p_alloc(i64 cap_records, i64 cap_leaves, void* ipc_handle64, void** local_ptr);
+  int p2p_attach(const void* handles, void* const* local_ptrs);
+  int exchange_kind() const { return p2p_ready_ ? 2 : (comm_ ? 1 : 0); }  // 0 caller, 1 NCCL, 2 peer memory
+  i64 mailbox_cap(int which) const { return which ? mbox_cap_leaf_ : mbox_cap_rec_; }
 
   // ---- pipelined insert: enqueue a scan and return; drain() completes everything queued (growing pools and
   // replaying from the first scan that ran short, if any). Input buffers must stay valid until drain().
@@ -131,6 +163,7 @@ class Map {
   void* comm_ = nullptr;  // ncclComm_t
   DevBuf x_send1_, x_recv1_, x_send2_, x_recv2_, x_flags_;
   i64 cap_rec_ = 0, cap_leaf_ = 1 << 13;
+  bool staged_p2p_ = false;  // the scan in flight uses the mailboxes
   struct ShardQueued {
     const void* points;
     i64 stride, n, n_max;
@@ -142,6 +175,19 @@ class Map {
   std::vector<ShardQueued> squeue_;
   int all_to_all(const void* send, void* recv, size_t block_bytes);
   int shard_drain();
+  int p2p_collective_setup(i64 cap_records, i64 cap_leaves);
+  void p2p_close_peers();
+  int upload_boxes();
+  unsigned char* mbox_ = nullptr;  // this rank's mailbox: [flags 4 KiB | inbox1 [world][cap_rec] x 16 B | inbox2 [world][cap_leaf] x 80 B]
+  i64 mbox_cap_rec_ = 0, mbox_cap_leaf_ = 0;
+  std::vector<void*> mbox_retired_;  // replaced mailboxes stay allocated until the map dies (a slow peer may still map them)
+  void* peer_base_[MAX_PEERS] = {};
+  bool peer_ipc_[MAX_PEERS] = {};
+  bool p2p_ready_ = false;
+  u32 xseq1_ = 0, xseq2_ = 0;  // arrival stamps: every rank enqueues the same sequence of exchanges
+  PeerBoxes px_host_ = {}, px_uploaded_ = {};
+  bool px_uploaded_valid_ = false, want_p2p_ = false;
+  DevBuf b_px_, x_handles_;
   // pipelined insert
   static constexpr u32 RING = 1024;
   struct Queued {

@@ -18,6 +18,7 @@ struct NcclApi {
   ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   void* handle = nullptr;
   bool ok = false;
@@ -43,9 +44,10 @@ inline const NcclApi& nccl_api(const char* path) {
   api.Send = reinterpret_cast<decltype(api.Send)>(sym("ncclSend"));
   api.Recv = reinterpret_cast<decltype(api.Recv)>(sym("ncclRecv"));
   api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
+  api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
   api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
   api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.GroupStart && api.GroupEnd && api.Send && api.Recv &&
-           api.AllReduce && api.GetErrorString;
+           api.AllReduce && api.AllGather && api.GetErrorString;
   return api;
 }
 

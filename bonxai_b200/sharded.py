@@ -3,9 +3,12 @@
 Each rank owns the roots with shard_owner(root) == rank and holds 1/world of every scan's points. The CUDA
 stages live behind the C ABI (bnx_map_shard_*); this module only moves the staged device buffers between ranks:
 
-    ShardedMap       one process per GPU, exchanges = torch.distributed (NCCL) all_to_all_single / all_reduce
-    LocalShardGroup  all shards in ONE process on one GPU, exchanges = block transposes on the device; used by
-                     the single-GPU tests to run the whole protocol (every kernel, every record format)
+    ShardedMap       one process per GPU; the library drives the scan itself (bnx_map_shard_insert): records go
+                     straight into the owners' mailboxes over NVLink (peer memory, CUDA IPC; NCCL only bootstraps),
+                     or through NCCL send/recv collectives with BNX_SHARD_EXCHANGE=nccl
+    LocalShardGroup  all shards in ONE process on one GPU; exchange="transpose": the staged buffers are moved by
+                     block transposes on the device, exchange="p2p": the mailbox kernels, with the raw pointers of
+                     the other shards as "peers". Used by the single-GPU tests to run the whole protocol
 
 Bit-exactness: the union of the shards' forEachCell dumps equals the unsharded map's dump after every scan.
 """
@@ -31,7 +34,7 @@ def split_points(n: int, world: int):
 class _Shard:
     """a ProbabilisticMap shard + its staging buffers (torch CUDA tensors)"""
 
-    def __init__(self, resolution: float, rank: int, world: int, device, cap_records: int = 1 << 15, cap_leaves: int = 1 << 13):
+    def __init__(self, resolution: float, rank: int, world: int, device, cap_records: int = 1 << 15, cap_leaves: int = 1 << 13, p2p: bool = False):
         import torch
         self.torch = torch
         self.rank, self.world, self.device = rank, world, device
@@ -39,10 +42,26 @@ class _Shard:
         self.lib = self.map.lib
         capi._check(self.lib.bnx_map_shard_config(self.map.h, rank, world))
         self.cap_records, self.cap_leaves = 0, 0
-        self._alloc_records(cap_records)
-        self._alloc_leaves(cap_leaves)
-        self.flags = torch.zeros(4, dtype=torch.int32, device=device)
+        self.p2p = p2p
+        self.mailbox = None
+        if p2p:
+            self.cap_records, self.cap_leaves = int(cap_records), int(cap_leaves)
+            self.alloc_mailbox()
+        else:
+            self._alloc_records(cap_records)
+            self._alloc_leaves(cap_leaves)
+            self.flags = torch.zeros(4, dtype=torch.int32, device=device)
         self.n_local = 0
+
+    # ---- peer-memory exchange: this shard's mailbox (bnx_map_shard_p2p_*)
+    def alloc_mailbox(self):
+        ptr = C.c_void_p(0)
+        capi._check(self.lib.bnx_map_shard_p2p_alloc(self.map.h, C.c_int64(self.cap_records), C.c_int64(self.cap_leaves), None, C.byref(ptr)))
+        self.mailbox = ptr.value
+
+    def attach(self, mailboxes):
+        arr = (C.c_void_p * self.world)(*mailboxes)
+        capi._check(self.lib.bnx_map_shard_p2p_attach(self.map.h, None, arr))
 
     def _alloc_records(self, cap):
         t = self.torch
@@ -61,7 +80,7 @@ class _Shard:
 
     # ---- the four stages (bnx_map_shard_*)
     def begin(self, pts, n, stride_bytes, f64, index_base, origin, max_range):
-        if n + 2 > self.cap_records:
+        if n + 2 > self.cap_records and not self.p2p:
             self._alloc_records(max(n + 2, self.cap_records * 2))
         o = np.ascontiguousarray(origin, dtype=np.float64)
         if isinstance(pts, capi.DevPtr):
@@ -70,20 +89,26 @@ class _Shard:
             arr = np.ascontiguousarray(pts)
             p, where = C.c_void_p(arr.ctypes.data), capi.BNX_HOST
         self.n_local = n
+        send1 = None if self.p2p else C.c_void_p(self.send1.data_ptr())
         capi._check(self.lib.bnx_map_shard_begin(self.map.h, p, C.c_int64(stride_bytes), C.c_int64(n), int(bool(f64)), C.c_uint32(index_base),
-                                                 C.c_void_p(o.ctypes.data), C.c_double(max_range), C.c_void_p(self.send1.data_ptr()),
-                                                 C.c_int64(self.cap_records), where))
+                                                 C.c_void_p(o.ctypes.data), C.c_double(max_range), send1, C.c_int64(self.cap_records), where))
 
     def resolve_mark(self):
-        capi._check(self.lib.bnx_map_shard_resolve_mark(self.map.h, C.c_void_p(self.recv1.data_ptr()), C.c_void_p(self.send2.data_ptr()),
-                                                        C.c_int64(self.cap_leaves)))
+        if self.p2p:
+            capi._check(self.lib.bnx_map_shard_resolve_mark(self.map.h, None, None, C.c_int64(0)))
+        else:
+            capi._check(self.lib.bnx_map_shard_resolve_mark(self.map.h, C.c_void_p(self.recv1.data_ptr()), C.c_void_p(self.send2.data_ptr()),
+                                                            C.c_int64(self.cap_leaves)))
 
     def merge(self):
-        capi._check(self.lib.bnx_map_shard_merge(self.map.h, C.c_void_p(self.recv2.data_ptr()), C.c_void_p(self.flags.data_ptr())))
+        if self.p2p:
+            capi._check(self.lib.bnx_map_shard_merge(self.map.h, None, None))
+        else:
+            capi._check(self.lib.bnx_map_shard_merge(self.map.h, C.c_void_p(self.recv2.data_ptr()), C.c_void_p(self.flags.data_ptr())))
 
     def finish(self) -> int:
         retry = C.c_int(0)
-        capi._check(self.lib.bnx_map_shard_finish(self.map.h, C.c_void_p(self.flags.data_ptr()), C.byref(retry)))
+        capi._check(self.lib.bnx_map_shard_finish(self.map.h, None if self.p2p else C.c_void_p(self.flags.data_ptr()), C.byref(retry)))
         return retry.value
 
     def grow_after(self, retry: int):
@@ -145,6 +170,12 @@ class ShardedMap:
         """completes the pipelined scans; collective: every rank must call it at the same point"""
         self.map.sync()
 
+    def exchange_kind(self) -> str:
+        """how the per-scan records travel: "p2p" (mailboxes in peer memory; after the first insert) or "nccl" """
+        kind = C.c_int(0)
+        capi._check(self.lib.bnx_map_shard_exchange(self.map.h, C.byref(kind)))
+        return {0: "caller", 1: "nccl", 2: "p2p"}[kind.value]
+
     def counters(self):
         return self.map.counters()
 
@@ -156,15 +187,34 @@ class LocalShardGroup:
     """all `world` shards of one map inside ONE process on one GPU: the exchanges are device-side block
     transposes. Same stages, kernels and record formats as ShardedMap; no NCCL needed."""
 
-    def __init__(self, resolution: float, world: int, device="cuda:0", cap_leaves: int = 1 << 13):
+    def __init__(self, resolution: float, world: int, device="cuda:0", cap_leaves: int = 1 << 13, exchange: str = "transpose",
+                 cap_records: int = 1 << 15):
         import torch
+        assert exchange in ("transpose", "p2p")
         self.torch = torch
         self.world = world
-        self.shards = [_Shard(resolution, r, world, torch.device(device), cap_leaves=cap_leaves) for r in range(world)]
+        self.p2p = exchange == "p2p"
+        self.shards = [_Shard(resolution, r, world, torch.device(device), cap_records=cap_records, cap_leaves=cap_leaves, p2p=self.p2p)
+                       for r in range(world)]
+        # one stream for all shards: every producer of a stage is enqueued before any consumer of the next stage
         stream = torch.cuda.current_stream().cuda_stream
         for s in self.shards:
             s.set_stream(stream)
+        if self.p2p:
+            self._attach_all()
         self.attempts = 0
+
+    def _attach_all(self):
+        boxes = [s.mailbox for s in self.shards]
+        for s in self.shards:
+            s.attach(boxes)
+
+    def _regrow_mailboxes(self, cap_records=None, cap_leaves=None):
+        for s in self.shards:
+            s.cap_records = int(cap_records or s.cap_records)
+            s.cap_leaves = int(cap_leaves or s.cap_leaves)
+            s.alloc_mailbox()
+        self._attach_all()
 
     def insert(self, pts: np.ndarray, origin, max_range):
         pts = np.ascontiguousarray(pts)
@@ -172,28 +222,46 @@ class LocalShardGroup:
         stride = pts.shape[1] * pts.dtype.itemsize
         parts = split_points(len(pts), self.world)
         need = max(hi - lo for lo, hi in parts) + 2
-        for s in self.shards:
-            if need > s.cap_records:
-                s._alloc_records(max(need, s.cap_records * 2))
-        for s, (lo, hi) in zip(self.shards, parts):
-            s.begin(pts[lo:hi], hi - lo, stride, f64, lo, origin, max_range)
-        self._exchange("send1", "recv1")
+        if self.p2p:
+            if need > self.shards[0].cap_records:
+                self._regrow_mailboxes(cap_records=max(need, self.shards[0].cap_records * 2))
+        else:
+            for s in self.shards:
+                if need > s.cap_records:
+                    s._alloc_records(max(need, s.cap_records * 2))
         while True:
-            self.attempts += 1
-            for s in self.shards:
-                s.resolve_mark()
-            self._exchange("send2", "recv2")
-            for s in self.shards:
-                s.merge()
-            flags = self.torch.stack([s.flags for s in self.shards]).max(dim=0).values
-            for s in self.shards:
-                s.flags.copy_(flags)
-            retries = [s.finish() for s in self.shards]
-            assert len(set(retries)) == 1
-            if not retries[0]:
-                return
-            for s in self.shards:
-                s.grow_after(retries[0])
+            for s, (lo, hi) in zip(self.shards, parts):
+                s.begin(pts[lo:hi], hi - lo, stride, f64, lo, origin, max_range)
+            if not self.p2p:
+                self._exchange("send1", "recv1")
+            restart = False
+            while not restart:
+                self.attempts += 1
+                for s in self.shards:
+                    s.resolve_mark()
+                if not self.p2p:
+                    self._exchange("send2", "recv2")
+                for s in self.shards:
+                    s.merge()
+                if not self.p2p:
+                    flags = self.torch.stack([s.flags for s in self.shards]).max(dim=0).values
+                    for s in self.shards:
+                        s.flags.copy_(flags)
+                retries = [s.finish() for s in self.shards]
+                assert len(set(retries)) == 1
+                if not retries[0]:
+                    return
+                if self.p2p:
+                    if retries[0] & (4 << 8):
+                        raise RuntimeError("endpoint record exchange overflowed")
+                    if retries[0] & (8 << 8):
+                        # larger mailboxes replace the old ones, and with them the received endpoint records:
+                        # the scan starts over (a failed attempt has changed nothing)
+                        self._regrow_mailboxes(cap_leaves=self.shards[0].cap_leaves * 4)
+                        restart = True
+                else:
+                    for s in self.shards:
+                        s.grow_after(retries[0])
 
     def _exchange(self, send, recv):
         # all-to-all: block o of rank r's send buffer becomes block r of rank o's receive buffer

@@ -244,6 +244,27 @@ BNX_API int bnx_map_shard_insert(bnx_map_t* m, const void* points, int64_t strid
                                  uint32_t index_base, int64_t n_max, const double origin[3], double max_range, int where,
                                  int async);
 
+
+/* Peer-memory exchange (NVLink P2P stores instead of collectives). Every rank owns a MAILBOX — one device allocation
+ * [arrival flags | endpoint-record inbox [world][cap_records] | leaf-record inbox [world][cap_leaves]] — that all
+ * peers map (CUDA IPC between processes, the raw pointer inside one process). The producing kernels of
+ * shard_begin / shard_resolve_mark / shard_merge store their records straight into block [rank] of the OWNER's
+ * inbox and their last thread block stamps an arrival flag there; the consuming kernels (and the apply pass, for the
+ * error flags) spin on the flags of their own mailbox. A scan then needs no collective launch and no staging copy.
+ *   bnx_map_shard_p2p_alloc   (re)creates the mailbox of this rank; returns its 64-byte cudaIpcMemHandle_t and/or
+ *                             its device pointer (either may be NULL). world <= 16.
+ *   bnx_map_shard_p2p_attach  ipc_handles: [world][64] bytes gathered from all ranks, or device_ptrs: [world] raw
+ *                             pointers when all shards live in this process. Afterwards the staged calls take NULL
+ *                             for their buffer arguments (send_records, recv_records, send_leaves, recv_leaves,
+ *                             flags, flags_reduced) and use the mailboxes.
+ * bnx_map_shard_comm_init + bnx_map_shard_insert do all of this themselves (handles all-gathered through NCCL,
+ * mailboxes re-created collectively when an exchange overflowed) unless BNX_SHARD_EXCHANGE=nccl is set; NCCL then
+ * only bootstraps. bnx_map_shard_exchange: 0 caller-run, 1 NCCL collectives, 2 peer memory. A peer that never
+ * arrives turns into an error after 8 s, not a hang. */
+BNX_API int bnx_map_shard_p2p_alloc(bnx_map_t* m, int64_t cap_records, int64_t cap_leaves, void* ipc_handle64, void** device_ptr);
+BNX_API int bnx_map_shard_p2p_attach(bnx_map_t* m, const void* ipc_handles, void* const* device_ptrs);
+BNX_API int bnx_map_shard_exchange(const bnx_map_t* m, int* kind);
+
 #ifdef __cplusplus
 }
 #endif

@@ -47,9 +47,11 @@ def main():
             order = np.lexsort((gx[:, 2], gx[:, 1], gx[:, 0]))
             ox, ow = om.dump()
             assert np.array_equal(gx[order], ox) and np.array_equal(gw[order], ow), f"scan {scan}: sharded map differs from the oracle"
+    want = os.environ.get("BNX_SHARD_EXCHANGE", "p2p")
+    assert sm.exchange_kind() == want, (sm.exchange_kind(), want)
     dist.barrier()
     if rank == 0:
-        print("SHARDED_OK", world)
+        print("SHARDED_OK", world, sm.exchange_kind())
     dist.destroy_process_group()
 
 

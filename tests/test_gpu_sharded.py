@@ -15,10 +15,11 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+@pytest.mark.parametrize("exchange", ["transpose", "p2p"])
 @pytest.mark.parametrize("world", [2, 3, 8])
-def test_local_shard_group_equals_oracle(bnx, port, world):
+def test_local_shard_group_equals_oracle(bnx, port, world, exchange):
     from bonxai_b200.sharded import LocalShardGroup
-    g, om = LocalShardGroup(0.1, world), port.map(0.1)
+    g, om = LocalShardGroup(0.1, world, exchange=exchange), port.map(0.1)
     for scan in range(4):
         pts, origin = synth.lidar_scan(scan * 3, beams=32, azimuths=1024)
         g.insert(pts, origin, 40.0)
@@ -31,10 +32,11 @@ def test_local_shard_group_equals_oracle(bnx, port, world):
     assert sum(sizes) == om.active_count() and min(sizes) > 0
 
 
-def test_local_shard_group_random_and_stale(bnx, port):
+@pytest.mark.parametrize("exchange", ["transpose", "p2p"])
+def test_local_shard_group_random_and_stale(bnx, port, exchange):
     from bonxai_b200.sharded import LocalShardGroup
     rng = np.random.default_rng(3)
-    g, om = LocalShardGroup(0.05, 4), port.map(0.05)
+    g, om = LocalShardGroup(0.05, 4, exchange=exchange), port.map(0.05)
     a = (rng.normal(0, 2.0, (3000, 3))).astype(np.float32)
     b = (rng.normal(0, 2.0, (2500, 3)) + [0.5, 0, 0]).astype(np.float32)
     a[:400] = a[0]  # duplicates split across ranks: the lowest GLOBAL index must win
@@ -49,11 +51,12 @@ def test_local_shard_group_random_and_stale(bnx, port):
     assert_same_dump(g.dump(), om.dump(), "f64 scan")
 
 
-def test_local_shard_group_growth_and_small_exchange_buffers(bnx, port, monkeypatch):
+@pytest.mark.parametrize("exchange", ["transpose", "p2p"])
+def test_local_shard_group_growth_and_small_exchange_buffers(bnx, port, monkeypatch, exchange):
     monkeypatch.setenv("BNX_INIT_LEAF_MB", "1")
     monkeypatch.setenv("BNX_INIT_INNER_MB", "0")
     from bonxai_b200.sharded import LocalShardGroup
-    g, om = LocalShardGroup(0.1, 2, cap_leaves=64), port.map(0.1)
+    g, om = LocalShardGroup(0.1, 2, cap_leaves=64, exchange=exchange, cap_records=1 << 12), port.map(0.1)
     for scan in range(2):
         pts, origin = synth.lidar_scan(scan, beams=32, azimuths=1024)
         g.insert(pts, origin, 40.0)
@@ -62,14 +65,16 @@ def test_local_shard_group_growth_and_small_exchange_buffers(bnx, port, monkeypa
     assert g.attempts > 2  # pools and the leaf exchange buffer had to grow
 
 
+@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
 @pytest.mark.parametrize("mode,tiny", [("sync", False), ("async", False), ("async", True)])
-def test_nccl_two_ranks(bnx, mode, tiny):
-    """the native NCCL driver (bnx_map_shard_insert) on 2 GPUs: synchronous, pipelined, and pipelined with pools so
-    small that a queued scan runs short and all ranks freeze + replay"""
+def test_nccl_two_ranks(bnx, mode, tiny, exchange):
+    """the native driver (bnx_map_shard_insert) on 2 GPUs, one process each, with the peer-memory exchange (CUDA IPC
+    mailboxes over NVLink) and with NCCL collectives: synchronous, pipelined, and pipelined with pools so small that a
+    queued scan runs short and all ranks freeze + replay"""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    env = dict(os.environ, BNX_SHARD_TEST_MODE=mode)
+    env = dict(os.environ, BNX_SHARD_TEST_MODE=mode, BNX_SHARD_EXCHANGE=exchange)
     if tiny:
         env.update(BNX_INIT_LEAF_MB="2", BNX_INIT_INNER_MB="0")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
