@@ -446,6 +446,17 @@ def run_gpu_sharded(args):
     dist.all_reduce(active, op=dist.ReduceOp.SUM)
     attempts = 0
     exchange = sm.exchange_kind()
+    # stage times of the sharded scan (CUDA events on the map's stream, one scan at a time; every stage includes the
+    # wait for the peers' records it consumes): a separate, untimed pass over the first scans again
+    sm.map.set_profiling(True)
+    acc, reps = {}, min(20, K)
+    for i in range(W, W + reps):
+        sm.insert(capi.DevPtr(dev[i].data_ptr()), n_local, 16, lo, n_max, slices[i][1], MAX_RANGE, use_async=True)
+        sm.sync()
+        pt = sm.map.phase_times()
+        for k, name in (("classify", "begin"), ("resolve", "resolve_mark"), ("mark", "merge"), ("apply", "apply"), ("total", "total")):
+            acc[name] = acc.get(name, 0.0) + pt[k] / reps
+    sm.map.set_profiling(False)
     del sm
 
     pinned = [torch.from_numpy(p).pin_memory().numpy() for p, _ in slices]
@@ -487,6 +498,8 @@ def run_gpu_sharded(args):
                        "attempts": attempts},
             "voxel_updates_per_s": U_all / secs, "ray_visits_per_s": V_all / secs, "rays_per_s": E_all / secs,
             "updates_per_scan": U_all / K, "visits_per_scan": V_all / K,
+            "phase_us_per_scan": {**acc, "note": "rank 0, one scan at a time; begin = classify + bucket, resolve_mark = wait(exchange 1) + dedupe + "
+                                  "resolve + mark + emit, merge = wait(exchange 2) + merge + flags, apply = wait(flags) + apply"},
             "roofline": {"bound": "hbm", "kernel": "whole sharded step (per-kernel events are taken in the 1-GPU run)", "achieved": achieved, "peak": peak,
                          "peak_kind": peak_kind + f" x{world}", "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "algorithmic_bytes_per_launch": alg_bytes},

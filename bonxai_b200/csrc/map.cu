@@ -98,6 +98,7 @@ __device__ __forceinline__ void publish_blocks(const PeerBoxes* px, bool leaves,
   if (threadIdx.x == 0) s_last = atomicAdd(done, 1u) == gridDim.x - 1;
   __syncthreads();
   if (!s_last) return;
+  if (threadIdx.x == 0) *done = 0u;  // ready for the next scan (the pipelined path does not memset the counters)
   if (threadIdx.x < world) {
     const u32 o = threadIdx.x;
     const u32 c = min(*reinterpret_cast<const volatile u32*>(cnt + o), cap - 1u);
@@ -267,11 +268,43 @@ __host__ __device__ __forceinline__ u32 shard_owner(int rx, int ry, int rz, u32 
   return (u32)((hash3(rx, ry, rz) >> 34) % world);
 }
 
+// Sharded map, receiver side of exchange 1: the inbox is [world][rec_cap] records with the count in element 0 of every
+// block. The records of all blocks are addressed as ONE dense range 0..R-1 (block after block), so that the threads of
+// the receiving kernels are fully used whatever the split between the senders is.
+// Called by FULL warps: lane s reads the header of block s, a warp scan turns the counts into ranges. Returns R and, for
+// i < R, the record itself.
+__device__ __forceinline__ u32 shard_locate(const ScanParams& p, const ScanBuffers& b, u32 i, bool& found, int4& e) {
+  const u32 lane = threadIdx.x & 31;
+  u32 incl = lane < p.world ? min((u32)__ldcg(&b.recs[(size_t)lane * p.rec_cap]).x, p.rec_cap - 1u) : 0u;
+  for (int o = 1; o < 32; o <<= 1) {
+    const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= (u32)o) incl += t;
+  }
+  const u32 total = __shfl_sync(0xffffffffu, incl, 31);
+  found = false;
+  u32 base = 0;
+  for (u32 src = 0; src < p.world; ++src) {
+    const u32 end = __shfl_sync(0xffffffffu, incl, src);
+    if (!found && i >= base && i < end) {
+      found = true;
+      e = __ldcg(&b.recs[(size_t)src * p.rec_cap + 1u + (i - base)]);
+    }
+    base = end;
+  }
+  return total;
+}
+// the receiver's dedupe table only uses as many slots as the records that actually arrived need (load <= 1/2)
+__device__ __forceinline__ u32 shard_table_mask(const ScanParams& p, u32 received) {
+  u32 slots = 1024u;
+  while (slots < 2u * received) slots <<= 1;
+  return min(slots - 1u, p.hash_mask);
+}
+
 // MODE 0: one thread per point of the scan (winner = lowest index of its endpoint voxel).
 // MODE 1: one thread per queued addHitPoint / addMissPoint endpoint (already updated and stamped when it was
 //         queued; it only needs its ray).
-// MODE 2: sharded map — one thread per slot of the received endpoint records [world][rec_cap]; w = global point
-//         index << 1 | type, winner = lowest w of its voxel.
+// MODE 2: sharded map — one thread per received endpoint record (dense range over the [world][rec_cap] inbox);
+//         w = global point index << 1 | type, winner = lowest w of its voxel.
 template <int MODE>
 __global__ void __launch_bounds__(TPB) k_resolve(GridDev g, ScanParams p, ScanBuffers b, u32 count) {
   constexpr bool PENDING = MODE == 1;
@@ -287,18 +320,16 @@ __global__ void __launch_bounds__(TPB) k_resolve(GridDev g, ScanParams p, ScanBu
   bool is_end = false, winner = false;
   int4 e = make_int4(0, 0, 0, 0);
   u32 leaf = NONE, ci = 0, m = 0, chunks = 0;
-  if (i < count) {
+  if (MODE == 2) {
+    shard_locate(p, b, i, winner, e);
+    if (winner) {
+      winner = b.table[b.slot_of[i]] == ~(u32)e.w;
+      e.w &= 1;
+    }
+  } else if (i < count) {
     if (MODE == 1) {
       e = b.pending[i];
       winner = true;
-    } else if (MODE == 2) {
-      const u32 j = i % p.rec_cap;
-      winner = j >= 1u && j <= (u32)b.recs[i - j].x;  // a filled slot of its peer block
-      if (winner) {
-        e = b.recs[i];
-        winner = b.table[b.slot_of[i]] == ~(u32)e.w;
-        e.w &= 1;
-      }
     } else {
       const u32 slot = b.slot_of[i];  // NONE: the point was dropped by the fused pre-step
       winner = slot != NONE && b.table[slot] == (p.packed ? ~i : i + 1u);
@@ -521,8 +552,23 @@ __global__ void __launch_bounds__(TPB, MARK_MIN_BLOCKS) k_mark(GridDev g, GridDe
   // pipelined insert: the dedupe table was last read by k_resolve; leave it zeroed for the next scan's k_classify
   // (saves a clearing launch per scan). Skipped when the pipeline is frozen, like every other write.
   if (p.clean16) {
-    uint4* tab = reinterpret_cast<uint4*>(b.table);
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < p.clean16; i += gridDim.x * blockDim.x) tab[i] = make_uint4(0, 0, 0, 0);
+    if (SHARD) {  // the receiver's table: only the slots the arrived records could use (table and keys are apart)
+      int4 e_;
+      bool f_;
+      const u32 n16 = (shard_table_mask(p, shard_locate(p, b, NONE, f_, e_)) + 1u) / 4u;
+      uint4* tab = reinterpret_cast<uint4*>(b.table);
+      uint4* keys = reinterpret_cast<uint4*>(b.keys);
+      for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < 3u * n16; i += gridDim.x * blockDim.x) {
+        if (i < n16) {
+          tab[i] = make_uint4(0, 0, 0, 0);
+        } else {
+          keys[i - n16] = make_uint4(0, 0, 0, 0);
+        }
+      }
+    } else {
+      uint4* tab = reinterpret_cast<uint4*>(b.table);
+      for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < p.clean16; i += gridDim.x * blockDim.x) tab[i] = make_uint4(0, 0, 0, 0);
+    }
   }
   const u32 lane = threadIdx.x & 31;
   const u32 warps = gridDim.x * (TPB / 32);
@@ -787,23 +833,26 @@ __global__ void __launch_bounds__(TPB) k_shard_bucket(ScanParams p, ScanBuffers 
   publish_blocks(b.px, false, b.sc->cnt1, &b.sc->done1, MBOX_FLAG1, p.rank, p.xseq1, p.world, cap);
 }
 
-// exchange 1, receiver: lowest global index per endpoint voxel over the records of all ranks
-__global__ void __launch_bounds__(TPB) k_shard_dedupe(ScanParams p, ScanBuffers b, u32 count) {
+// exchange 1, receiver: lowest global index per endpoint voxel over the records of all ranks. Pipelined path: also
+// zeroes the sender-side dedupe table of this scan (its last reader, k_shard_bucket, is done) for the next scan.
+__global__ void __launch_bounds__(TPB) k_shard_dedupe(ScanParams p, ScanBuffers b, u32 count, uint4* clean, u32 clean16) {
   // peer-memory exchange: the records of every rank must have arrived (the wait happens even when the pipeline is
   // frozen, so that no rank ever runs ahead of an exchange point)
   wait_arrivals(b.my_flags ? b.my_flags + MBOX_FLAG1 : nullptr, 1, p.world, p.xseq1, const_cast<u32*>(b.poison));
+  if (*b.poison) return;
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= count || *b.poison) return;
-  const u32 j = i % p.rec_cap;
-  if (j == 0u || j > (u32)__ldcg(&b.recs[i - j]).x) return;
-  const int4 e = __ldcg(&b.recs[i]);
+  for (u32 k = i; k < clean16; k += gridDim.x * blockDim.x) clean[k] = make_uint4(0, 0, 0, 0);
+  int4 e;
+  bool found;
+  const u32 mask = shard_table_mask(p, shard_locate(p, b, i, found, e));
+  if (!found) return;
   const unsigned long long key = pack_key(e);
-  u32 slot = (u32)hash3(e.x, e.y, e.z) & p.hash_mask;
+  u32 slot = (u32)hash3(e.x, e.y, e.z) & mask;
   for (;;) {
     unsigned long long k = b.keys[slot];
     if (k == 0ull) k = atomicCAS(&b.keys[slot], 0ull, key);
     if (k == 0ull || k == key) break;
-    slot = (slot + 1) & p.hash_mask;
+    slot = (slot + 1) & mask;
   }
   atomicMax(&b.table[slot], ~(u32)e.w);
   b.slot_of[i] = slot;
@@ -840,33 +889,10 @@ __global__ void __launch_bounds__(TPB) k_shard_emit(GridDev gs, ScanParams p, Sc
   publish_blocks(b.px, true, b.sc->cnt2, &b.sc->done2, MBOX_FLAG2, p.rank, p.xseq2, p.world, cap);
 }
 
-// exchange 2, receiver: OR the remote masks into this rank's leaves (one warp per record)
-__global__ void __launch_bounds__(TPB) k_shard_merge(GridDev g, ScanParams p, ScanBuffers b, const int4* recv, u32 cap) {
-  const u32 lane = threadIdx.x & 31;
-  const u32 warps = gridDim.x * (TPB / 32);
-  const u32 slots = p.world * cap;
-  wait_arrivals(b.my_flags ? b.my_flags + MBOX_FLAG2 : nullptr, 1, p.world, p.xseq2, const_cast<u32*>(b.poison));
-  if (*b.poison) return;
-  for (u32 t = blockIdx.x * (TPB / 32) + (threadIdx.x >> 5); t < slots; t += warps) {
-    const u32 j = t % cap;
-    const int4* block = recv + (size_t)(t - j) * 5;
-    if (j == 0u || j > min((u32)__ldcg(&block[0]).x, cap - 1u)) continue;
-    const int4 hdr = __ldcg(&block[(size_t)j * 5]);
-    u32 leaf = NONE;
-    if (lane == 0) leaf = leaf_find_or_create(g, hdr.x, hdr.y, hdr.z);
-    leaf = __shfl_sync(0xffffffffu, leaf, 0);
-    if (leaf == NONE) continue;
-    if (lane < 8) {
-      const unsigned long long bits = __ldcg(reinterpret_cast<const unsigned long long*>(block + (size_t)j * 5 + 1) + lane);
-      if (bits) mark_bits(g, leaf, reinterpret_cast<unsigned long long*>(leaf_touched(g, leaf)) + lane, bits, p.seq, &b.sc->n_touched, b.touched, p.touched_cap);
-    }
-  }
-}
-
-// flags of this rank for the reduction (MAX / OR) that gates the apply phase on every rank. Caller-run exchange and
+// This rank's error flags for the reduction (OR) that gates the apply phase on every rank. Caller-run exchange and
 // NCCL: written to `flags`, all-reduced afterwards. Peer memory: stored into slot [rank] of every rank's flag table
-// (values first, then the stamp), the apply kernel ORs the table itself. One warp.
-__global__ void k_shard_flags(GridDev g, GridDev gs, ScanParams p, ScanBuffers b, u32* flags) {
+// (values first, then the stamp); the apply kernel ORs the table itself. Threads 0..world-1 of one block.
+__device__ __forceinline__ void shard_flags(const GridDev& g, const GridDev& gs, const ScanParams& p, const ScanBuffers& b, u32* flags) {
   const u32 f0 = g.ctr->error | (gs.ctr->error << 8), f1 = b.sc->overflow;
   if (b.px->flag[0] == nullptr) {
     if (threadIdx.x == 0) {
@@ -884,6 +910,38 @@ __global__ void k_shard_flags(GridDev g, GridDev gs, ScanParams p, ScanBuffers b
     __threadfence_system();
     st_release_sys(dst + 3, p.xseq2);
   }
+}
+
+// exchange 2, receiver: OR the remote masks into this rank's leaves (one warp per record); the last block then
+// publishes this rank's error flags
+__global__ void __launch_bounds__(TPB) k_shard_merge(GridDev g, GridDev gs, ScanParams p, ScanBuffers b, const int4* recv, u32 cap, u32* flags) {
+  const u32 lane = threadIdx.x & 31;
+  const u32 warps = gridDim.x * (TPB / 32);
+  const u32 slots = p.world * cap;
+  wait_arrivals(b.my_flags ? b.my_flags + MBOX_FLAG2 : nullptr, 1, p.world, p.xseq2, const_cast<u32*>(b.poison));
+  const bool frozen = *b.poison != 0u;
+  for (u32 t = blockIdx.x * (TPB / 32) + (threadIdx.x >> 5); t < slots && !frozen; t += warps) {
+    const u32 j = t % cap;
+    const int4* block = recv + (size_t)(t - j) * 5;
+    if (j == 0u || j > min((u32)__ldcg(&block[0]).x, cap - 1u)) continue;
+    const int4 hdr = __ldcg(&block[(size_t)j * 5]);
+    u32 leaf = NONE;
+    if (lane == 0) leaf = leaf_find_or_create(g, hdr.x, hdr.y, hdr.z);
+    leaf = __shfl_sync(0xffffffffu, leaf, 0);
+    if (leaf == NONE) continue;
+    if (lane < 8) {
+      const unsigned long long bits = __ldcg(reinterpret_cast<const unsigned long long*>(block + (size_t)j * 5 + 1) + lane);
+      if (bits) mark_bits(g, leaf, reinterpret_cast<unsigned long long*>(leaf_touched(g, leaf)) + lane, bits, p.seq, &b.sc->n_touched, b.touched, p.touched_cap);
+    }
+  }
+  __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&b.sc->done3, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  if (threadIdx.x == 0) b.sc->done3 = 0u;
+  shard_flags(g, gs, p, b, flags);
 }
 
 // public addHitPoint / addMissPoint (probabilistic_map.cpp:30-54): update now, queue the ray
@@ -990,17 +1048,20 @@ int Map::init(double resolution) {
   return reserve_scan(0, 16, 1.0);
 }
 
-int Map::reserve_scan(i64 n, i64 stride_bytes, double max_range) {
+int Map::reserve_scan(i64 n, i64 stride_bytes, double max_range, i64 table_n) {
   (void)stride_bytes;
   const size_t np = (size_t)n + n_pending_ + 32;
   BNX_TRY(b_ep_.reserve(np * sizeof(int4)));
   BNX_TRY(b_slot_.reserve(np * 4));
   BNX_TRY(b_rays_.reserve(np * sizeof(int4)));
   // [ScanCounters | table u32[slots] | keys u64[slots]] — contiguous so that one memset clears all of it
-  const u64 slots = table_slots(n);
+  const u64 slots = table_slots(table_n >= 0 ? table_n : n);
   const void* table_before = b_table_.p;
   BNX_TRY(b_table_.reserve(SC_BYTES + slots * 12));
-  if (b_table_.p != table_before) clean_slots_ = 0;  // fresh allocation: nothing is known to be zero
+  if (b_table_.p != table_before) {  // fresh allocation: nothing is known to be zero
+    clean_slots_ = 0;
+    sc_clean_ = t1_clean_ = false;
+  }
   // 32-chunk tiles: estimated from the longest possible ray, grown on overflow
   double cells = std::isfinite(max_range) ? std::ceil(max_range * grid.inv_resolution) + 2.0 : 512.0;
   cells = std::min(cells, 4096.0);
@@ -1110,6 +1171,7 @@ int Map::launch_scan(const void* d_points, i64 stride_bytes, bool f64, ScanParam
   p.seq = ++seq_;
   p.tile_cap = (u32)std::min<size_t>(b_tiles_.bytes / 4, 0xFFFFFFFFull);
   p.touched_cap = (u32)std::min<size_t>(b_touched_.bytes / 4, 0xFFFFFFFFull);
+  sc_clean_ = t1_clean_ = false;
   if (first_attempt) {
     if (profiling) cudaEventRecord(ev_[1], s);
     // counters + dedupe table (+ packed keys) in one clear
@@ -1402,12 +1464,32 @@ int Map::shard_begin(const void* points, i64 stride_bytes, i64 n, bool f64, u32 
   cudaStream_t s = grid.stream();
   scratch_->set_stream(s);
   const i64 slots = (i64)world_ * cap_records;
-  BNX_TRY(reserve_scan(std::max<i64>(n, slots), stride_bytes, max_range));
+  // sender-side dedupe table: sized from the exchange capacity (>= n + 2), so it does not change from scan to scan
+  BNX_TRY(reserve_scan(std::max<i64>(n, slots), stride_bytes, max_range, cap_records));
+  const bool lean = shard_async_;  // pipelined: the kernels leave tables and counters zeroed for the next scan
   const void* d_points = points;
+  int stage_slot = -1;
   if (where == BNX_HOST && n > 0) {
-    BNX_TRY(b_pts_.reserve((size_t)n * stride_bytes));
-    BNX_CUDA(cudaMemcpyAsync(b_pts_.p, points, (size_t)n * stride_bytes, cudaMemcpyHostToDevice, s));
-    d_points = b_pts_.p;
+    if (lean) {
+      // double-buffered staging on a copy stream: the copy of scan k+1 overlaps the kernels of scan k. Sized from
+      // n_max, which is the same on every rank (growing it drains, and draining a sharded map is collective).
+      stage_slot = (int)(shard_async_id_ & 1u);
+      const size_t need = (size_t)std::max<i64>(n, shard_n_max_) * stride_bytes;
+      if (need > b_stage_[stage_slot].bytes) {
+        BNX_TRY(drain());
+        BNX_TRY(b_stage_[stage_slot].reserve(need));
+        stage_used_[stage_slot] = false;
+      }
+      if (stage_used_[stage_slot]) BNX_CUDA(cudaStreamWaitEvent(copy_stream_, ev_consumed_[stage_slot], 0));
+      BNX_CUDA(cudaMemcpyAsync(b_stage_[stage_slot].p, points, (size_t)n * stride_bytes, cudaMemcpyHostToDevice, copy_stream_));
+      BNX_CUDA(cudaEventRecord(ev_copied_[stage_slot], copy_stream_));
+      BNX_CUDA(cudaStreamWaitEvent(s, ev_copied_[stage_slot], 0));
+      d_points = b_stage_[stage_slot].p;
+    } else {
+      BNX_TRY(b_pts_.reserve((size_t)n * stride_bytes));
+      BNX_CUDA(cudaMemcpyAsync(b_pts_.p, points, (size_t)n * stride_bytes, cudaMemcpyHostToDevice, s));
+      d_points = b_pts_.p;
+    }
   }
   ScanParams p = {};
   p.ox = origin[0];
@@ -1438,10 +1520,12 @@ int Map::shard_begin(const void* points, i64 stride_bytes, i64 n, bool f64, u32 
     set_error("sharded insert needs a finite max_range and |voxel coordinates| < 2^20");
     return BNX_ERR_UNSUPPORTED;
   }
-  const u64 tslots = table_slots(std::max<i64>(n, slots));
+  const u64 tslots = table_slots(cap_records);
   p.hash_mask = (u32)(tslots - 1);
   sp_ = p;
   shard_retries_ = 0;
+  shard_attempt_ = 0;
+  if (profiling) cudaEventRecord(ev_[0], s);
   if (!staged_p2p_) {
     BNX_REQUIRE(world_ <= MAX_PEERS, "sharded insert: at most 16 ranks");
     px_host_ = PeerBoxes{};
@@ -1451,7 +1535,9 @@ int Map::shard_begin(const void* points, i64 stride_bytes, i64 n, bool f64, u32 
   } else {
     buf_.my_flags = reinterpret_cast<const u32*>(mbox_);
   }
-  BNX_CUDA(cudaMemsetAsync(d_sc_, 0, SC_BYTES + tslots * 12, s));
+  if (!(lean && sc_clean_ && t1_clean_)) BNX_CUDA(cudaMemsetAsync(d_sc_, 0, SC_BYTES + tslots * 12, s));
+  sc_clean_ = t1_clean_ = lean;  // pipelined: the apply epilogue zeroes the counters, k_shard_dedupe this table
+  clean_slots_ = 0;
   const int blocks = blocks_for(n);
   if (n > 0) {
     const unsigned char* pts = static_cast<const unsigned char*>(d_points);
@@ -1462,10 +1548,15 @@ int Map::shard_begin(const void* points, i64 stride_bytes, i64 n, bool f64, u32 
     } else {
       launch_classify<false, false>(true, blocks, s, pts, (u32)stride_bytes, p, buf_);
     }
+    if (stage_slot >= 0) {
+      BNX_CUDA(cudaEventRecord(ev_consumed_[stage_slot], s));  // classify is the only reader of the points
+      stage_used_[stage_slot] = true;
+    }
   }
   // always launched: its last block writes the block headers (counts) and, with mailboxes, the arrival stamps
   note_launch(), k_shard_bucket<<<blocks, TPB, 0, s>>>(p, buf_, index_base);
   BNX_CUDA(cudaGetLastError());
+  if (profiling) cudaEventRecord(ev_[1], s);
   return BNX_OK;
 }
 
@@ -1496,14 +1587,29 @@ int Map::shard_resolve_mark(const void* recv_records, void* send_leaves, i64 cap
   p.touched_cap = (u32)std::min<size_t>(b_touched_.bytes / 4, 0xFFFFFFFFull);
   p.touched2_cap = (u32)std::min<size_t>(b_touched2_.bytes / 4, 0xFFFFFFFFull);
   p.leaf_cap2 = (u32)cap_leaves;
-  const u64 tslots = (u64)p.hash_mask + 1;
-  BNX_CUDA(cudaMemsetAsync(d_sc_, 0, SC_BYTES + tslots * 12, s));
+  // receiver-side dedupe table [table u32[t2] | keys u64[t2]]: large enough for the worst case (every record of every
+  // rank lands here); the kernels only use — and, pipelined, zero again — the part the arrived records need
+  const u64 t1 = table_slots(p.rec_cap), t2 = table_slots(slots);
+  const void* before = b_table2_.p;
+  BNX_TRY(b_table2_.reserve(t2 * 12));
+  if (b_table2_.p != before) t2_clean_ = false;
+  uint4* table1 = reinterpret_cast<uint4*>(b_table_.as<unsigned char>() + SC_BYTES);
+  buf_.table = b_table2_.as<u32>();
+  buf_.keys = reinterpret_cast<unsigned long long*>(b_table2_.as<unsigned char>() + t2 * 4);
+  p.hash_mask = (u32)(t2 - 1);
+  const bool lean = shard_async_ && shard_attempt_ == 0;
+  if (shard_attempt_ > 0) BNX_CUDA(cudaMemsetAsync(d_sc_, 0, SC_BYTES, s));  // a retry: counters of the failed attempt
+  if (!(lean && t2_clean_)) BNX_CUDA(cudaMemsetAsync(b_table2_.p, 0, t2 * 12, s));
+  t2_clean_ = lean;
+  p.clean16 = lean ? 1u : 0u;
+  ++shard_attempt_;
   const GridDev g = grid.dev(), gs = scratch_->dev();
-  note_launch(), k_shard_dedupe<<<blocks_for(slots), TPB, 0, s>>>(p, buf_, slots);
+  note_launch(), k_shard_dedupe<<<blocks_for(slots), TPB, 0, s>>>(p, buf_, slots, table1, lean ? (u32)(t1 * 12 / 16) : 0u);
   note_launch(), k_resolve<2><<<blocks_for(slots), TPB, 0, s>>>(g, p, buf_, slots);
   note_launch(), k_mark<true><<<persistent, TPB, 0, s>>>(g, gs, p, buf_);
   note_launch(), k_shard_emit<<<persistent, TPB, 0, s>>>(gs, p, buf_);
   BNX_CUDA(cudaGetLastError());
+  if (profiling) cudaEventRecord(ev_[2], s);
   return BNX_OK;
 }
 
@@ -1516,9 +1622,9 @@ int Map::shard_merge(const void* recv_leaves, void* flags) {
   }
   cudaStream_t s = grid.stream();
   const GridDev g = grid.dev(), gs = scratch_->dev();
-  note_launch(), k_shard_merge<<<sm_count() * 8, TPB, 0, s>>>(g, sp_, buf_, static_cast<const int4*>(recv_leaves), sp_.leaf_cap2);
-  note_launch(), k_shard_flags<<<1, 32, 0, s>>>(g, gs, sp_, buf_, static_cast<u32*>(flags));
+  note_launch(), k_shard_merge<<<sm_count() * 8, TPB, 0, s>>>(g, gs, sp_, buf_, static_cast<const int4*>(recv_leaves), sp_.leaf_cap2, static_cast<u32*>(flags));
   BNX_CUDA(cudaGetLastError());
+  if (profiling) cudaEventRecord(ev_[3], s);
   return BNX_OK;
 }
 
@@ -1535,9 +1641,11 @@ int Map::shard_finish(const void* flags_reduced, int* retry) {
   buf_.gate = static_cast<const u32*>(flags_reduced);
   note_launch(), k_apply_leaves<<<persistent, TPB, 0, s>>>(g, sp_, buf_);
   BNX_CUDA(cudaGetLastError());
+  if (profiling) cudaEventRecord(ev_[4], s);
   BNX_CUDA(cudaMemcpyAsync(h_status_, d_sc_, sizeof(ScanCounters), cudaMemcpyDeviceToHost, s));
   BNX_CUDA(cudaStreamSynchronize(s));
   buf_.gate = nullptr;
+  shard_phase_times();
   const ScanCounters st = *h_status_;
   const u32 any_pool = st.gate_pool, any_ovf = st.gate_ovf;
   *retry = 0;
@@ -1586,6 +1694,23 @@ int Map::shard_finish(const void* flags_reduced, int* retry) {
   BNX_TRY(scratch_->read_counters(&sgc));
   BNX_TRY(scratch_->maintain(sgc));
   return grid.maintain(st.gc);
+}
+
+// device time of the stages of the last sharded scan: {0, begin, resolve_mark (waits for exchange 1), merge (waits for
+// exchange 2), apply (waits for the flags), total}; valid once the stream has been synchronised
+void Map::shard_phase_times() {
+  if (!profiling) return;
+  float ms = 0.f;
+  phase_us[0] = 0.0;
+  for (int k = 0; k < 4; ++k) {
+    if (cudaEventElapsedTime(&ms, ev_[k], ev_[k + 1]) != cudaSuccess) {
+      cudaGetLastError();
+      return;
+    }
+    phase_us[k + 1] = ms * 1e3;
+  }
+  cudaEventElapsedTime(&ms, ev_[0], ev_[4]);
+  phase_us[5] = ms * 1e3;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1755,6 +1880,9 @@ int Map::shard_insert(const void* points, i64 stride_bytes, i64 n, bool f64, u32
   const bool p2p = want_p2p_;
   u32* flags = x_flags_.as<u32>();
   const u32 my_async = async ? async_next_++ : NONE;
+  shard_async_ = async;
+  shard_async_id_ = my_async;
+  shard_n_max_ = n_max;
   BNX_TRY(shard_begin(points, stride_bytes, n, f64, index_base, origin, max_range, p2p ? nullptr : x_send1_.p, cap_rec_, where));
   sp_.async_id = my_async;
   if (!p2p) BNX_TRY(all_to_all(x_send1_.p, x_recv1_.p, (size_t)cap_rec_ * 16));
@@ -1767,7 +1895,9 @@ int Map::shard_insert(const void* points, i64 stride_bytes, i64 n, bool f64, u32
       buf_.gate = p2p ? reinterpret_cast<const u32*>(mbox_) + MBOX_FLAGS4 : flags;
       note_launch(), k_apply_leaves<<<sm_count() * 8, TPB, 0, s>>>(grid.dev(), sp_, buf_);
       BNX_CUDA(cudaGetLastError());
+      if (profiling) cudaEventRecord(ev_[4], s);
       buf_.gate = nullptr;
+      shard_async_ = false;
       ShardQueued q;
       q.points = points;
       q.stride = stride_bytes;
@@ -1785,6 +1915,7 @@ int Map::shard_insert(const void* points, i64 stride_bytes, i64 n, bool f64, u32
       return BNX_OK;
     }
     int retry = 0;
+    shard_async_ = false;
     BNX_TRY(shard_finish(p2p ? nullptr : flags, &retry));
     if (!retry) return BNX_OK;
     if (retry & (int)(OVF_RECORDS << 8)) {
@@ -1808,6 +1939,8 @@ int Map::shard_drain() {
   BNX_CUDA(cudaMemcpyAsync(h_status_, d_sc_, sizeof(ScanCounters), cudaMemcpyDeviceToHost, s));
   GridCounters gc;
   BNX_TRY(grid.read_counters(&gc));  // synchronises the stream
+  shard_phase_times();
+  if (gc.error) sc_clean_ = t1_clean_ = t2_clean_ = false;  // frozen kernels cleaned nothing
   std::vector<ShardQueued> q;
   q.swap(squeue_);
   size_t done = q.size();

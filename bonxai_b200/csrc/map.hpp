@@ -60,7 +60,8 @@ struct ScanCounters {
   u32 cnt2[MAX_PEERS];           // sharded: leaf records emitted for owner o
   u32 done1, done2;              // last-block tickets of the two producing kernels
   u32 gate_pool, gate_ovf;       // sharded: the reduced error flags the apply pass acted on
-  u32 pad_[2];
+  u32 done3;                     // last-block ticket of the merge kernel
+  u32 pad_;
 };
 static_assert(sizeof(ScanCounters) % 16 == 0, "cleared in 16-byte units");
 
@@ -146,7 +147,7 @@ class Map {
   double phase_us[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
  private:
-  int reserve_scan(i64 n, i64 stride_bytes, double max_range);
+  int reserve_scan(i64 n, i64 stride_bytes, double max_range, i64 table_n = -1);
   int run_scan(const void* d_points, i64 stride_bytes, bool f64, const ScanParams& base, bool reuse_classify);
 
   ScanBuffers buf_ = {};
@@ -164,6 +165,12 @@ class Map {
   DevBuf x_send1_, x_recv1_, x_send2_, x_recv2_, x_flags_;
   i64 cap_rec_ = 0, cap_leaf_ = 1 << 13;
   bool staged_p2p_ = false;  // the scan in flight uses the mailboxes
+  bool shard_async_ = false;  // the scan being enqueued is pipelined (set by shard_insert around the stages)
+  u32 shard_async_id_ = 0, shard_attempt_ = 0;
+  i64 shard_n_max_ = 0;
+  bool sc_clean_ = false, t1_clean_ = false, t2_clean_ = false;  // pipelined: counters / tables known to be zero
+  DevBuf b_table2_;  // receiver-side dedupe table of the sharded map
+  void shard_phase_times();
   struct ShardQueued {
     const void* points;
     i64 stride, n, n_max;
