@@ -42,6 +42,17 @@ constexpr u32 OVF_TILES = 1u, OVF_CHUNKS = 2u, OVF_RECORDS = 4u, OVF_LEAVES = 8u
 
 inline int blocks_for(i64 n, int tpb = TPB) { return (int)std::max<i64>(1, ceil_div(n, tpb)); }
 
+// Two mark kernels. "direct" (default) flushes every (leaf, word) segment of a ray chunk to the grid; "staged"
+// (BNX_MARK=staged) first ORs the segments of neighbouring rays into leaf masks in shared memory. Measured on the LiDAR
+// bench the staged kernel is not faster yet (profiles/r1_notes.md), so it stays opt-in.
+inline bool direct_mark() {
+  static const bool v = [] {
+    const char* e = std::getenv("BNX_MARK");
+    return !(e && std::strcmp(e, "staged") == 0);
+  }();
+  return v;
+}
+
 // ------------------------------------------------------------------------------------------------
 // peer-memory exchange primitives (sharded map)
 // ------------------------------------------------------------------------------------------------
@@ -636,6 +647,294 @@ __global__ void __launch_bounds__(TPB, MARK_MIN_BLOCKS) k_mark(GridDev g, GridDe
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// phase 3, staged flavour (opt-in, BNX_MARK=staged; needs all voxel coordinates of the scan to fit 21 bits per axis)
+// ------------------------------------------------------------------------------------------------
+// Neighbouring rays of a scan (adjacent beams / azimuths) run through the same leaves, so every block takes a
+// CONTIGUOUS range of tiles and ORs the segments of its rays into leaf masks held in SHARED memory: a 256-slot
+// open-addressing table keyed by the packed leaf coordinates (64-bit atomicCAS claims a slot), 512 mask bits per
+// slot. Only when the table fills up, and at the end, every staged leaf is looked up (or created) ONCE in the
+// grid and its non-zero 64-bit words go to the leaf's touched mask with the usual test + atomicOr.
+//   walk    one lane = one 8-cell chunk, straight-line code (all lanes run CHUNK + 1 rounds and reconverge). A lane
+//           whose (leaf, word) segment ends appends it to its warp's segment QUEUE (ballot + popc: dense).
+//   drain   whenever the queue holds 32 segments the warp stages them, one per lane: every staging round is full,
+//           instead of one sparse round per cell.
+#ifndef MARK_STAGED_MIN_BLOCKS
+#define MARK_STAGED_MIN_BLOCKS 6
+#endif
+constexpr u32 MARK_SLOTS = 256;
+constexpr u32 MARK_FLUSH_AT = 128;  // staged leaves that trigger a flush at the next group boundary
+constexpr u32 MARK_GROUP = 4;       // tiles per warp between two block-wide flush checks
+constexpr u32 MARK_QUEUE = 64;      // ring entries per warp (32 left over + 32 new at most)
+struct MarkStage {
+  unsigned long long key[MARK_SLOTS];      // 0 = empty, else packed leaf coordinates (bit 63 set)
+  unsigned long long mask[MARK_SLOTS][8];  // touched bits of the staged leaf, same layout as the leaf's own mask
+  u32 leaf[MARK_SLOTS];                    // flush: grid index of the leaf (bit 31: it lives in the scratch grid)
+  u32 used;
+  int4 q_where[TPB / 32][MARK_QUEUE];                // segment queue: leaf coordinates + mask word
+  unsigned long long q_bits[TPB / 32][MARK_QUEUE];   //                its bits
+};
+
+// leaf coordinates are voxel coordinates >> 3: |l| < 2^17 for packed scans
+__device__ __forceinline__ unsigned long long pack_leaf(int lx, int ly, int lz) {
+  return (unsigned long long)(u32)(lx + (1 << 19)) | ((unsigned long long)(u32)(ly + (1 << 19)) << 20) |
+         ((unsigned long long)(u32)(lz + (1 << 19)) << 40) | (1ull << 63);
+}
+
+__device__ __forceinline__ bool stage_segment(MarkStage& S, int lx, int ly, int lz, u32 w, unsigned long long bits) {
+  const unsigned long long key = pack_leaf(lx, ly, lz);
+  u32 h = (((u32)lx * 0x9E3779B1u) ^ ((u32)ly * 0x85EBCA77u) ^ ((u32)lz * 0xC2B2AE3Du)) >> 24;
+#pragma unroll 1
+  for (int probe = 0; probe < 8; ++probe) {
+    unsigned long long k = S.key[h];
+    if (k == 0ull) {
+      k = atomicCAS(&S.key[h], 0ull, key);
+      if (k == 0ull) {
+        atomicAdd(&S.used, 1u);
+        k = key;
+      }
+    }
+    if (k == key) {
+      u32* m = reinterpret_cast<u32*>(&S.mask[h][w]);
+      const u32 lo = (u32)bits, hi = (u32)(bits >> 32);
+      if (lo & ~m[0]) atomicOr(&m[0], lo);
+      if (hi & ~m[1]) atomicOr(&m[1], hi);
+      return true;
+    }
+    h = (h + 1) & (MARK_SLOTS - 1);
+  }
+  return false;
+}
+
+// one segment straight to the grid (the staging table had no room within its probe limit)
+template <bool SHARD>
+__device__ __forceinline__ void mark_direct(const GridDev& g, const GridDev& gs, const ScanParams& p, const ScanBuffers& b, int lx, int ly, int lz, u32 w,
+                                            unsigned long long bits) {
+  u32 inner = NONE;
+  if (!SHARD || shard_owner(lx >> 2, ly >> 2, lz >> 2, p.world) == p.rank) {
+    const u32 leaf = mark_leaf(g, inner, true, lx, ly, lz);
+    if (leaf != NONE) mark_bits(g, leaf, reinterpret_cast<unsigned long long*>(leaf_touched(g, leaf)) + w, bits, p.seq, &b.sc->n_touched, b.touched, p.touched_cap);
+  } else {
+    const u32 leaf = mark_leaf(gs, inner, true, lx, ly, lz);
+    if (leaf != NONE) mark_bits(gs, leaf, reinterpret_cast<unsigned long long*>(leaf_touched(gs, leaf)) + w, bits, p.seq, &b.sc->n_touched2, b.touched2, p.touched2_cap);
+  }
+}
+
+// the first `count` (<= 32) queued segments of this warp, one per lane
+template <bool SHARD>
+__device__ __forceinline__ void drain_queue(MarkStage& S, const GridDev& g, const GridDev& gs, const ScanParams& p, const ScanBuffers& b, u32 warp, u32 lane,
+                                            u32 head, u32 count) {
+  __syncwarp();
+  if (lane < count) {
+    const u32 at = (head + lane) & (MARK_QUEUE - 1);
+    const int4 wh = S.q_where[warp][at];
+    const unsigned long long bits = S.q_bits[warp][at];
+    if (!stage_segment(S, wh.x, wh.y, wh.z, (u32)wh.w, bits)) mark_direct<SHARD>(g, gs, p, b, wh.x, wh.y, wh.z, (u32)wh.w, bits);
+  }
+  __syncwarp();
+}
+
+// floor(n / d) for n < 2^23 with the reciprocal of d at hand (rcp = 1.0f / d): one multiply + one fix-up step
+__device__ __forceinline__ u32 div_small(u32 n, u32 d, float rcp) {
+  u32 q = (u32)__float2int_rz(__fmul_rz((float)n, rcp));
+  const int r = (int)(n - q * d);
+  if (r < 0) {
+    --q;
+  } else if (r >= (int)d) {
+    ++q;
+  }
+  return q;
+}
+
+// the same exact DDA as walk_chunk for the cells [k0, k1) of one ray (k0 == k1: an idle lane that only takes part in
+// the warp-wide queue bookkeeping). qh / qn: head and fill of the warp's segment ring, kept identical in all lanes.
+template <bool SHARD>
+__device__ __forceinline__ void walk_stage(MarkStage& S, const GridDev& g, const GridDev& gs, const ScanParams& p, const ScanBuffers& b, const RayGeom& r,
+                                           u32 k0, u32 k1, u32 warp, u32 lane, u32& qh, u32& qn) {
+  u32 px, py, pz;
+  if (r.m < 2048u) {  // 2 * k0 * a + m < 2^23: exact in float
+    const float rcp = __frcp_rn((float)(2u * r.m));
+    px = div_small(2u * k0 * r.ax + r.m, 2u * r.m, rcp);
+    py = div_small(2u * k0 * r.ay + r.m, 2u * r.m, rcp);
+    pz = div_small(2u * k0 * r.az + r.m, 2u * r.m, rcp);
+  } else {
+    px = (u32)((2ull * k0 * r.ax + r.m) / (2ull * r.m));
+    py = (u32)((2ull * k0 * r.ay + r.m) / (2ull * r.m));
+    pz = (u32)((2ull * k0 * r.az + r.m) / (2ull * r.m));
+  }
+  // packed coordinates: m < 2^21 and k0 < m, the residuals fit 32 bits... only through 64-bit products
+  int ex = (int)((i64)k0 * r.ax - (i64)px * r.m), ey = (int)((i64)k0 * r.ay - (i64)py * r.m), ez = (int)((i64)k0 * r.az - (i64)pz * r.m);
+  int x = p.Ox + r.sx * (int)px, y = p.Oy + r.sy * (int)py, z = p.Oz + r.sz * (int)pz;
+  const int em = (int)r.m, half = (int)((r.m + 1u) >> 1);  // (e << 1) >= m  <=>  e >= ceil(m / 2)
+  const int dax = (int)r.ax, day = (int)r.ay, daz = (int)r.az;
+  const u32 cnt = k1 - k0;
+  const u32 lt = (1u << lane) - 1u;
+  u32 key = 0xFFFFFFFFu;
+  unsigned long long bits = 0;
+  int lx = 0, ly = 0, lz = 0;
+  // Straight-line control flow (fully unrolled, no early exit): all lanes run CHUNK + 1 rounds, the extra round ends
+  // the last segment.
+#pragma unroll
+  for (u32 c = 0; c <= CHUNK; ++c) {
+    // segment key: mask word (z & 7) + the leaf-parity bit of every axis. Inside a chunk a coordinate crosses at
+    // most one leaf boundary, so equal keys <=> same leaf and same word.
+    const bool live = c < cnt;
+    const u32 kc = live ? (((u32)z & 7u) | ((u32)x & 8u) | (((u32)y & 8u) << 1) | (((u32)z & 8u) << 2)) : 0xFFFFFFFEu;
+    const bool change = kc != key;
+    const bool emit = change && bits != 0ull;
+    const u32 em_mask = __ballot_sync(0xffffffffu, emit);
+    if (em_mask) {
+      if (emit) {
+        const u32 at = (qh + qn + __popc(em_mask & lt)) & (MARK_QUEUE - 1);
+        S.q_where[warp][at] = make_int4(lx, ly, lz, (int)(key & 7u));
+        S.q_bits[warp][at] = bits;
+      }
+      qn += __popc(em_mask);
+      if (qn >= 32u) {
+        drain_queue<SHARD>(S, g, gs, p, b, warp, lane, qh, 32u);
+        qh = (qh + 32u) & (MARK_QUEUE - 1);
+        qn -= 32u;
+      }
+    }
+    if (change) {
+      key = kc;
+      bits = 0;
+      lx = x >> 3;
+      ly = y >> 3;
+      lz = z >> 3;
+    }
+    if (live) {
+      bits |= 1ull << (((u32)x & 7u) | (((u32)y & 7u) << 3));
+      ex += dax;
+      ey += day;
+      ez += daz;
+      if (ex >= half) {
+        x += r.sx;
+        ex -= em;
+      }
+      if (ey >= half) {
+        y += r.sy;
+        ey -= em;
+      }
+      if (ez >= half) {
+        z += r.sz;
+        ez -= em;
+      }
+    }
+  }
+}
+
+// staged leaves -> grid: one thread per slot finds / creates its leaf, then one thread per (slot, word) merges the bits
+template <bool SHARD>
+__device__ __forceinline__ void flush_stage(MarkStage& S, const GridDev& g, const GridDev& gs, const ScanParams& p, const ScanBuffers& b) {
+  for (u32 slot = threadIdx.x; slot < MARK_SLOTS; slot += TPB) {
+    const unsigned long long key = S.key[slot];
+    u32 leaf = NONE;
+    if (key) {
+      const int lx = (int)(u32)(key & 0xFFFFFu) - (1 << 19), ly = (int)(u32)((key >> 20) & 0xFFFFFu) - (1 << 19), lz = (int)(u32)((key >> 40) & 0xFFFFFu) - (1 << 19);
+      u32 inner = NONE;
+      if (!SHARD || shard_owner(lx >> 2, ly >> 2, lz >> 2, p.world) == p.rank) {
+        leaf = mark_leaf(g, inner, true, lx, ly, lz);
+      } else {
+        leaf = mark_leaf(gs, inner, true, lx, ly, lz);
+        if (leaf != NONE) leaf |= 0x80000000u;
+      }
+    }
+    S.leaf[slot] = leaf;
+  }
+  __syncthreads();
+  for (u32 idx = threadIdx.x; idx < MARK_SLOTS * 8u; idx += TPB) {
+    const u32 slot = idx >> 3, w = idx & 7u;
+    const unsigned long long bits = S.mask[slot][w];
+    if (bits) {
+      S.mask[slot][w] = 0ull;
+      const u32 leaf = S.leaf[slot];
+      if (leaf != NONE) {
+        if (!SHARD || !(leaf & 0x80000000u)) {
+          mark_bits(g, leaf, reinterpret_cast<unsigned long long*>(leaf_touched(g, leaf)) + w, bits, p.seq, &b.sc->n_touched, b.touched, p.touched_cap);
+        } else {
+          const u32 l2 = leaf & 0x7FFFFFFFu;
+          mark_bits(gs, l2, reinterpret_cast<unsigned long long*>(leaf_touched(gs, l2)) + w, bits, p.seq, &b.sc->n_touched2, b.touched2, p.touched2_cap);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (u32 slot = threadIdx.x; slot < MARK_SLOTS; slot += TPB) S.key[slot] = 0ull;
+  if (threadIdx.x == 0) S.used = 0u;
+  __syncthreads();
+}
+
+template <bool SHARD>
+__global__ void __launch_bounds__(TPB, MARK_STAGED_MIN_BLOCKS) k_mark_staged(GridDev g, GridDev gs, ScanParams p, ScanBuffers b) {
+  __shared__ MarkStage S;
+  const unsigned long long rc = b.sc->ray_chunk;
+  const u32 n_rays = (u32)(rc >> 40);
+  const u32 total = (u32)(rc & CHUNK_FIELD);
+  if (b.sc->overflow | *b.poison) return;
+  if (p.clean16) {  // see k_mark
+    if (SHARD) {
+      int4 e_;
+      bool f_;
+      const u32 n16 = (shard_table_mask(p, shard_locate(p, b, NONE, f_, e_)) + 1u) / 4u;
+      uint4* tab = reinterpret_cast<uint4*>(b.table);
+      uint4* keys = reinterpret_cast<uint4*>(b.keys);
+      for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < 3u * n16; i += gridDim.x * blockDim.x) {
+        if (i < n16) {
+          tab[i] = make_uint4(0, 0, 0, 0);
+        } else {
+          keys[i - n16] = make_uint4(0, 0, 0, 0);
+        }
+      }
+    } else {
+      uint4* tab = reinterpret_cast<uint4*>(b.table);
+      for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < p.clean16; i += gridDim.x * blockDim.x) tab[i] = make_uint4(0, 0, 0, 0);
+    }
+  }
+  {
+    unsigned long long* z = reinterpret_cast<unsigned long long*>(&S);
+    for (u32 i = threadIdx.x; i < MARK_SLOTS * 9u; i += TPB) z[i] = 0ull;  // keys + masks
+    if (threadIdx.x == 0) S.used = 0u;
+  }
+  __syncthreads();
+  const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const u32 n_tiles = (total + 31u) >> 5;
+  const u32 t0 = (u32)((u64)blockIdx.x * n_tiles / gridDim.x), t1 = (u32)((u64)(blockIdx.x + 1u) * n_tiles / gridDim.x);
+  constexpr u32 PER_GROUP = (TPB / 32) * MARK_GROUP;
+  u32 qh = 0, qn = 0;
+  for (u32 base = t0; base < t1; base += PER_GROUP) {
+    // warp w walks MARK_GROUP adjacent tiles of this group
+    for (u32 j = 0; j < MARK_GROUP; ++j) {
+      const u32 tile = base + warp * MARK_GROUP + j;
+      if (tile >= t1) break;
+      const u32 c0 = tile * 32;
+      const u32 r_first = b.tile_first[tile];
+      // which of the next 32 rays start inside this tile? bit j = a ray starts at chunk c0 + j
+      const u32 rb = r_first + 1 + lane;
+      u32 bit = 0;
+      if (rb < n_rays) {
+        const u32 cb = (u32)b.rays[rb].w;
+        if (cb - c0 < 32u) bit = 1u << (cb - c0);
+      }
+      const u32 starts = __reduce_or_sync(0xffffffffu, bit);
+      const u32 chunk = c0 + lane;
+      const u32 r = min(r_first + __popc(starts & ((2u << lane) - 1u)), n_rays - 1u);
+      const int4 ray = b.rays[r];
+      const RayGeom rg = ray_geom(p, ray.x, ray.y, ray.z);
+      u32 k0 = 0, k1 = 0;
+      if (chunk < total) chunk_range(rg, chunk - (u32)ray.w, k0, k1);
+      walk_stage<SHARD>(S, g, gs, p, b, rg, k0, k1, warp, lane, qh, qn);
+    }
+    if (qn) {
+      drain_queue<SHARD>(S, g, gs, p, b, warp, lane, qh, qn);
+      qh = 0;
+      qn = 0;
+    }
+    __syncthreads();
+    if (S.used >= MARK_FLUSH_AT || base + PER_GROUP >= t1) flush_stage<SHARD>(S, g, gs, p, b);
+  }
+}
+
 // retry path only: a failed attempt leaves touched bits behind; the list of that attempt says where
 __global__ void __launch_bounds__(TPB) k_clear_touched(GridDev g, ScanBuffers b, u32 n) {
   const u32 lane = threadIdx.x & 31;
@@ -1204,7 +1503,11 @@ int Map::launch_scan(const void* d_points, i64 stride_bytes, bool f64, ScanParam
   if (n_pending_) note_launch(), k_resolve<1><<<blocks_for(n_pending_), TPB, 0, s>>>(g, p, buf_, n_pending_);
   if (n > 0) note_launch(), k_resolve<0><<<blocks_for(n), TPB, 0, s>>>(g, p, buf_, (u32)n);
   if (profiling && first_attempt) cudaEventRecord(ev_[3], s);
-  note_launch(), k_mark<false><<<persistent, TPB, 0, s>>>(g, g, p, buf_);
+  if (p.packed && !direct_mark()) {
+    note_launch(), k_mark_staged<false><<<sm_count() * MARK_STAGED_MIN_BLOCKS, TPB, 0, s>>>(g, g, p, buf_);
+  } else {
+    note_launch(), k_mark<false><<<persistent, TPB, 0, s>>>(g, g, p, buf_);
+  }
   if (profiling && first_attempt) cudaEventRecord(ev_[4], s);
   note_launch(), k_apply_leaves<<<persistent, TPB, 0, s>>>(g, p, buf_);
   BNX_CUDA(cudaGetLastError());
@@ -1606,7 +1909,11 @@ int Map::shard_resolve_mark(const void* recv_records, void* send_leaves, i64 cap
   const GridDev g = grid.dev(), gs = scratch_->dev();
   note_launch(), k_shard_dedupe<<<blocks_for(slots), TPB, 0, s>>>(p, buf_, slots, table1, lean ? (u32)(t1 * 12 / 16) : 0u);
   note_launch(), k_resolve<2><<<blocks_for(slots), TPB, 0, s>>>(g, p, buf_, slots);
-  note_launch(), k_mark<true><<<persistent, TPB, 0, s>>>(g, gs, p, buf_);
+  if (!direct_mark()) {  // sharded scans always have packed coordinates
+    note_launch(), k_mark_staged<true><<<sm_count() * MARK_STAGED_MIN_BLOCKS, TPB, 0, s>>>(g, gs, p, buf_);
+  } else {
+    note_launch(), k_mark<true><<<persistent, TPB, 0, s>>>(g, gs, p, buf_);
+  }
   note_launch(), k_shard_emit<<<persistent, TPB, 0, s>>>(gs, p, buf_);
   BNX_CUDA(cudaGetLastError());
   if (profiling) cudaEventRecord(ev_[2], s);
