@@ -429,8 +429,10 @@ def run_gpu_sharded(args):
     launches0 = capi.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
+    th0 = time.perf_counter()
     for i in range(W, total):
         sm.insert(capi.DevPtr(dev[i].data_ptr()), n_local, 16, lo, n_max, slices[i][1], MAX_RANGE, use_async=True)
+    enqueue_dev_us = 1e6 * (time.perf_counter() - th0) / K
     e1.record(stream)
     sm.sync()
     barrier()
@@ -469,6 +471,7 @@ def run_gpu_sharded(args):
     t0 = time.perf_counter()
     for i in range(W, total):
         sm2.insert(pinned[i], n_local, 16, lo, n_max, slices[i][1], MAX_RANGE, use_async=True)
+    enqueue_host_us = 1e6 * (time.perf_counter() - t0) / K
     sm2.sync()
     t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -505,7 +508,9 @@ def run_gpu_sharded(args):
                          "algorithmic_bytes_per_launch": alg_bytes},
             "e2e": {"value": K * n_scan / e2e_s, "unit": "points/s", "h2d_bytes_per_step": n_local * 16, "d2h_bytes_per_step": 128 + 16,
                     "ms_per_step": 1e3 * e2e_s / K},
-            "gpu_launches": int(launches_all), "clocks": clocks,
+            "gpu_launches": int(launches_all),
+            "host_enqueue_us_per_scan": {"device_buffers": enqueue_dev_us, "host_buffers": enqueue_host_us, "note": "rank 0, host time inside the insert calls"},
+            "clocks": clocks,
         }
         print(json.dumps(line))
     dist.destroy_process_group()

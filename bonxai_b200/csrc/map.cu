@@ -100,16 +100,19 @@ __device__ __forceinline__ void publish_blocks(const PeerBoxes* px, bool leaves,
                                                u32 cap) {
   __shared__ bool s_last;
   const bool remote = px->flag[0] != nullptr;
-  if (remote) {
-    __threadfence_system();
-  } else {
-    __threadfence();
+  __syncthreads();  // the block's stores happen before thread 0's fence (cumulative), which happens before its ticket
+  if (threadIdx.x == 0) {
+    if (remote) {
+      __threadfence_system();
+    } else {
+      __threadfence();
+    }
+    s_last = atomicAdd(done, 1u) == gridDim.x - 1;
   }
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicAdd(done, 1u) == gridDim.x - 1;
   __syncthreads();
   if (!s_last) return;
   if (threadIdx.x == 0) *done = 0u;  // ready for the next scan (the pipelined path does not memset the counters)
+  __threadfence();
   if (threadIdx.x < world) {
     const u32 o = threadIdx.x;
     const u32 c = min(*reinterpret_cast<const volatile u32*>(cnt + o), cap - 1u);
@@ -323,16 +326,19 @@ __global__ void __launch_bounds__(TPB) k_resolve(GridDev g, ScanParams p, ScanBu
   __shared__ u32 s_warp_e[TPB / 32];
   __shared__ unsigned long long s_base, s_m;
   __shared__ u32 s_base_e;
-  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (MODE != 1 && *b.poison) return;  // an earlier pipelined scan ran short: freeze until the host recovers
+  // MODE 2 is launched for the expected number of received records and loops (block-uniformly) over the rest
+  for (u32 vb = blockIdx.x;; vb += gridDim.x) {
+  const u32 i = vb * blockDim.x + threadIdx.x;
+  u32 received = 0;
   if (threadIdx.x == 0) s_m = 0;
 
   bool is_end = false, winner = false;
   int4 e = make_int4(0, 0, 0, 0);
   u32 leaf = NONE, ci = 0, m = 0, chunks = 0;
   if (MODE == 2) {
-    shard_locate(p, b, i, winner, e);
+    received = shard_locate(p, b, i, winner, e);
     if (winner) {
       winner = b.table[b.slot_of[i]] == ~(u32)e.w;
       e.w &= 1;
@@ -436,6 +442,9 @@ __global__ void __launch_bounds__(TPB) k_resolve(GridDev g, ScanParams p, ScanBu
         }
       }
     }
+  }
+  if (MODE != 2 || (u64)(vb + gridDim.x) * blockDim.x >= received) break;
+  __syncthreads();
   }
 }
 
@@ -1139,50 +1148,64 @@ __global__ void __launch_bounds__(TPB) k_shard_dedupe(ScanParams p, ScanBuffers 
   // frozen, so that no rank ever runs ahead of an exchange point)
   wait_arrivals(b.my_flags ? b.my_flags + MBOX_FLAG1 : nullptr, 1, p.world, p.xseq1, const_cast<u32*>(b.poison));
   if (*b.poison) return;
-  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  for (u32 k = i; k < clean16; k += gridDim.x * blockDim.x) clean[k] = make_uint4(0, 0, 0, 0);
-  int4 e;
-  bool found;
-  const u32 mask = shard_table_mask(p, shard_locate(p, b, i, found, e));
-  if (!found) return;
-  const unsigned long long key = pack_key(e);
-  u32 slot = (u32)hash3(e.x, e.y, e.z) & mask;
+  const u32 stride = gridDim.x * blockDim.x;
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  for (u32 k = i; k < clean16; k += stride) clean[k] = make_uint4(0, 0, 0, 0);
+  // launched for the expected number of records; whole warps loop over the rest (count = the worst case)
   for (;;) {
-    unsigned long long k = b.keys[slot];
-    if (k == 0ull) k = atomicCAS(&b.keys[slot], 0ull, key);
-    if (k == 0ull || k == key) break;
-    slot = (slot + 1) & mask;
+    int4 e;
+    bool found;
+    const u32 received = shard_locate(p, b, i, found, e);
+    if (found) {
+      const u32 mask = shard_table_mask(p, received);
+      const unsigned long long key = pack_key(e);
+      u32 slot = (u32)hash3(e.x, e.y, e.z) & mask;
+      for (;;) {
+        unsigned long long k = b.keys[slot];
+        if (k == 0ull) k = atomicCAS(&b.keys[slot], 0ull, key);
+        if (k == 0ull || k == key) break;
+        slot = (slot + 1) & mask;
+      }
+      atomicMax(&b.table[slot], ~(u32)e.w);
+      b.slot_of[i] = slot;
+    }
+    i += stride;
+    if ((i & ~31u) >= min(received, count)) break;
   }
-  atomicMax(&b.table[slot], ~(u32)e.w);
-  b.slot_of[i] = slot;
 }
 
-// exchange 2, sender: one warp per scratch leaf touched in this scan -> {leaf origin, 512-bit mask} into block [rank] of
-// the inbox of the rank that owns its root; the scratch mask is cleared for the next scan. Record = 5 x int4 (80 B).
+// exchange 2, sender: eight lanes per scratch leaf touched in this scan -> {leaf origin, 512-bit mask} into block [rank]
+// of the inbox of the rank that owns its root; the scratch mask is cleared for the next scan. Record = 5 x int4 (80 B).
 __global__ void __launch_bounds__(TPB) k_shard_emit(GridDev gs, ScanParams p, ScanBuffers b) {
   const u32 n = min(b.sc->n_touched2, p.touched2_cap);
   const u32 cap = p.leaf_cap2;
-  const u32 lane = threadIdx.x & 31;
-  const u32 warps = gridDim.x * (TPB / 32);
-  for (u32 t = blockIdx.x * (TPB / 32) + (threadIdx.x >> 5); t < n; t += warps) {
-    const u32 leaf = b.touched2[t];
-    const int4 hdr = *reinterpret_cast<const int4*>(leaf_ptr(gs, leaf));
-    unsigned long long* touched = reinterpret_cast<unsigned long long*>(leaf_touched(gs, leaf));
-    const u32 o = shard_owner(hdr.x >> 5, hdr.y >> 5, hdr.z >> 5, p.world);
-    int4* block = b.px->leaf[o];
+  const u32 lane = threadIdx.x & 31, sub = lane & 7u, first = lane & 24u;
+  const u32 groups = gridDim.x * (TPB / 8);
+  for (u32 t0 = (blockIdx.x * (TPB / 32) + (threadIdx.x >> 5)) * 4u; t0 < n; t0 += groups) {  // warp-uniform trip count
+    const u32 t = t0 + (lane >> 3);
+    const bool valid = t < n;
     u32 at = 0;
-    if (lane == 0) at = atomicAdd(&b.sc->cnt2[o], 1u) + 1u;
-    at = __shfl_sync(0xffffffffu, at, 0);
+    int4 hdr = make_int4(0, 0, 0, 0);
     unsigned long long m = 0;
-    if (lane < 8) {
-      m = touched[lane];
-      touched[lane] = 0ull;
+    int4* block = nullptr;
+    if (valid) {
+      const u32 leaf = b.touched2[t];
+      hdr = *reinterpret_cast<const int4*>(leaf_ptr(gs, leaf));
+      unsigned long long* touched = reinterpret_cast<unsigned long long*>(leaf_touched(gs, leaf));
+      const u32 o = shard_owner(hdr.x >> 5, hdr.y >> 5, hdr.z >> 5, p.world);
+      block = b.px->leaf[o];
+      if (sub == 0) at = atomicAdd(&b.sc->cnt2[o], 1u) + 1u;
+      m = touched[sub];
+      touched[sub] = 0ull;
     }
-    if (at < cap) {
-      if (lane == 0) block[(size_t)at * 5] = make_int4(hdr.x, hdr.y, hdr.z, 0);
-      if (lane < 8) reinterpret_cast<unsigned long long*>(block + (size_t)at * 5 + 1)[lane] = m;
-    } else if (lane == 0) {
-      atomicOr(&b.sc->overflow, OVF_LEAVES);
+    at = __shfl_sync(0xffffffffu, at, first);
+    if (valid) {
+      if (at < cap) {
+        if (sub == 0) block[(size_t)at * 5] = make_int4(hdr.x, hdr.y, hdr.z, 0);
+        reinterpret_cast<unsigned long long*>(block + (size_t)at * 5 + 1)[sub] = m;
+      } else if (sub == 0) {
+        atomicOr(&b.sc->overflow, OVF_LEAVES);
+      }
     }
   }
   publish_blocks(b.px, true, b.sc->cnt2, &b.sc->done2, MBOX_FLAG2, p.rank, p.xseq2, p.world, cap);
@@ -1211,35 +1234,50 @@ __device__ __forceinline__ void shard_flags(const GridDev& g, const GridDev& gs,
   }
 }
 
-// exchange 2, receiver: OR the remote masks into this rank's leaves (one warp per record); the last block then
-// publishes this rank's error flags
+// exchange 2, receiver: OR the remote masks into this rank's leaves. The records of all senders are addressed as one
+// dense range (as in k_shard_dedupe), eight lanes per record: one finds / creates the leaf, each merges one 64-bit word.
+// The last block then publishes this rank's error flags.
 __global__ void __launch_bounds__(TPB) k_shard_merge(GridDev g, GridDev gs, ScanParams p, ScanBuffers b, const int4* recv, u32 cap, u32* flags) {
-  const u32 lane = threadIdx.x & 31;
-  const u32 warps = gridDim.x * (TPB / 32);
-  const u32 slots = p.world * cap;
+  const u32 lane = threadIdx.x & 31, sub = lane & 7u, first = lane & 24u;
+  const u32 groups = gridDim.x * (TPB / 8);
   wait_arrivals(b.my_flags ? b.my_flags + MBOX_FLAG2 : nullptr, 1, p.world, p.xseq2, const_cast<u32*>(b.poison));
   const bool frozen = *b.poison != 0u;
-  for (u32 t = blockIdx.x * (TPB / 32) + (threadIdx.x >> 5); t < slots && !frozen; t += warps) {
-    const u32 j = t % cap;
-    const int4* block = recv + (size_t)(t - j) * 5;
-    if (j == 0u || j > min((u32)__ldcg(&block[0]).x, cap - 1u)) continue;
-    const int4 hdr = __ldcg(&block[(size_t)j * 5]);
+  u32 incl = lane < p.world ? min((u32)__ldcg(&recv[(size_t)lane * cap * 5]).x, cap - 1u) : 0u;
+  for (int o = 1; o < 32; o <<= 1) {
+    const u32 v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= (u32)o) incl += v;
+  }
+  const u32 total = frozen ? 0u : __shfl_sync(0xffffffffu, incl, 31);
+  for (u32 t0 = (blockIdx.x * (TPB / 32) + (threadIdx.x >> 5)) * 4u; t0 < total; t0 += groups) {  // warp-uniform trip count
+    const u32 t = t0 + (lane >> 3);
+    const int4* rec = nullptr;
+    u32 base = 0;
+    for (u32 src = 0; src < p.world; ++src) {
+      const u32 end = __shfl_sync(0xffffffffu, incl, src);
+      if (rec == nullptr && t >= base && t < end) rec = recv + ((size_t)src * cap + 1u + (t - base)) * 5;
+      base = end;
+    }
     u32 leaf = NONE;
-    if (lane == 0) leaf = leaf_find_or_create(g, hdr.x, hdr.y, hdr.z);
-    leaf = __shfl_sync(0xffffffffu, leaf, 0);
-    if (leaf == NONE) continue;
-    if (lane < 8) {
-      const unsigned long long bits = __ldcg(reinterpret_cast<const unsigned long long*>(block + (size_t)j * 5 + 1) + lane);
-      if (bits) mark_bits(g, leaf, reinterpret_cast<unsigned long long*>(leaf_touched(g, leaf)) + lane, bits, p.seq, &b.sc->n_touched, b.touched, p.touched_cap);
+    if (rec != nullptr && sub == 0) {
+      const int4 hdr = __ldcg(rec);
+      leaf = leaf_find_or_create(g, hdr.x, hdr.y, hdr.z);
+    }
+    leaf = __shfl_sync(0xffffffffu, leaf, first);
+    if (leaf != NONE) {
+      const unsigned long long bits = __ldcg(reinterpret_cast<const unsigned long long*>(rec + 1) + sub);
+      if (bits) mark_bits(g, leaf, reinterpret_cast<unsigned long long*>(leaf_touched(g, leaf)) + sub, bits, p.seq, &b.sc->n_touched, b.touched, p.touched_cap);
     }
   }
   __shared__ bool s_last;
-  __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicAdd(&b.sc->done3, 1u) == gridDim.x - 1;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicAdd(&b.sc->done3, 1u) == gridDim.x - 1;
+  }
   __syncthreads();
   if (!s_last) return;
   if (threadIdx.x == 0) b.sc->done3 = 0u;
+  __threadfence();  // acquire side: the error bits other blocks set before their tickets
   shard_flags(g, gs, p, b, flags);
 }
 
@@ -1907,8 +1945,10 @@ int Map::shard_resolve_mark(const void* recv_records, void* send_leaves, i64 cap
   p.clean16 = lean ? 1u : 0u;
   ++shard_attempt_;
   const GridDev g = grid.dev(), gs = scratch_->dev();
-  note_launch(), k_shard_dedupe<<<blocks_for(slots), TPB, 0, s>>>(p, buf_, slots, table1, lean ? (u32)(t1 * 12 / 16) : 0u);
-  note_launch(), k_resolve<2><<<blocks_for(slots), TPB, 0, s>>>(g, p, buf_, slots);
+  // a rank receives about one slice worth of records; the kernels loop if it is (much) more
+  const int rblocks = blocks_for(std::min<i64>(slots, 2 * (i64)p.rec_cap));
+  note_launch(), k_shard_dedupe<<<rblocks, TPB, 0, s>>>(p, buf_, slots, table1, lean ? (u32)(t1 * 12 / 16) : 0u);
+  note_launch(), k_resolve<2><<<rblocks, TPB, 0, s>>>(g, p, buf_, slots);
   if (!direct_mark()) {  // sharded scans always have packed coordinates
     note_launch(), k_mark_staged<true><<<sm_count() * MARK_STAGED_MIN_BLOCKS, TPB, 0, s>>>(g, gs, p, buf_);
   } else {

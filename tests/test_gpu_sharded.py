@@ -52,6 +52,23 @@ def test_local_shard_group_random_and_stale(bnx, port, exchange):
 
 
 @pytest.mark.parametrize("exchange", ["transpose", "p2p"])
+def test_local_shard_group_one_owner_gets_everything(bnx, port, exchange):
+    """all endpoints and rays inside ONE root (3.2 m cube): a single rank receives the records of every rank, more
+    than the receiving kernels are launched for (they loop), the other ranks receive nothing"""
+    from bonxai_b200.sharded import LocalShardGroup
+    rng = np.random.default_rng(11)
+    g, om = LocalShardGroup(0.1, 4, exchange=exchange, cap_records=1100), port.map(0.1)
+    for k in range(3):
+        pts = rng.uniform(0.15, 3.0, (4000, 3)).astype(np.float32)
+        o = np.float32([1.5, 1.5 + 0.1 * k, 1.5])
+        g.insert(pts, o, 10.0)
+        om.insert(pts, o, 10.0)
+        assert_same_dump(g.dump(), om.dump(), f"scan {k}")
+    sizes = sorted(s.map.active_count() for s in g.shards)
+    assert sizes[:3] == [0, 0, 0] and sizes[3] == om.active_count()
+
+
+@pytest.mark.parametrize("exchange", ["transpose", "p2p"])
 def test_local_shard_group_growth_and_small_exchange_buffers(bnx, port, monkeypatch, exchange):
     monkeypatch.setenv("BNX_INIT_LEAF_MB", "1")
     monkeypatch.setenv("BNX_INIT_INNER_MB", "0")
