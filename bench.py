@@ -202,7 +202,9 @@ def run_gpu(args):
             dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
             dist.barrier()
     capi.load_library()
-    stream = torch.cuda.current_stream()
+    # a real (non-blocking-capable) stream, not the legacy default stream: the library launches its kernels with
+    # programmatic dependent launch, which the NULL stream serialises
+    stream = torch.cuda.Stream()
 
     def barrier():
         if world > 1:
@@ -408,7 +410,8 @@ def run_gpu_sharded(args):
     with _stdout_to_stderr():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         dist.barrier()
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)  # ShardedMap launches on torch's current stream
     n_local = hi - lo
 
     def barrier():

@@ -54,6 +54,54 @@ inline bool direct_mark() {
 }
 
 // ------------------------------------------------------------------------------------------------
+// programmatic dependent launch (PDL): the kernels of a scan are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so the NEXT kernel of the stream is scheduled while this one
+// still runs (its launch latency and block start-up overlap this kernel's tail) and blocks in pdl_enter() until the
+// previous kernel has completed and its memory operations are visible. pdl_enter() is the first statement of
+// every scan kernel; in a kernel launched the ordinary way both instructions do nothing. BNX_PDL=0 turns it off.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+inline bool pdl_enabled() {
+  static const bool v = [] {
+    const char* e = std::getenv("BNX_PDL");
+    return !(e && std::strcmp(e, "0") == 0);
+  }();
+  return v;
+}
+
+// only the pipelined paths use it: between the memsets, event records and copies of the synchronous path it costs time
+thread_local bool t_pdl = false;
+struct PdlScope {
+  bool saved;
+  explicit PdlScope(bool on) : saved(t_pdl) { t_pdl = on && pdl_enabled(); }
+  ~PdlScope() { t_pdl = saved; }
+};
+
+template <typename... KArgs, typename... Args>
+inline void launch_scan_kernel(void (*kernel)(KArgs...), int blocks, int threads, cudaStream_t s, Args&&... args) {
+  note_launch();
+  if (!t_pdl) {
+    kernel<<<blocks, threads, 0, s>>>(KArgs(args)...);
+    return;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)blocks);
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+// ------------------------------------------------------------------------------------------------
 // peer-memory exchange primitives (sharded map)
 // ------------------------------------------------------------------------------------------------
 constexpr unsigned long long PEER_TIMEOUT_NS = 8000000000ull;  // a dead peer becomes ERR_PEER, never a hang
@@ -159,6 +207,7 @@ __device__ __forceinline__ unsigned long long pack_key(const int4& e) {
 
 template <bool F64, bool VEC4, bool PACKED>
 __global__ void __launch_bounds__(TPB) k_classify(const unsigned char* __restrict__ pts, u32 stride, ScanParams p, ScanBuffers b) {
+  pdl_enter();
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.n || *b.poison) return;
   double px, py, pz;
@@ -321,6 +370,7 @@ __device__ __forceinline__ u32 shard_table_mask(const ScanParams& p, u32 receive
 //         w = global point index << 1 | type, winner = lowest w of its voxel.
 template <int MODE>
 __global__ void __launch_bounds__(TPB) k_resolve(GridDev g, ScanParams p, ScanBuffers b, u32 count) {
+  pdl_enter();
   constexpr bool PENDING = MODE == 1;
   __shared__ unsigned long long s_warp[TPB / 32];
   __shared__ u32 s_warp_e[TPB / 32];
@@ -563,6 +613,7 @@ __device__ __forceinline__ void mark_bits(const GridDev& G, u32 leaf, unsigned l
 // their (leaf, mask) records travel to the owner after the kernel.
 template <bool SHARD>
 __global__ void __launch_bounds__(TPB, MARK_MIN_BLOCKS) k_mark(GridDev g, GridDev gs, ScanParams p, ScanBuffers b) {
+  pdl_enter();
   __shared__ unsigned long long s_bits[CHUNK][TPB];
   __shared__ unsigned char s_key[CHUNK][TPB];
   const unsigned long long rc = b.sc->ray_chunk;
@@ -876,6 +927,7 @@ __device__ __forceinline__ void flush_stage(MarkStage& S, const GridDev& g, cons
 
 template <bool SHARD>
 __global__ void __launch_bounds__(TPB, MARK_STAGED_MIN_BLOCKS) k_mark_staged(GridDev g, GridDev gs, ScanParams p, ScanBuffers b) {
+  pdl_enter();
   __shared__ MarkStage S;
   const unsigned long long rc = b.sc->ray_chunk;
   const u32 n_rays = (u32)(rc >> 40);
@@ -946,6 +998,7 @@ __global__ void __launch_bounds__(TPB, MARK_STAGED_MIN_BLOCKS) k_mark_staged(Gri
 
 // retry path only: a failed attempt leaves touched bits behind; the list of that attempt says where
 __global__ void __launch_bounds__(TPB) k_clear_touched(GridDev g, ScanBuffers b, u32 n) {
+  pdl_enter();
   const u32 lane = threadIdx.x & 31;
   const u32 warps = gridDim.x * (TPB / 32);
   for (u32 t = blockIdx.x * (TPB / 32) + (threadIdx.x >> 5); t < n; t += warps) {
@@ -984,6 +1037,7 @@ __device__ __forceinline__ void read_gate(const ScanParams& p, const ScanBuffers
 // endpoints (clearPoint / addMissPoint, :43-54,81-89). Hit endpoints are never stale (resolve filtered them) and win
 // over ray cells, like the reference where they are stamped before any ray is cast.
 __global__ void __launch_bounds__(TPB) k_apply_leaves(GridDev g, ScanParams p, ScanBuffers b) {
+  pdl_enter();
   // last kernel of the scan: the host reads counters + grid counters with one copy
   u32 gate_pool, gate_ovf;
   read_gate(p, b, gate_pool, gate_ovf);
@@ -1099,6 +1153,7 @@ __global__ void __launch_bounds__(TPB) k_apply_leaves(GridDev g, ScanParams p, S
 // pipelined insert: clears the scan counters + dedupe table like the memset of the synchronous path, unless the
 // pipeline is frozen (the failed scan's counters and touched list must survive until the host has seen them)
 __global__ void __launch_bounds__(TPB) k_begin_scan(ScanBuffers b, uint4* base, u32 n16) {
+  pdl_enter();
   if (*b.poison) return;
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x) base[i] = make_uint4(0, 0, 0, 0);
 }
@@ -1110,6 +1165,7 @@ __global__ void __launch_bounds__(TPB) k_begin_scan(ScanBuffers b, uint4* base, 
 // the owner's inbox (peer memory) or of the caller's send buffer: record = {x, y, z, global point index << 1 | type};
 // slot 0 of a block carries the count. Slots are handed out per owner by a warp-aggregated atomic on a LOCAL counter.
 __global__ void __launch_bounds__(TPB) k_shard_bucket(ScanParams p, ScanBuffers b, u32 index_base) {
+  pdl_enter();
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   const u32 lane = threadIdx.x & 31;
   const u32 cap = p.rec_cap;
@@ -1144,6 +1200,7 @@ __global__ void __launch_bounds__(TPB) k_shard_bucket(ScanParams p, ScanBuffers 
 // exchange 1, receiver: lowest global index per endpoint voxel over the records of all ranks. Pipelined path: also
 // zeroes the sender-side dedupe table of this scan (its last reader, k_shard_bucket, is done) for the next scan.
 __global__ void __launch_bounds__(TPB) k_shard_dedupe(ScanParams p, ScanBuffers b, u32 count, uint4* clean, u32 clean16) {
+  pdl_enter();
   // peer-memory exchange: the records of every rank must have arrived (the wait happens even when the pipeline is
   // frozen, so that no rank ever runs ahead of an exchange point)
   wait_arrivals(b.my_flags ? b.my_flags + MBOX_FLAG1 : nullptr, 1, p.world, p.xseq1, const_cast<u32*>(b.poison));
@@ -1177,6 +1234,7 @@ __global__ void __launch_bounds__(TPB) k_shard_dedupe(ScanParams p, ScanBuffers 
 // exchange 2, sender: eight lanes per scratch leaf touched in this scan -> {leaf origin, 512-bit mask} into block [rank]
 // of the inbox of the rank that owns its root; the scratch mask is cleared for the next scan. Record = 5 x int4 (80 B).
 __global__ void __launch_bounds__(TPB) k_shard_emit(GridDev gs, ScanParams p, ScanBuffers b) {
+  pdl_enter();
   const u32 n = min(b.sc->n_touched2, p.touched2_cap);
   const u32 cap = p.leaf_cap2;
   const u32 lane = threadIdx.x & 31, sub = lane & 7u, first = lane & 24u;
@@ -1238,6 +1296,7 @@ __device__ __forceinline__ void shard_flags(const GridDev& g, const GridDev& gs,
 // dense range (as in k_shard_dedupe), eight lanes per record: one finds / creates the leaf, each merges one 64-bit word.
 // The last block then publishes this rank's error flags.
 __global__ void __launch_bounds__(TPB) k_shard_merge(GridDev g, GridDev gs, ScanParams p, ScanBuffers b, const int4* recv, u32 cap, u32* flags) {
+  pdl_enter();
   const u32 lane = threadIdx.x & 31, sub = lane & 7u, first = lane & 24u;
   const u32 groups = gridDim.x * (TPB / 8);
   wait_arrivals(b.my_flags ? b.my_flags + MBOX_FLAG2 : nullptr, 1, p.world, p.xseq2, const_cast<u32*>(b.poison));
@@ -1488,11 +1547,10 @@ int Map::insert(const void* points, i64 stride_bytes, i64 n, bool f64, const dou
 
 template <bool F64, bool VEC4>
 static void launch_classify(bool packed, int blocks, cudaStream_t s, const unsigned char* pts, u32 stride, const ScanParams& p, const ScanBuffers& b) {
-  note_launch();
   if (packed) {
-    k_classify<F64, VEC4, true><<<blocks, TPB, 0, s>>>(pts, stride, p, b);
+    launch_scan_kernel(k_classify<F64, VEC4, true>, blocks, TPB, s, pts, stride, p, b);
   } else {
-    k_classify<F64, VEC4, false><<<blocks, TPB, 0, s>>>(pts, stride, p, b);
+    launch_scan_kernel(k_classify<F64, VEC4, false>, blocks, TPB, s, pts, stride, p, b);
   }
 }
 
@@ -1518,7 +1576,7 @@ int Map::launch_scan(const void* d_points, i64 stride_bytes, bool f64, ScanParam
       clean_slots_ = 0;  // the synchronous path leaves a used table behind
     } else {
       if (slots > clean_slots_) {
-        note_launch(), k_begin_scan<<<std::min<int>(persistent, blocks_for((i64)(bytes / 16))), TPB, 0, s>>>(buf_, reinterpret_cast<uint4*>(d_sc_), (u32)(bytes / 16));
+        launch_scan_kernel(k_begin_scan, std::min<int>(persistent, blocks_for((i64)(bytes / 16))), TPB, s, buf_, reinterpret_cast<uint4*>(d_sc_), (u32)(bytes / 16));
       }
       p.clean16 = (u32)(slots * 12 / 16);  // k_mark zeroes table + keys again, the epilogue the counters
       clean_slots_ = slots;
@@ -1538,16 +1596,16 @@ int Map::launch_scan(const void* d_points, i64 stride_bytes, bool f64, ScanParam
   } else {
     BNX_CUDA(cudaMemsetAsync(d_sc_, 0, SC_BYTES, s));
   }
-  if (n_pending_) note_launch(), k_resolve<1><<<blocks_for(n_pending_), TPB, 0, s>>>(g, p, buf_, n_pending_);
-  if (n > 0) note_launch(), k_resolve<0><<<blocks_for(n), TPB, 0, s>>>(g, p, buf_, (u32)n);
+  if (n_pending_) launch_scan_kernel(k_resolve<1>, blocks_for(n_pending_), TPB, s, g, p, buf_, n_pending_);
+  if (n > 0) launch_scan_kernel(k_resolve<0>, blocks_for(n), TPB, s, g, p, buf_, (u32)n);
   if (profiling && first_attempt) cudaEventRecord(ev_[3], s);
   if (p.packed && !direct_mark()) {
-    note_launch(), k_mark_staged<false><<<sm_count() * MARK_STAGED_MIN_BLOCKS, TPB, 0, s>>>(g, g, p, buf_);
+    launch_scan_kernel(k_mark_staged<false>, sm_count() * MARK_STAGED_MIN_BLOCKS, TPB, s, g, g, p, buf_);
   } else {
-    note_launch(), k_mark<false><<<persistent, TPB, 0, s>>>(g, g, p, buf_);
+    launch_scan_kernel(k_mark<false>, persistent, TPB, s, g, g, p, buf_);
   }
   if (profiling && first_attempt) cudaEventRecord(ev_[4], s);
-  note_launch(), k_apply_leaves<<<persistent, TPB, 0, s>>>(g, p, buf_);
+  launch_scan_kernel(k_apply_leaves, persistent, TPB, s, g, p, buf_);
   BNX_CUDA(cudaGetLastError());
   if (profiling && first_attempt) cudaEventRecord(ev_[5], s);
   return BNX_OK;
@@ -1687,7 +1745,10 @@ int Map::insert_async(const void* points, i64 stride_bytes, i64 n, bool f64, con
     BNX_CUDA(cudaStreamWaitEvent(s, ev_copied_[slot], 0));
     d_points = b_stage_[slot].p;
   }
-  BNX_TRY(launch_scan(d_points, stride_bytes, f64, q.p, true));
+  {
+    PdlScope pdl(true);
+    BNX_TRY(launch_scan(d_points, stride_bytes, f64, q.p, true));
+  }
   if (where == BNX_HOST && n > 0) {
     const int slot = (int)(q.p.async_id & 1u);
     BNX_CUDA(cudaEventRecord(ev_consumed_[slot], s));
@@ -1895,7 +1956,7 @@ int Map::shard_begin(const void* points, i64 stride_bytes, i64 n, bool f64, u32 
     }
   }
   // always launched: its last block writes the block headers (counts) and, with mailboxes, the arrival stamps
-  note_launch(), k_shard_bucket<<<blocks, TPB, 0, s>>>(p, buf_, index_base);
+  launch_scan_kernel(k_shard_bucket, blocks, TPB, s, p, buf_, index_base);
   BNX_CUDA(cudaGetLastError());
   if (profiling) cudaEventRecord(ev_[1], s);
   return BNX_OK;
@@ -1947,14 +2008,14 @@ int Map::shard_resolve_mark(const void* recv_records, void* send_leaves, i64 cap
   const GridDev g = grid.dev(), gs = scratch_->dev();
   // a rank receives about one slice worth of records; the kernels loop if it is (much) more
   const int rblocks = blocks_for(std::min<i64>(slots, 2 * (i64)p.rec_cap));
-  note_launch(), k_shard_dedupe<<<rblocks, TPB, 0, s>>>(p, buf_, slots, table1, lean ? (u32)(t1 * 12 / 16) : 0u);
-  note_launch(), k_resolve<2><<<rblocks, TPB, 0, s>>>(g, p, buf_, slots);
+  launch_scan_kernel(k_shard_dedupe, rblocks, TPB, s, p, buf_, slots, table1, lean ? (u32)(t1 * 12 / 16) : 0u);
+  launch_scan_kernel(k_resolve<2>, rblocks, TPB, s, g, p, buf_, slots);
   if (!direct_mark()) {  // sharded scans always have packed coordinates
-    note_launch(), k_mark_staged<true><<<sm_count() * MARK_STAGED_MIN_BLOCKS, TPB, 0, s>>>(g, gs, p, buf_);
+    launch_scan_kernel(k_mark_staged<true>, sm_count() * MARK_STAGED_MIN_BLOCKS, TPB, s, g, gs, p, buf_);
   } else {
-    note_launch(), k_mark<true><<<persistent, TPB, 0, s>>>(g, gs, p, buf_);
+    launch_scan_kernel(k_mark<true>, persistent, TPB, s, g, gs, p, buf_);
   }
-  note_launch(), k_shard_emit<<<persistent, TPB, 0, s>>>(gs, p, buf_);
+  launch_scan_kernel(k_shard_emit, persistent, TPB, s, gs, p, buf_);
   BNX_CUDA(cudaGetLastError());
   if (profiling) cudaEventRecord(ev_[2], s);
   return BNX_OK;
@@ -1969,7 +2030,7 @@ int Map::shard_merge(const void* recv_leaves, void* flags) {
   }
   cudaStream_t s = grid.stream();
   const GridDev g = grid.dev(), gs = scratch_->dev();
-  note_launch(), k_shard_merge<<<sm_count() * 8, TPB, 0, s>>>(g, gs, sp_, buf_, static_cast<const int4*>(recv_leaves), sp_.leaf_cap2, static_cast<u32*>(flags));
+  launch_scan_kernel(k_shard_merge, sm_count() * 8, TPB, s, g, gs, sp_, buf_, static_cast<const int4*>(recv_leaves), sp_.leaf_cap2, static_cast<u32*>(flags));
   BNX_CUDA(cudaGetLastError());
   if (profiling) cudaEventRecord(ev_[3], s);
   return BNX_OK;
@@ -1986,7 +2047,7 @@ int Map::shard_finish(const void* flags_reduced, int* retry) {
   const int persistent = sm_count() * 8;
   const GridDev g = grid.dev();
   buf_.gate = static_cast<const u32*>(flags_reduced);
-  note_launch(), k_apply_leaves<<<persistent, TPB, 0, s>>>(g, sp_, buf_);
+  launch_scan_kernel(k_apply_leaves, persistent, TPB, s, g, sp_, buf_);
   BNX_CUDA(cudaGetLastError());
   if (profiling) cudaEventRecord(ev_[4], s);
   BNX_CUDA(cudaMemcpyAsync(h_status_, d_sc_, sizeof(ScanCounters), cudaMemcpyDeviceToHost, s));
@@ -2225,6 +2286,7 @@ int Map::shard_insert(const void* points, i64 stride_bytes, i64 n, bool f64, u32
     }
   }
   const bool p2p = want_p2p_;
+  PdlScope pdl(async);
   u32* flags = x_flags_.as<u32>();
   const u32 my_async = async ? async_next_++ : NONE;
   shard_async_ = async;
@@ -2240,7 +2302,7 @@ int Map::shard_insert(const void* points, i64 stride_bytes, i64 n, bool f64, u32
     if (!p2p) BNX_NCCL(api, api.AllReduce(flags, flags, 4, ncclUint32, ncclMax, static_cast<ncclComm_t>(comm_), s));
     if (async) {
       buf_.gate = p2p ? reinterpret_cast<const u32*>(mbox_) + MBOX_FLAGS4 : flags;
-      note_launch(), k_apply_leaves<<<sm_count() * 8, TPB, 0, s>>>(grid.dev(), sp_, buf_);
+      launch_scan_kernel(k_apply_leaves, sm_count() * 8, TPB, s, grid.dev(), sp_, buf_);
       BNX_CUDA(cudaGetLastError());
       if (profiling) cudaEventRecord(ev_[4], s);
       buf_.gate = nullptr;

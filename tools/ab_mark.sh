@@ -1,6 +1,6 @@
-# A/B of the two mark kernels on the LiDAR bench (BNX_MARK=direct|staged); optional first arg: pytest selection
+# bench of the LiDAR config with the mark kernel variants named in $MODES (default "direct"); optional first arg: pytest selection
 if [ -n "$1" ]; then python -m pytest $1 -m gpu -x -q 2>&1 | tail -3; fi
-for m in direct staged; do BNX_MARK=$m python bench.py --steps 300 --warmup 10 --no-cpu > gpurun_out/bench_s_$m.json 2> gpurun_out/bench_s_$m.err; python - <<PY
+for m in ${MODES:-direct}; do BNX_MARK=$m python bench.py --steps 300 --warmup 10 --no-cpu > gpurun_out/bench_s_$m.json 2> gpurun_out/bench_s_$m.err; python - <<PY
 import json
 d=json.loads([l for l in open("gpurun_out/bench_s_$m.json") if l.startswith("{")][-1])
 print("$m", round(d["value"]/1e6), d["ms_per_step"]*1e3, d["phase_us_per_scan"], d["e2e"]["ms_per_step"]*1e3)
