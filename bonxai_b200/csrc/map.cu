@@ -42,17 +42,6 @@ constexpr u32 OVF_TILES = 1u, OVF_CHUNKS = 2u, OVF_RECORDS = 4u, OVF_LEAVES = 8u
 
 inline int blocks_for(i64 n, int tpb = TPB) { return (int)std::max<i64>(1, ceil_div(n, tpb)); }
 
-// Two mark kernels. "direct" (default) flushes every (leaf, word) segment of a ray chunk to the grid; "staged"
-// (BNX_MARK=staged) first ORs the segments of neighbouring rays into leaf masks in shared memory. Measured on the LiDAR
-// bench the staged kernel is not faster yet (profiles/r1_notes.md), so it stays opt-in.
-inline bool direct_mark() {
-  static const bool v = [] {
-    const char* e = std::getenv("BNX_MARK");
-    return !(e && std::strcmp(e, "staged") == 0);
-  }();
-  return v;
-}
-
 // ------------------------------------------------------------------------------------------------
 // programmatic dependent launch (PDL): the kernels of a scan are launched with
 // cudaLaunchAttributeProgrammaticStreamSerialization, so the NEXT kernel of the stream is scheduled while this one
@@ -707,295 +696,6 @@ __global__ void __launch_bounds__(TPB, MARK_MIN_BLOCKS) k_mark(GridDev g, GridDe
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// phase 3, staged flavour (opt-in, BNX_MARK=staged; needs all voxel coordinates of the scan to fit 21 bits per axis)
-// ------------------------------------------------------------------------------------------------
-// Neighbouring rays of a scan (adjacent beams / azimuths) run through the same leaves, so every block takes a
-// CONTIGUOUS range of tiles and ORs the segments of its rays into leaf masks held in SHARED memory: a 256-slot
-// open-addressing table keyed by the packed leaf coordinates (64-bit atomicCAS claims a slot), 512 mask bits per
-// slot. Only when the table fills up, and at the end, every staged leaf is looked up (or created) ONCE in the
-// grid and its non-zero 64-bit words go to the leaf's touched mask with the usual test + atomicOr.
-//   walk    one lane = one 8-cell chunk, straight-line code (all lanes run CHUNK + 1 rounds and reconverge). A lane
-//           whose (leaf, word) segment ends appends it to its warp's segment QUEUE (ballot + popc: dense).
-//   drain   whenever the queue holds 32 segments the warp stages them, one per lane: every staging round is full,
-//           instead of one sparse round per cell.
-#ifndef MARK_STAGED_MIN_BLOCKS
-#define MARK_STAGED_MIN_BLOCKS 6
-#endif
-constexpr u32 MARK_SLOTS = 256;
-constexpr u32 MARK_FLUSH_AT = 128;  // staged leaves that trigger a flush at the next group boundary
-constexpr u32 MARK_GROUP = 4;       // tiles per warp between two block-wide flush checks
-constexpr u32 MARK_QUEUE = 64;      // ring entries per warp (32 left over + 32 new at most)
-struct MarkStage {
-  unsigned long long key[MARK_SLOTS];      // 0 = empty, else packed leaf coordinates (bit 63 set)
-  unsigned long long mask[MARK_SLOTS][8];  // touched bits of the staged leaf, same layout as the leaf's own mask
-  u32 leaf[MARK_SLOTS];                    // flush: grid index of the leaf (bit 31: it lives in the scratch grid)
-  u32 used;
-  int4 q_where[TPB / 32][MARK_QUEUE];                // segment queue: leaf coordinates + mask word
-  unsigned long long q_bits[TPB / 32][MARK_QUEUE];   //                its bits
-};
-
-// leaf coordinates are voxel coordinates >> 3: |l| < 2^17 for packed scans
-__device__ __forceinline__ unsigned long long pack_leaf(int lx, int ly, int lz) {
-  return (unsigned long long)(u32)(lx + (1 << 19)) | ((unsigned long long)(u32)(ly + (1 << 19)) << 20) |
-         ((unsigned long long)(u32)(lz + (1 << 19)) << 40) | (1ull << 63);
-}
-
-__device__ __forceinline__ bool stage_segment(MarkStage& S, int lx, int ly, int lz, u32 w, unsigned long long bits) {
-  const unsigned long long key = pack_leaf(lx, ly, lz);
-  u32 h = (((u32)lx * 0x9E3779B1u) ^ ((u32)ly * 0x85EBCA77u) ^ ((u32)lz * 0xC2B2AE3Du)) >> 24;
-#pragma unroll 1
-  for (int probe = 0; probe < 8; ++probe) {
-    unsigned long long k = S.key[h];
-    if (k == 0ull) {
-      k = atomicCAS(&S.key[h], 0ull, key);
-      if (k == 0ull) {
-        atomicAdd(&S.used, 1u);
-        k = key;
-      }
-    }
-    if (k == key) {
-      u32* m = reinterpret_cast<u32*>(&S.mask[h][w]);
-      const u32 lo = (u32)bits, hi = (u32)(bits >> 32);
-      if (lo & ~m[0]) atomicOr(&m[0], lo);
-      if (hi & ~m[1]) atomicOr(&m[1], hi);
-      return true;
-    }
-    h = (h + 1) & (MARK_SLOTS - 1);
-  }
-  return false;
-}
-
-// one segment straight to the grid (the staging table had no room within its probe limit)
-template <bool SHARD>
-__device__ __forceinline__ void mark_direct(const GridDev& g, const GridDev& gs, const ScanParams& p, const ScanBuffers& b, int lx, int ly, int lz, u32 w,
-                                            unsigned long long bits) {
-  u32 inner = NONE;
-  if (!SHARD || shard_owner(lx >> 2, ly >> 2, lz >> 2, p.world) == p.rank) {
-    const u32 leaf = mark_leaf(g, inner, true, lx, ly, lz);
-    if (leaf != NONE) mark_bits(g, leaf, reinterpret_cast<unsigned long long*>(leaf_touched(g, leaf)) + w, bits, p.seq, &b.sc->n_touched, b.touched, p.touched_cap);
-  } else {
-    const u32 leaf = mark_leaf(gs, inner, true, lx, ly, lz);
-    if (leaf != NONE) mark_bits(gs, leaf, reinterpret_cast<unsigned long long*>(leaf_touched(gs, leaf)) + w, bits, p.seq, &b.sc->n_touched2, b.touched2, p.touched2_cap);
-  }
-}
-
-// the first `count` (<= 32) queued segments of this warp, one per lane
-template <bool SHARD>
-__device__ __forceinline__ void drain_queue(MarkStage& S, const GridDev& g, const GridDev& gs, const ScanParams& p, const ScanBuffers& b, u32 warp, u32 lane,
-                                            u32 head, u32 count) {
-  __syncwarp();
-  if (lane < count) {
-    const u32 at = (head + lane) & (MARK_QUEUE - 1);
-    const int4 wh = S.q_where[warp][at];
-    const unsigned long long bits = S.q_bits[warp][at];
-    if (!stage_segment(S, wh.x, wh.y, wh.z, (u32)wh.w, bits)) mark_direct<SHARD>(g, gs, p, b, wh.x, wh.y, wh.z, (u32)wh.w, bits);
-  }
-  __syncwarp();
-}
-
-// floor(n / d) for n < 2^23 with the reciprocal of d at hand (rcp = 1.0f / d): one multiply + one fix-up step
-__device__ __forceinline__ u32 div_small(u32 n, u32 d, float rcp) {
-  u32 q = (u32)__float2int_rz(__fmul_rz((float)n, rcp));
-  const int r = (int)(n - q * d);
-  if (r < 0) {
-    --q;
-  } else if (r >= (int)d) {
-    ++q;
-  }
-  return q;
-}
-
-// the same exact DDA as walk_chunk for the cells [k0, k1) of one ray (k0 == k1: an idle lane that only takes part in
-// the warp-wide queue bookkeeping). qh / qn: head and fill of the warp's segment ring, kept identical in all lanes.
-template <bool SHARD>
-__device__ __forceinline__ void walk_stage(MarkStage& S, const GridDev& g, const GridDev& gs, const ScanParams& p, const ScanBuffers& b, const RayGeom& r,
-                                           u32 k0, u32 k1, u32 warp, u32 lane, u32& qh, u32& qn) {
-  u32 px, py, pz;
-  if (r.m < 2048u) {  // 2 * k0 * a + m < 2^23: exact in float
-    const float rcp = __frcp_rn((float)(2u * r.m));
-    px = div_small(2u * k0 * r.ax + r.m, 2u * r.m, rcp);
-    py = div_small(2u * k0 * r.ay + r.m, 2u * r.m, rcp);
-    pz = div_small(2u * k0 * r.az + r.m, 2u * r.m, rcp);
-  } else {
-    px = (u32)((2ull * k0 * r.ax + r.m) / (2ull * r.m));
-    py = (u32)((2ull * k0 * r.ay + r.m) / (2ull * r.m));
-    pz = (u32)((2ull * k0 * r.az + r.m) / (2ull * r.m));
-  }
-  // packed coordinates: m < 2^21 and k0 < m, the residuals fit 32 bits... only through 64-bit products
-  int ex = (int)((i64)k0 * r.ax - (i64)px * r.m), ey = (int)((i64)k0 * r.ay - (i64)py * r.m), ez = (int)((i64)k0 * r.az - (i64)pz * r.m);
-  int x = p.Ox + r.sx * (int)px, y = p.Oy + r.sy * (int)py, z = p.Oz + r.sz * (int)pz;
-  const int em = (int)r.m, half = (int)((r.m + 1u) >> 1);  // (e << 1) >= m  <=>  e >= ceil(m / 2)
-  const int dax = (int)r.ax, day = (int)r.ay, daz = (int)r.az;
-  const u32 cnt = k1 - k0;
-  const u32 lt = (1u << lane) - 1u;
-  u32 key = 0xFFFFFFFFu;
-  unsigned long long bits = 0;
-  int lx = 0, ly = 0, lz = 0;
-  // Straight-line control flow (fully unrolled, no early exit): all lanes run CHUNK + 1 rounds, the extra round ends
-  // the last segment.
-#pragma unroll
-  for (u32 c = 0; c <= CHUNK; ++c) {
-    // segment key: mask word (z & 7) + the leaf-parity bit of every axis. Inside a chunk a coordinate crosses at
-    // most one leaf boundary, so equal keys <=> same leaf and same word.
-    const bool live = c < cnt;
-    const u32 kc = live ? (((u32)z & 7u) | ((u32)x & 8u) | (((u32)y & 8u) << 1) | (((u32)z & 8u) << 2)) : 0xFFFFFFFEu;
-    const bool change = kc != key;
-    const bool emit = change && bits != 0ull;
-    const u32 em_mask = __ballot_sync(0xffffffffu, emit);
-    if (em_mask) {
-      if (emit) {
-        const u32 at = (qh + qn + __popc(em_mask & lt)) & (MARK_QUEUE - 1);
-        S.q_where[warp][at] = make_int4(lx, ly, lz, (int)(key & 7u));
-        S.q_bits[warp][at] = bits;
-      }
-      qn += __popc(em_mask);
-      if (qn >= 32u) {
-        drain_queue<SHARD>(S, g, gs, p, b, warp, lane, qh, 32u);
-        qh = (qh + 32u) & (MARK_QUEUE - 1);
-        qn -= 32u;
-      }
-    }
-    if (change) {
-      key = kc;
-      bits = 0;
-      lx = x >> 3;
-      ly = y >> 3;
-      lz = z >> 3;
-    }
-    if (live) {
-      bits |= 1ull << (((u32)x & 7u) | (((u32)y & 7u) << 3));
-      ex += dax;
-      ey += day;
-      ez += daz;
-      if (ex >= half) {
-        x += r.sx;
-        ex -= em;
-      }
-      if (ey >= half) {
-        y += r.sy;
-        ey -= em;
-      }
-      if (ez >= half) {
-        z += r.sz;
-        ez -= em;
-      }
-    }
-  }
-}
-
-// staged leaves -> grid: one thread per slot finds / creates its leaf, then one thread per (slot, word) merges the bits
-template <bool SHARD>
-__device__ __forceinline__ void flush_stage(MarkStage& S, const GridDev& g, const GridDev& gs, const ScanParams& p, const ScanBuffers& b) {
-  for (u32 slot = threadIdx.x; slot < MARK_SLOTS; slot += TPB) {
-    const unsigned long long key = S.key[slot];
-    u32 leaf = NONE;
-    if (key) {
-      const int lx = (int)(u32)(key & 0xFFFFFu) - (1 << 19), ly = (int)(u32)((key >> 20) & 0xFFFFFu) - (1 << 19), lz = (int)(u32)((key >> 40) & 0xFFFFFu) - (1 << 19);
-      u32 inner = NONE;
-      if (!SHARD || shard_owner(lx >> 2, ly >> 2, lz >> 2, p.world) == p.rank) {
-        leaf = mark_leaf(g, inner, true, lx, ly, lz);
-      } else {
-        leaf = mark_leaf(gs, inner, true, lx, ly, lz);
-        if (leaf != NONE) leaf |= 0x80000000u;
-      }
-    }
-    S.leaf[slot] = leaf;
-  }
-  __syncthreads();
-  for (u32 idx = threadIdx.x; idx < MARK_SLOTS * 8u; idx += TPB) {
-    const u32 slot = idx >> 3, w = idx & 7u;
-    const unsigned long long bits = S.mask[slot][w];
-    if (bits) {
-      S.mask[slot][w] = 0ull;
-      const u32 leaf = S.leaf[slot];
-      if (leaf != NONE) {
-        if (!SHARD || !(leaf & 0x80000000u)) {
-          mark_bits(g, leaf, reinterpret_cast<unsigned long long*>(leaf_touched(g, leaf)) + w, bits, p.seq, &b.sc->n_touched, b.touched, p.touched_cap);
-        } else {
-          const u32 l2 = leaf & 0x7FFFFFFFu;
-          mark_bits(gs, l2, reinterpret_cast<unsigned long long*>(leaf_touched(gs, l2)) + w, bits, p.seq, &b.sc->n_touched2, b.touched2, p.touched2_cap);
-        }
-      }
-    }
-  }
-  __syncthreads();
-  for (u32 slot = threadIdx.x; slot < MARK_SLOTS; slot += TPB) S.key[slot] = 0ull;
-  if (threadIdx.x == 0) S.used = 0u;
-  __syncthreads();
-}
-
-template <bool SHARD>
-__global__ void __launch_bounds__(TPB, MARK_STAGED_MIN_BLOCKS) k_mark_staged(GridDev g, GridDev gs, ScanParams p, ScanBuffers b) {
-  pdl_enter();
-  __shared__ MarkStage S;
-  const unsigned long long rc = b.sc->ray_chunk;
-  const u32 n_rays = (u32)(rc >> 40);
-  const u32 total = (u32)(rc & CHUNK_FIELD);
-  if (b.sc->overflow | *b.poison) return;
-  if (p.clean16) {  // see k_mark
-    if (SHARD) {
-      int4 e_;
-      bool f_;
-      const u32 n16 = (shard_table_mask(p, shard_locate(p, b, NONE, f_, e_)) + 1u) / 4u;
-      uint4* tab = reinterpret_cast<uint4*>(b.table);
-      uint4* keys = reinterpret_cast<uint4*>(b.keys);
-      for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < 3u * n16; i += gridDim.x * blockDim.x) {
-        if (i < n16) {
-          tab[i] = make_uint4(0, 0, 0, 0);
-        } else {
-          keys[i - n16] = make_uint4(0, 0, 0, 0);
-        }
-      }
-    } else {
-      uint4* tab = reinterpret_cast<uint4*>(b.table);
-      for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < p.clean16; i += gridDim.x * blockDim.x) tab[i] = make_uint4(0, 0, 0, 0);
-    }
-  }
-  {
-    unsigned long long* z = reinterpret_cast<unsigned long long*>(&S);
-    for (u32 i = threadIdx.x; i < MARK_SLOTS * 9u; i += TPB) z[i] = 0ull;  // keys + masks
-    if (threadIdx.x == 0) S.used = 0u;
-  }
-  __syncthreads();
-  const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const u32 n_tiles = (total + 31u) >> 5;
-  const u32 t0 = (u32)((u64)blockIdx.x * n_tiles / gridDim.x), t1 = (u32)((u64)(blockIdx.x + 1u) * n_tiles / gridDim.x);
-  constexpr u32 PER_GROUP = (TPB / 32) * MARK_GROUP;
-  u32 qh = 0, qn = 0;
-  for (u32 base = t0; base < t1; base += PER_GROUP) {
-    // warp w walks MARK_GROUP adjacent tiles of this group
-    for (u32 j = 0; j < MARK_GROUP; ++j) {
-      const u32 tile = base + warp * MARK_GROUP + j;
-      if (tile >= t1) break;
-      const u32 c0 = tile * 32;
-      const u32 r_first = b.tile_first[tile];
-      // which of the next 32 rays start inside this tile? bit j = a ray starts at chunk c0 + j
-      const u32 rb = r_first + 1 + lane;
-      u32 bit = 0;
-      if (rb < n_rays) {
-        const u32 cb = (u32)b.rays[rb].w;
-        if (cb - c0 < 32u) bit = 1u << (cb - c0);
-      }
-      const u32 starts = __reduce_or_sync(0xffffffffu, bit);
-      const u32 chunk = c0 + lane;
-      const u32 r = min(r_first + __popc(starts & ((2u << lane) - 1u)), n_rays - 1u);
-      const int4 ray = b.rays[r];
-      const RayGeom rg = ray_geom(p, ray.x, ray.y, ray.z);
-      u32 k0 = 0, k1 = 0;
-      if (chunk < total) chunk_range(rg, chunk - (u32)ray.w, k0, k1);
-      walk_stage<SHARD>(S, g, gs, p, b, rg, k0, k1, warp, lane, qh, qn);
-    }
-    if (qn) {
-      drain_queue<SHARD>(S, g, gs, p, b, warp, lane, qh, qn);
-      qh = 0;
-      qn = 0;
-    }
-    __syncthreads();
-    if (S.used >= MARK_FLUSH_AT || base + PER_GROUP >= t1) flush_stage<SHARD>(S, g, gs, p, b);
-  }
-}
-
 // retry path only: a failed attempt leaves touched bits behind; the list of that attempt says where
 __global__ void __launch_bounds__(TPB) k_clear_touched(GridDev g, ScanBuffers b, u32 n) {
   pdl_enter();
@@ -1392,6 +1092,12 @@ Map::~Map() {
     cudaStreamSynchronize(copy_stream_);
     cudaStreamDestroy(copy_stream_);
   }
+  if (pre_stream_) {
+    cudaStreamSynchronize(pre_stream_);
+    cudaStreamDestroy(pre_stream_);
+  }
+  for (auto& st : sets_)
+    if (st.classified) cudaEventDestroy(st.classified);
   for (int k = 0; k < 2; ++k) {
     if (ev_copied_[k]) cudaEventDestroy(ev_copied_[k]);
     if (ev_consumed_[k]) cudaEventDestroy(ev_consumed_[k]);
@@ -1411,7 +1117,7 @@ static i32 logods_host(float prob) {  // probabilistic_map.hpp:34-36
   return (i32)(1e6 * std::log(prob / (1.0 - prob)));
 }
 
-constexpr size_t SC_BYTES = 256;  // ScanCounters header of b_table_
+constexpr size_t SC_BYTES = 256;  // ScanCounters header of a set's table buffer
 static_assert(sizeof(ScanCounters) <= SC_BYTES, "ScanCounters must fit its header");
 
 static u64 table_slots(i64 n) {
@@ -1435,6 +1141,8 @@ int Map::init(double resolution) {
   std::memset(h_ring_, 0xFF, sizeof(AsyncRecord) * RING);
   BNX_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_ring_), h_ring_, 0));
   BNX_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+  BNX_CUDA(cudaStreamCreateWithFlags(&pre_stream_, cudaStreamNonBlocking));
+  for (auto& st : sets_) BNX_CUDA(cudaEventCreateWithFlags(&st.classified, cudaEventDisableTiming));
   for (int k = 0; k < 2; ++k) {
     BNX_CUDA(cudaEventCreateWithFlags(&ev_copied_[k], cudaEventDisableTiming));
     BNX_CUDA(cudaEventCreateWithFlags(&ev_consumed_[k], cudaEventDisableTiming));
@@ -1444,32 +1152,35 @@ int Map::init(double resolution) {
   return reserve_scan(0, 16, 1.0);
 }
 
+// 32-chunk tiles of a scan: estimated from the longest possible ray, grown on overflow
+size_t Map::tile_bytes(size_t np, double max_range) const {
+  double cells = std::isfinite(max_range) ? std::ceil(max_range * grid.inv_resolution) + 2.0 : 512.0;
+  cells = std::min(cells, 4096.0);
+  return ((size_t)((double)np * (cells / CHUNK + 2.0) / 32.0) + np / 32 + 64) * 4;
+}
+
 int Map::reserve_scan(i64 n, i64 stride_bytes, double max_range, i64 table_n) {
   (void)stride_bytes;
   const size_t np = (size_t)n + n_pending_ + 32;
-  BNX_TRY(b_ep_.reserve(np * sizeof(int4)));
-  BNX_TRY(b_slot_.reserve(np * 4));
+  BNX_TRY(S().ep.reserve(np * sizeof(int4)));
+  BNX_TRY(S().slot.reserve(np * 4));
   BNX_TRY(b_rays_.reserve(np * sizeof(int4)));
   // [ScanCounters | table u32[slots] | keys u64[slots]] — contiguous so that one memset clears all of it
   const u64 slots = table_slots(table_n >= 0 ? table_n : n);
-  const void* table_before = b_table_.p;
-  BNX_TRY(b_table_.reserve(SC_BYTES + slots * 12));
-  if (b_table_.p != table_before) {  // fresh allocation: nothing is known to be zero
-    clean_slots_ = 0;
-    sc_clean_ = t1_clean_ = false;
+  const void* table_before = S().table.p;
+  BNX_TRY(S().table.reserve(SC_BYTES + slots * 12));
+  if (S().table.p != table_before) {  // fresh allocation: nothing is known to be zero
+    S().clean_slots = 0;
+    S().sc_clean = S().t1_clean = false;
   }
-  // 32-chunk tiles: estimated from the longest possible ray, grown on overflow
-  double cells = std::isfinite(max_range) ? std::ceil(max_range * grid.inv_resolution) + 2.0 : 512.0;
-  cells = std::min(cells, 4096.0);
-  const size_t tiles = (size_t)((double)np * (cells / CHUNK + 2.0) / 32.0) + np / 32 + 64;
-  BNX_TRY(b_tiles_.reserve(tiles * 4));
+  BNX_TRY(b_tiles_.reserve(tile_bytes(np, max_range)));
   BNX_TRY(b_touched_.reserve((size_t)grid.dev().leaf_cap * 4));
-  d_sc_ = b_table_.as<ScanCounters>();
+  d_sc_ = S().table.as<ScanCounters>();
   buf_.sc = d_sc_;
-  buf_.table = reinterpret_cast<u32*>(b_table_.as<unsigned char>() + SC_BYTES);
-  buf_.keys = reinterpret_cast<unsigned long long*>(b_table_.as<unsigned char>() + SC_BYTES + slots * 4);
-  buf_.ep = b_ep_.as<int4>();
-  buf_.slot_of = b_slot_.as<u32>();
+  buf_.table = reinterpret_cast<u32*>(S().table.as<unsigned char>() + SC_BYTES);
+  buf_.keys = reinterpret_cast<unsigned long long*>(S().table.as<unsigned char>() + SC_BYTES + slots * 4);
+  buf_.ep = S().ep.as<int4>();
+  buf_.slot_of = S().slot.as<u32>();
   buf_.rays = b_rays_.as<int4>();
   buf_.tile_first = b_tiles_.as<u32>();
   buf_.touched = b_touched_.as<u32>();
@@ -1529,6 +1240,7 @@ static int check_insert_args(const void* points, i64 stride_bytes, i64 n, bool f
 int Map::insert(const void* points, i64 stride_bytes, i64 n, bool f64, const double origin[3], double max_range, int where) {
   BNX_TRY(check_insert_args(points, stride_bytes, n, f64, origin, n_pending_));
   BNX_TRY(drain());
+  set_ = 0;
   cudaStream_t s = grid.stream();
   if (profiling) cudaEventRecord(ev_[0], s);
   BNX_TRY(reserve_scan(n, stride_bytes, max_range));
@@ -1554,11 +1266,42 @@ static void launch_classify(bool packed, int blocks, cudaStream_t s, const unsig
   }
 }
 
-// the kernel sequence of ONE attempt at a scan (no synchronisation)
-int Map::launch_scan(const void* d_points, i64 stride_bytes, bool f64, ScanParams& p, bool first_attempt) {
-  cudaStream_t s = grid.stream();
+int Map::launch_front(cudaStream_t s, const void* d_points, i64 stride_bytes, bool f64, ScanParams& p) {
   const i64 n = p.n;
   const u64 slots = (u64)p.hash_mask + 1;
+  const int persistent = sm_count() * 8;
+  buf_.poison = &grid.dev().ctr->error;
+  buf_.ring = d_ring_;
+  S().sc_clean = S().t1_clean = false;
+  // counters + dedupe table (+ packed keys) in one clear
+  const size_t bytes = n > 0 ? SC_BYTES + slots * (p.packed ? 12 : 4) : SC_BYTES;
+  if (p.async_id == NONE) {
+    BNX_CUDA(cudaMemsetAsync(d_sc_, 0, bytes, s));
+    S().clean_slots = 0;  // the synchronous path leaves a used table behind
+  } else {
+    if (slots > S().clean_slots) {
+      launch_scan_kernel(k_begin_scan, std::min<int>(persistent, blocks_for((i64)(bytes / 16))), TPB, s, buf_, reinterpret_cast<uint4*>(d_sc_), (u32)(bytes / 16));
+    }
+    p.clean16 = (u32)(slots * 12 / 16);  // k_mark zeroes table + keys again, the epilogue the counters
+    S().clean_slots = slots;
+  }
+  if (n > 0) {
+    const unsigned char* pts = static_cast<const unsigned char*>(d_points);
+    const int blocks = blocks_for(n);
+    if (f64) {
+      launch_classify<true, false>(p.packed, blocks, s, pts, (u32)stride_bytes, p, buf_);
+    } else if (stride_bytes == 16 && (reinterpret_cast<uintptr_t>(pts) & 15u) == 0) {
+      launch_classify<false, true>(p.packed, blocks, s, pts, 16u, p, buf_);
+    } else {
+      launch_classify<false, false>(p.packed, blocks, s, pts, (u32)stride_bytes, p, buf_);
+    }
+  }
+  BNX_CUDA(cudaGetLastError());
+  return BNX_OK;
+}
+
+int Map::launch_back(cudaStream_t s, ScanParams& p, bool first_attempt) {
+  const i64 n = p.n;
   const int persistent = sm_count() * 8;
   const GridDev g = grid.dev();
   buf_.poison = &g.ctr->error;
@@ -1566,49 +1309,28 @@ int Map::launch_scan(const void* d_points, i64 stride_bytes, bool f64, ScanParam
   p.seq = ++seq_;
   p.tile_cap = (u32)std::min<size_t>(b_tiles_.bytes / 4, 0xFFFFFFFFull);
   p.touched_cap = (u32)std::min<size_t>(b_touched_.bytes / 4, 0xFFFFFFFFull);
-  sc_clean_ = t1_clean_ = false;
-  if (first_attempt) {
-    if (profiling) cudaEventRecord(ev_[1], s);
-    // counters + dedupe table (+ packed keys) in one clear
-    const size_t bytes = n > 0 ? SC_BYTES + slots * (p.packed ? 12 : 4) : SC_BYTES;
-    if (p.async_id == NONE) {
-      BNX_CUDA(cudaMemsetAsync(d_sc_, 0, bytes, s));
-      clean_slots_ = 0;  // the synchronous path leaves a used table behind
-    } else {
-      if (slots > clean_slots_) {
-        launch_scan_kernel(k_begin_scan, std::min<int>(persistent, blocks_for((i64)(bytes / 16))), TPB, s, buf_, reinterpret_cast<uint4*>(d_sc_), (u32)(bytes / 16));
-      }
-      p.clean16 = (u32)(slots * 12 / 16);  // k_mark zeroes table + keys again, the epilogue the counters
-      clean_slots_ = slots;
-    }
-    if (n > 0) {
-      const unsigned char* pts = static_cast<const unsigned char*>(d_points);
-      const int blocks = blocks_for(n);
-      if (f64) {
-        launch_classify<true, false>(p.packed, blocks, s, pts, (u32)stride_bytes, p, buf_);
-      } else if (stride_bytes == 16 && (reinterpret_cast<uintptr_t>(pts) & 15u) == 0) {
-        launch_classify<false, true>(p.packed, blocks, s, pts, 16u, p, buf_);
-      } else {
-        launch_classify<false, false>(p.packed, blocks, s, pts, (u32)stride_bytes, p, buf_);
-      }
-    }
-    if (profiling) cudaEventRecord(ev_[2], s);
-  } else {
-    BNX_CUDA(cudaMemsetAsync(d_sc_, 0, SC_BYTES, s));
-  }
   if (n_pending_) launch_scan_kernel(k_resolve<1>, blocks_for(n_pending_), TPB, s, g, p, buf_, n_pending_);
   if (n > 0) launch_scan_kernel(k_resolve<0>, blocks_for(n), TPB, s, g, p, buf_, (u32)n);
   if (profiling && first_attempt) cudaEventRecord(ev_[3], s);
-  if (p.packed && !direct_mark()) {
-    launch_scan_kernel(k_mark_staged<false>, sm_count() * MARK_STAGED_MIN_BLOCKS, TPB, s, g, g, p, buf_);
-  } else {
-    launch_scan_kernel(k_mark<false>, persistent, TPB, s, g, g, p, buf_);
-  }
+  launch_scan_kernel(k_mark<false>, persistent, TPB, s, g, g, p, buf_);
   if (profiling && first_attempt) cudaEventRecord(ev_[4], s);
   launch_scan_kernel(k_apply_leaves, persistent, TPB, s, g, p, buf_);
   BNX_CUDA(cudaGetLastError());
   if (profiling && first_attempt) cudaEventRecord(ev_[5], s);
   return BNX_OK;
+}
+
+// the kernel sequence of ONE attempt at a scan on the map's stream (no synchronisation)
+int Map::launch_scan(const void* d_points, i64 stride_bytes, bool f64, ScanParams& p, bool first_attempt) {
+  cudaStream_t s = grid.stream();
+  if (first_attempt) {
+    if (profiling) cudaEventRecord(ev_[1], s);
+    BNX_TRY(launch_front(s, d_points, stride_bytes, f64, p));
+    if (profiling) cudaEventRecord(ev_[2], s);
+  } else {
+    BNX_CUDA(cudaMemsetAsync(d_sc_, 0, SC_BYTES, s));
+  }
+  return launch_back(s, p, first_attempt);
 }
 
 void Map::account(const ScanCounters& st, i64 n, i64 pending, i64 retries) {
@@ -1684,21 +1406,38 @@ int Map::insert_async(const void* points, i64 stride_bytes, i64 n, bool f64, con
   if (n_pending_ || world_ > 1) return insert(points, stride_bytes, n, f64, origin, max_range, where);  // rare paths stay synchronous
   cudaStream_t s = grid.stream();
   if (queue_.size() >= RING / 2) BNX_TRY(drain());
-  // Flow control without a CUDA sync: at most MAX_IN_FLIGHT scans are queued ahead of the newest record the device
-  // has published in the host ring; that bounds how stale the pool head-room information below can be.
-  if (queue_.size() > done_upto_ + MAX_IN_FLIGHT) {
-    const u32 wait_id = queue_[queue_.size() - 1 - MAX_IN_FLIGHT].p.async_id;
+  // how many scratch sets (= scans in flight + 2) does this scan size allow? (2 GiB of scratch at most)
+  {
+    const size_t np = (size_t)n + 32;
+    const size_t set_bytes = np * 20 + SC_BYTES + table_slots(n) * 12 + (where == BNX_HOST ? (size_t)n * stride_bytes : 0);
+    const int want = (int)std::min<size_t>(SETS, std::max<size_t>(4, (2ull << 30) / std::max<size_t>(set_bytes, 1)));
+    if (want != sets_active_) {
+      BNX_TRY(drain());  // the id -> set mapping changes: nothing may be in flight
+      sets_active_ = want;
+    }
+  }
+  const size_t max_in_flight = (size_t)sets_active_ - 2;
+  // Flow control without a CUDA sync: at most max_in_flight scans are queued ahead of the newest record the device
+  // has published in the host ring; that bounds how stale the pool head-room information below can be, and it makes
+  // the scratch set of scan (id - sets_active_) free when scan id is enqueued.
+  if (queue_.size() > done_upto_ + max_in_flight) {
+    const u32 wait_id = queue_[queue_.size() - 1 - max_in_flight].p.async_id;
     const volatile AsyncRecord* r = &h_ring_[wait_id & (RING - 1)];
     unsigned spins = 0;
+    bool seen = true;
     while (r->id != wait_id) {
       if (++spins > (1u << 14)) {  // never spin on a wedged device: fall back to a real synchronisation
-        if (cudaStreamQuery(s) != cudaErrorNotReady) break;
+        if (cudaStreamQuery(s) != cudaErrorNotReady) {
+          seen = r->id == wait_id;
+          break;
+        }
         spins = 0;
       }
 #if defined(__x86_64__)
       __builtin_ia32_pause();
 #endif
     }
+    if (!seen) BNX_TRY(drain());  // the stream is idle but the record never came (a frozen or failed pipeline)
   }
   // head-room check on the newest published record: grow early, so that a queued scan (almost) never runs short
   if (!queue_.empty()) {
@@ -1718,41 +1457,50 @@ int Map::insert_async(const void* points, i64 stride_bytes, i64 n, bool f64, con
       break;
     }
   }
-  // scratch must not be reallocated under scans in flight
-  const size_t np = (size_t)n + 32;
-  const bool fits = np * sizeof(int4) <= b_ep_.bytes && SC_BYTES + table_slots(n) * 12 <= b_table_.bytes &&
-                    (size_t)grid.dev().leaf_cap * 4 <= b_touched_.bytes;
-  if (!fits) BNX_TRY(drain());
-  BNX_TRY(reserve_scan(n, stride_bytes, max_range));
+  // buffers shared by all scans in flight (stream-ordered use) must not be reallocated under them
+  if ((size_t)grid.dev().leaf_cap * 4 > b_touched_.bytes || ((size_t)n + 32) * sizeof(int4) > b_rays_.bytes ||
+      tile_bytes((size_t)n + 32, max_range) > b_tiles_.bytes) {
+    BNX_TRY(drain());
+  }
+  // all scratch sets are sized together, up front: an allocation in the middle of the pipeline would synchronise the device
+  if (n > sets_n_ || (where == BNX_HOST && (size_t)n * stride_bytes > sets_stage_bytes_)) {
+    BNX_TRY(drain());
+    sets_n_ = std::max<i64>(sets_n_, n + n / 8);
+    if (where == BNX_HOST) sets_stage_bytes_ = std::max<size_t>(sets_stage_bytes_, (size_t)(n + n / 8) * stride_bytes);
+    const int keep = set_;
+    for (set_ = 0; set_ < sets_active_; ++set_) {
+      BNX_TRY(reserve_scan(sets_n_, stride_bytes, max_range));
+      if (sets_stage_bytes_) BNX_TRY(S().stage.reserve(sets_stage_bytes_));
+    }
+    set_ = keep;
+  }
   Queued q;
+  q.p.async_id = async_next_;
+  set_ = (int)(async_next_ % (u32)sets_active_);  // free: its previous scan (id - sets_active_) has published its record
+  ++async_next_;
+  const u32 my_id = q.p.async_id;
+  BNX_TRY(reserve_scan(n, stride_bytes, max_range));
   BNX_TRY(build_params(n, origin, max_range, &q.p));
-  q.p.async_id = async_next_++;
+  q.p.async_id = my_id;
   q.points = points;
   q.stride = stride_bytes;
   q.f64 = f64;
   q.where = where;
+  // front half on the pre-stream, any number of scans ahead of the map updates: H2D copy (host input) + classify.
+  // It only touches this scan's scratch set, never the map.
   const void* d_points = points;
   if (where == BNX_HOST && n > 0) {
-    // double-buffered staging on a copy stream: the copy of scan k+1 overlaps the kernels of scan k
-    const int slot = (int)(q.p.async_id & 1u);
-    if ((size_t)n * stride_bytes > b_stage_[slot].bytes) {
-      BNX_TRY(drain());
-      BNX_TRY(b_stage_[slot].reserve((size_t)n * stride_bytes));
-    }
-    if (stage_used_[slot]) BNX_CUDA(cudaStreamWaitEvent(copy_stream_, ev_consumed_[slot], 0));
-    BNX_CUDA(cudaMemcpyAsync(b_stage_[slot].p, points, (size_t)n * stride_bytes, cudaMemcpyHostToDevice, copy_stream_));
-    BNX_CUDA(cudaEventRecord(ev_copied_[slot], copy_stream_));
-    BNX_CUDA(cudaStreamWaitEvent(s, ev_copied_[slot], 0));
-    d_points = b_stage_[slot].p;
+    BNX_TRY(S().stage.reserve((size_t)n * stride_bytes));
+    BNX_CUDA(cudaMemcpyAsync(S().stage.p, points, (size_t)n * stride_bytes, cudaMemcpyHostToDevice, pre_stream_));
+    d_points = S().stage.p;
   }
   {
     PdlScope pdl(true);
-    BNX_TRY(launch_scan(d_points, stride_bytes, f64, q.p, true));
-  }
-  if (where == BNX_HOST && n > 0) {
-    const int slot = (int)(q.p.async_id & 1u);
-    BNX_CUDA(cudaEventRecord(ev_consumed_[slot], s));
-    stage_used_[slot] = true;
+    BNX_TRY(launch_front(pre_stream_, d_points, stride_bytes, f64, q.p));
+    BNX_CUDA(cudaEventRecord(S().classified, pre_stream_));
+    // back half on the map's stream: resolve -> mark -> apply, one scan after the other
+    BNX_CUDA(cudaStreamWaitEvent(s, S().classified, 0));
+    BNX_TRY(launch_back(s, q.p, true));
   }
   queue_.push_back(q);
   if (++update_count == 4) update_count = 1;
@@ -1763,12 +1511,23 @@ int Map::drain() {
   if (!squeue_.empty()) return shard_drain();
   if (queue_.empty()) return BNX_OK;
   cudaStream_t s = grid.stream();
-  BNX_CUDA(cudaMemcpyAsync(h_status_, d_sc_, sizeof(ScanCounters), cudaMemcpyDeviceToHost, s));
   GridCounters gc;
-  BNX_TRY(grid.read_counters(&gc));  // synchronises the stream
+  BNX_TRY(grid.read_counters(&gc));  // synchronises the map's stream
+  BNX_CUDA(cudaStreamSynchronize(pre_stream_));
   std::vector<Queued> q;
   q.swap(queue_);
   done_upto_ = 0;
+  if (gc.error) {
+    // the counters of the scan that failed are still in ITS scratch set; the front halves that ran ahead of the freeze
+    // left used tables behind, so no set is known to be clean any more
+    set_ = (int)(gc.failed_id % (u32)sets_active_);
+    BNX_CUDA(cudaMemcpyAsync(h_status_, sets_[set_].table.p, sizeof(ScanCounters), cudaMemcpyDeviceToHost, s));
+    BNX_CUDA(cudaStreamSynchronize(s));
+    for (auto& st : sets_) {
+      st.clean_slots = 0;
+      st.sc_clean = st.t1_clean = false;
+    }
+  }
   size_t done = q.size();
   if (gc.error) {
     // frozen at the first scan that ran short: everything before it is applied, nothing after it is
@@ -1804,6 +1563,7 @@ int Map::drain() {
     BNX_TRY(b_tiles_.reserve((size_t)(chunks / 32 + 64) * 4));
     buf_.tile_first = b_tiles_.as<u32>();
   }
+  set_ = 0;
   for (size_t k = done; k < q.size(); ++k) {
     const Queued& e = q[k];
     BNX_TRY(reserve_scan(e.p.n, e.stride, e.p.max_range));
@@ -1863,6 +1623,7 @@ int Map::shard_begin(const void* points, i64 stride_bytes, i64 n, bool f64, u32 
   BNX_REQUIRE(origin && cap_records >= 2, "shard_begin: null argument");
   BNX_REQUIRE(f64 ? (stride_bytes >= 24 && stride_bytes % 8 == 0) : (stride_bytes >= 12 && stride_bytes % 4 == 0), "shard_begin: bad stride");
   if (!queue_.empty()) BNX_TRY(drain());  // single-GPU pipeline first; the sharded queue is drained collectively
+  set_ = 0;
   cudaStream_t s = grid.stream();
   scratch_->set_stream(s);
   const i64 slots = (i64)world_ * cap_records;
@@ -1937,9 +1698,9 @@ int Map::shard_begin(const void* points, i64 stride_bytes, i64 n, bool f64, u32 
   } else {
     buf_.my_flags = reinterpret_cast<const u32*>(mbox_);
   }
-  if (!(lean && sc_clean_ && t1_clean_)) BNX_CUDA(cudaMemsetAsync(d_sc_, 0, SC_BYTES + tslots * 12, s));
-  sc_clean_ = t1_clean_ = lean;  // pipelined: the apply epilogue zeroes the counters, k_shard_dedupe this table
-  clean_slots_ = 0;
+  if (!(lean && S().sc_clean && S().t1_clean)) BNX_CUDA(cudaMemsetAsync(d_sc_, 0, SC_BYTES + tslots * 12, s));
+  S().sc_clean = S().t1_clean = lean;  // pipelined: the apply epilogue zeroes the counters, k_shard_dedupe this table
+  S().clean_slots = 0;
   const int blocks = blocks_for(n);
   if (n > 0) {
     const unsigned char* pts = static_cast<const unsigned char*>(d_points);
@@ -1995,7 +1756,7 @@ int Map::shard_resolve_mark(const void* recv_records, void* send_leaves, i64 cap
   const void* before = b_table2_.p;
   BNX_TRY(b_table2_.reserve(t2 * 12));
   if (b_table2_.p != before) t2_clean_ = false;
-  uint4* table1 = reinterpret_cast<uint4*>(b_table_.as<unsigned char>() + SC_BYTES);
+  uint4* table1 = reinterpret_cast<uint4*>(S().table.as<unsigned char>() + SC_BYTES);
   buf_.table = b_table2_.as<u32>();
   buf_.keys = reinterpret_cast<unsigned long long*>(b_table2_.as<unsigned char>() + t2 * 4);
   p.hash_mask = (u32)(t2 - 1);
@@ -2010,11 +1771,7 @@ int Map::shard_resolve_mark(const void* recv_records, void* send_leaves, i64 cap
   const int rblocks = blocks_for(std::min<i64>(slots, 2 * (i64)p.rec_cap));
   launch_scan_kernel(k_shard_dedupe, rblocks, TPB, s, p, buf_, slots, table1, lean ? (u32)(t1 * 12 / 16) : 0u);
   launch_scan_kernel(k_resolve<2>, rblocks, TPB, s, g, p, buf_, slots);
-  if (!direct_mark()) {  // sharded scans always have packed coordinates
-    launch_scan_kernel(k_mark_staged<true>, sm_count() * MARK_STAGED_MIN_BLOCKS, TPB, s, g, gs, p, buf_);
-  } else {
-    launch_scan_kernel(k_mark<true>, persistent, TPB, s, g, gs, p, buf_);
-  }
+  launch_scan_kernel(k_mark<true>, persistent, TPB, s, g, gs, p, buf_);
   launch_scan_kernel(k_shard_emit, persistent, TPB, s, gs, p, buf_);
   BNX_CUDA(cudaGetLastError());
   if (profiling) cudaEventRecord(ev_[2], s);
@@ -2349,7 +2106,7 @@ int Map::shard_drain() {
   GridCounters gc;
   BNX_TRY(grid.read_counters(&gc));  // synchronises the stream
   shard_phase_times();
-  if (gc.error) sc_clean_ = t1_clean_ = t2_clean_ = false;  // frozen kernels cleaned nothing
+  if (gc.error) S().sc_clean = S().t1_clean = t2_clean_ = false;  // frozen kernels cleaned nothing
   std::vector<ShardQueued> q;
   q.swap(squeue_);
   size_t done = q.size();

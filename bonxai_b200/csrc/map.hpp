@@ -148,10 +148,26 @@ class Map {
 
  private:
   int reserve_scan(i64 n, i64 stride_bytes, double max_range, i64 table_n = -1);
+  size_t tile_bytes(size_t np, double max_range) const;
   int run_scan(const void* d_points, i64 stride_bytes, bool f64, const ScanParams& base, bool reuse_classify);
 
   ScanBuffers buf_ = {};
-  DevBuf b_pts_, b_ep_, b_slot_, b_table_, b_rays_, b_tiles_, b_touched_, b_pending_, b_q_xyz_, b_q_out_;
+  DevBuf b_pts_, b_rays_, b_tiles_, b_touched_, b_pending_, b_q_xyz_, b_q_out_;
+  // Scratch written BEFORE a scan touches the map (classify: endpoints, their dedupe table, the counters) exists once
+  // per scan in flight: the pipelined insert classifies on its own stream, many scans ahead of the map updates.
+  struct ScratchSet {
+    DevBuf ep, slot, table, stage;  // table = [ScanCounters | table u32[slots] | keys u64[slots]]; stage = H2D staging
+    u64 clean_slots = 0;            // dedupe-table slots known to be zero (left clean by the set's previous scan)
+    bool sc_clean = false, t1_clean = false;
+    cudaEvent_t classified = nullptr;
+  };
+  static constexpr int SETS = 34;  // MAX_IN_FLIGHT + 2: the set of scan id - SETS is free when scan id is enqueued
+  ScratchSet sets_[SETS];
+  int set_ = 0, sets_active_ = SETS;
+  i64 sets_n_ = -1;              // points every active set is sized for (pipelined insert)
+  size_t sets_stage_bytes_ = 0;  // H2D staging bytes every active set holds
+  ScratchSet& S() { return sets_[set_]; }
+  cudaStream_t pre_stream_ = nullptr;  // H2D copy + classify of the pipelined insert
   ScanCounters* d_sc_ = nullptr;    // head of b_table_: counters + dedupe table are cleared by ONE memset
   ScanCounters* h_status_ = nullptr;  // pinned
   u32 n_pending_ = 0;
@@ -168,7 +184,7 @@ class Map {
   bool shard_async_ = false;  // the scan being enqueued is pipelined (set by shard_insert around the stages)
   u32 shard_async_id_ = 0, shard_attempt_ = 0;
   i64 shard_n_max_ = 0;
-  bool sc_clean_ = false, t1_clean_ = false, t2_clean_ = false;  // pipelined: counters / tables known to be zero
+  bool t2_clean_ = false;  // pipelined: receiver table known to be zero
   DevBuf b_table2_;  // receiver-side dedupe table of the sharded map
   void shard_phase_times();
   struct ShardQueued {
@@ -208,16 +224,16 @@ class Map {
   AsyncRecord* h_ring_ = nullptr;  // pinned + mapped
   AsyncRecord* d_ring_ = nullptr;
   u32 async_next_ = 0;
-  static constexpr size_t MAX_IN_FLIGHT = 32;  // scans queued ahead of the newest published record
   size_t done_upto_ = 0;                       // queue_ entries whose record has been seen
   u64 max_leaf_growth_ = 2048;                 // largest per-scan leaf allocation seen so far (head-room estimate)
-  u64 clean_slots_ = 0;  // dedupe-table slots known to be zero (left clean by the previous pipelined scan)
   cudaStream_t copy_stream_ = nullptr;
   cudaEvent_t ev_copied_[2] = {nullptr, nullptr}, ev_consumed_[2] = {nullptr, nullptr};
   bool stage_used_[2] = {false, false};
   DevBuf b_stage_[2];
   int build_params(i64 n, const double origin[3], double max_range, ScanParams* out);
   int launch_scan(const void* d_points, i64 stride_bytes, bool f64, ScanParams& p, bool first_attempt);
+  int launch_front(cudaStream_t s, const void* d_points, i64 stride_bytes, bool f64, ScanParams& p);  // clear + classify
+  int launch_back(cudaStream_t s, ScanParams& p, bool first_attempt);                                  // resolve, mark, apply
   void account(const ScanCounters& st, i64 n, i64 pending, i64 retries);
   DevBuf b_touched2_;
   u32 seq_ = 0;

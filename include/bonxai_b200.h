@@ -154,13 +154,18 @@ BNX_API int bnx_map_insert_f32(bnx_map_t* m, const void* points, int64_t stride_
                                const float origin[3], double max_range, int where);
 BNX_API int bnx_map_insert_f64(bnx_map_t* m, const void* points, int64_t stride_bytes, int64_t n,
                                const double origin[3], double max_range, int where);
-/* Pipelined insertPointCloud: same result as bnx_map_insert_*, but the call only ENQUEUES the scan on the map's
- * stream and returns; no host synchronisation per scan. The input buffer (device memory, or host memory —
- * pinned for a real overlap of the copy with the previous scan's kernels) must stay valid and unchanged until
- * bnx_map_sync() or any other call on the map returns; those complete the queue first. If a queued scan runs
- * out of pool space the device freezes the pipeline at that scan (later scans skip themselves), and the next
- * synchronising call grows the pools and replays from there: the map is always exactly what the synchronous
- * calls would have produced. */
+/* Pipelined insertPointCloud: same result as bnx_map_insert_*, but the call only ENQUEUES the scan and returns; no
+ * host synchronisation per scan. The scan is split in two: its FRONT half (host-to-device copy of a host buffer,
+ * classification, endpoint dedupe — nothing that touches the map) runs on an internal stream, up to 32 scans ahead of
+ * the map updates; its BACK half (resolve, mark, apply) runs on the map's stream, one scan after the other. So the
+ * copy and the classification of later scans overlap the map updates of earlier ones.
+ *   - the input buffer (device memory, or host memory — pinned for an asynchronous copy) must stay valid and
+ *     unchanged until bnx_map_sync() or any other call on the map returns; those complete the queue first;
+ *   - a BNX_DEVICE buffer is read on the internal stream: its contents must be COMPLETE when the call is made (the
+ *     synchronous bnx_map_insert_* reads on the map's stream instead, ordered after earlier work on that stream).
+ * If a queued scan runs out of pool space the device freezes the pipeline at that scan (later scans skip
+ * themselves), and the next synchronising call grows the pools and replays from there: the map is always exactly
+ * what the synchronous calls would have produced. */
 BNX_API int bnx_map_insert_async_f32(bnx_map_t* m, const void* points, int64_t stride_bytes, int64_t n,
                                      const float origin[3], double max_range, int where);
 BNX_API int bnx_map_insert_async_f64(bnx_map_t* m, const void* points, int64_t stride_bytes, int64_t n,
