@@ -607,8 +607,8 @@ int Grid::init(double voxel_size, int ib, int lb, int cbytes) {
   d.leaf = static_cast<unsigned char*>(leaf_arena_.base());
   d.inner = static_cast<u32*>(inner_arena_.base());
   BNX_TRY(grow_root_table(1ull << 14));
-  BNX_TRY(ensure_inner_capacity(env_mb("BNX_INIT_INNER_MB", 4) / (d.inner_stride * 4)));
-  BNX_TRY(ensure_leaf_capacity(env_mb("BNX_INIT_LEAF_MB", 128) / d.leaf_stride));
+  BNX_TRY(ensure_inner_capacity(env_mb("BNX_INIT_INNER_MB", 16) / (d.inner_stride * 4)));
+  BNX_TRY(ensure_leaf_capacity(env_mb("BNX_INIT_LEAF_MB", 512) / d.leaf_stride));
   return sync();
 }
 

@@ -736,7 +736,10 @@ __device__ __forceinline__ void read_gate(const ScanParams& p, const ScanBuffers
 // One warp per listed leaf: hit endpoints (addHitPoint, probabilistic_map.cpp:30-41) and the union of all rays + miss
 // endpoints (clearPoint / addMissPoint, :43-54,81-89). Hit endpoints are never stale (resolve filtered them) and win
 // over ray cells, like the reference where they are stamped before any ray is cast.
-__global__ void __launch_bounds__(TPB) k_apply_leaves(GridDev g, ScanParams p, ScanBuffers b) {
+#ifndef APPLY_MIN_BLOCKS
+#define APPLY_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(TPB, APPLY_MIN_BLOCKS) k_apply_leaves(GridDev g, ScanParams p, ScanBuffers b) {
   pdl_enter();
   // last kernel of the scan: the host reads counters + grid counters with one copy
   u32 gate_pool, gate_ovf;
@@ -751,60 +754,57 @@ __global__ void __launch_bounds__(TPB) k_apply_leaves(GridDev g, ScanParams p, S
   const u32 lane = threadIdx.x & 31;
   const u32 warps = gridDim.x * (TPB / 32);
   u32 changed = 0;
-  // the masks of the NEXT leaf of this warp are loaded while the current leaf's cells are in flight
+  // Kept at 32 registers so that all sm_count * 8 blocks are resident in ONE wave (64 warps per SM): the kernel is a chain
+  // of dependent loads per leaf (list entry -> masks -> cells), so what hides the latency is the number of leaves in
+  // flight, not work per thread. Only the list entry of the warp's next leaf is prefetched.
   u32 t = blockIdx.x * (TPB / 32) + (threadIdx.x >> 5);
   u32 leaf_n = t < n ? b.touched[t] : NONE;
-  unsigned long long tw_n = 0, aw_n = 0, hw_n = 0;
-  if (leaf_n != NONE && lane < 8) {
-    tw_n = reinterpret_cast<const unsigned long long*>(leaf_touched(g, leaf_n))[lane];
-    hw_n = reinterpret_cast<const unsigned long long*>(leaf_hit(g, leaf_n))[lane];
-    aw_n = reinterpret_cast<const unsigned long long*>(leaf_active(g, leaf_n))[lane];
-  }
   for (; t < n; t += warps) {
     const u32 leaf = leaf_n;
-    const unsigned long long tw = tw_n, aw = aw_n, hw = hw_n;
-    unsigned long long* touched = reinterpret_cast<unsigned long long*>(leaf_touched(g, leaf));
-    unsigned long long* hitm = reinterpret_cast<unsigned long long*>(leaf_hit(g, leaf));
-    unsigned long long* active = reinterpret_cast<unsigned long long*>(leaf_active(g, leaf));
-    u32* cells = reinterpret_cast<u32*>(leaf_cells(g, leaf));
     leaf_n = t + warps < n ? b.touched[t + warps] : NONE;
-    if (leaf_n != NONE && lane < 8) {
-      tw_n = reinterpret_cast<const unsigned long long*>(leaf_touched(g, leaf_n))[lane];
-      hw_n = reinterpret_cast<const unsigned long long*>(leaf_hit(g, leaf_n))[lane];
-      aw_n = reinterpret_cast<const unsigned long long*>(leaf_active(g, leaf_n))[lane];
+    unsigned char* lp = leaf_ptr(g, leaf);
+    // lane j < 16 holds 32-bit half j of the three masks = the bits of cell row j (cells 32 j .. 32 j + 31)
+    u32 th = 0, hh = 0, ah = 0;
+    if (lane < 16) {
+      th = reinterpret_cast<const u32*>(lp + g.off_touched)[lane];
+      hh = reinterpret_cast<const u32*>(lp + g.off_hit)[lane];
+      ah = reinterpret_cast<const u32*>(lp + g.off_active)[lane];
     }
-    // lane owns cells it*32 + lane, it = 0..15 (coalesced 128-B rows); bit `it` of mine/on = that cell touched/ON
+    // lane owns cells it*32 + lane, it = 0..15 (coalesced 128-B rows); bit `it` of mine/on/hit = that cell touched/ON/hit
     u32 mine = 0, on = 0, hit = 0;
 #pragma unroll
-    for (u32 w = 0; w < 8; ++w) {
-      const unsigned long long t64 = __shfl_sync(0xffffffffu, tw, w);
-      const unsigned long long a64 = __shfl_sync(0xffffffffu, aw, w);
-      const unsigned long long h64 = __shfl_sync(0xffffffffu, hw, w);
-      mine |= (u32)((t64 >> lane) & 1ull) << (2 * w) | (u32)((t64 >> (32 + lane)) & 1ull) << (2 * w + 1);
-      on |= (u32)((a64 >> lane) & 1ull) << (2 * w) | (u32)((a64 >> (32 + lane)) & 1ull) << (2 * w + 1);
-      hit |= (u32)((h64 >> lane) & 1ull) << (2 * w) | (u32)((h64 >> (32 + lane)) & 1ull) << (2 * w + 1);
+    for (u32 j = 0; j < 16; ++j) {
+      const u32 t32 = __shfl_sync(0xffffffffu, th, j), a32 = __shfl_sync(0xffffffffu, ah, j), h32 = __shfl_sync(0xffffffffu, hh, j);
+      mine |= ((t32 >> lane) & 1u) << j;
+      on |= ((a32 >> lane) & 1u) << j;
+      hit |= ((h32 >> lane) & 1u) << j;
     }
     mine |= hit;
-    // all loads of this leaf are issued before the first use (memory-level parallelism)
-    u32 word[16];
+    u32* cells = reinterpret_cast<u32*>(lp + g.off_cells);
 #pragma unroll
-    for (u32 it = 0; it < 16; ++it) word[it] = ((mine & on) >> it) & 1u ? cells[it * 32 + lane] : 0u;
+    for (u32 half = 0; half < 2; ++half) {
+      // the 8 loads of a half leaf are issued before the first use
+      u32 word[8];
 #pragma unroll
-    for (u32 it = 0; it < 16; ++it) {
-      if ((hit >> it) & 1u) {
-        const i32 prob = min(((i32)word[it] >> 4) + p.hit, p.cmax);
-        cells[it * 32 + lane] = ((u32)prob << 4) | p.c;
-        ++changed;
-      } else if (((mine >> it) & 1u) && (word[it] & 0xFu) != p.c) {
-        const i32 prob = max(((i32)word[it] >> 4) + p.miss, p.cmin);
-        cells[it * 32 + lane] = ((u32)prob << 4) | p.c;
-        ++changed;
+      for (u32 it = 0; it < 8; ++it) word[it] = ((mine & on) >> (half * 8 + it)) & 1u ? cells[(half * 8 + it) * 32 + lane] : 0u;
+#pragma unroll
+      for (u32 it = 0; it < 8; ++it) {
+        const u32 r = half * 8 + it;
+        if ((hit >> r) & 1u) {
+          const i32 prob = min(((i32)word[it] >> 4) + p.hit, p.cmax);
+          cells[r * 32 + lane] = ((u32)prob << 4) | p.c;
+          ++changed;
+        } else if (((mine >> r) & 1u) && (word[it] & 0xFu) != p.c) {
+          const i32 prob = max(((i32)word[it] >> 4) + p.miss, p.cmin);
+          cells[r * 32 + lane] = ((u32)prob << 4) | p.c;
+          ++changed;
+        }
       }
     }
-    if (lane < 8 && (tw | hw)) {
-      active[lane] = aw | tw | hw;
-      touched[lane] = 0ull;
-      hitm[lane] = 0ull;
+    if (lane < 16 && (th | hh)) {
+      reinterpret_cast<u32*>(lp + g.off_active)[lane] = ah | th | hh;
+      reinterpret_cast<u32*>(lp + g.off_touched)[lane] = 0u;
+      reinterpret_cast<u32*>(lp + g.off_hit)[lane] = 0u;
     }
   }
   for (int o = 16; o; o >>= 1) changed += __shfl_xor_sync(0xffffffffu, changed, o);
@@ -1314,7 +1314,7 @@ int Map::launch_back(cudaStream_t s, ScanParams& p, bool first_attempt) {
   if (profiling && first_attempt) cudaEventRecord(ev_[3], s);
   launch_scan_kernel(k_mark<false>, persistent, TPB, s, g, g, p, buf_);
   if (profiling && first_attempt) cudaEventRecord(ev_[4], s);
-  launch_scan_kernel(k_apply_leaves, persistent, TPB, s, g, p, buf_);
+  launch_scan_kernel(k_apply_leaves, sm_count() * APPLY_MIN_BLOCKS, TPB, s, g, p, buf_);
   BNX_CUDA(cudaGetLastError());
   if (profiling && first_attempt) cudaEventRecord(ev_[5], s);
   return BNX_OK;
@@ -1448,8 +1448,15 @@ int Map::insert_async(const void* points, i64 stride_bytes, i64 n, bool f64, con
       const GridDev g = grid.dev();
       const u64 ahead = queue_.size() - k;  // scans that may still allocate before we look again
       const u64 leaves_ahead = (u64)r.n_leaves + ahead * max_leaf_growth_, inner_ahead = (u64)r.n_inner + ahead * 64;
-      if (r.error || leaves_ahead * 2 > g.leaf_cap || inner_ahead * 2 > g.inner_cap || (u64)(r.n_roots + ahead * 64) * 2 > (u64)g.root_mask + 1) {
+      const u64 roots_ahead = (u64)r.n_roots + ahead * 64;
+      if (r.error || leaves_ahead * 2 > g.leaf_cap || inner_ahead * 2 > g.inner_cap || roots_ahead * 2 > (u64)g.root_mask + 1) {
         BNX_TRY(drain());
+        // grow for what the refilled pipeline may allocate before the next look, not only for what is in use now
+        // (otherwise the same check drains again and again without growing anything)
+        const u64 full = (u64)sets_active_ * max_leaf_growth_;
+        BNX_TRY(grid.ensure_leaf_capacity(((u64)r.n_leaves + full) * 4));
+        BNX_TRY(grid.ensure_inner_capacity(((u64)r.n_inner + (u64)sets_active_ * 64) * 4));
+        if (roots_ahead * 2 > (u64)g.root_mask + 1) BNX_TRY(grid.grow_root_table(((u64)g.root_mask + 1) * 4));
       } else if (k > 0) {
         const AsyncRecord& q = h_ring_[queue_[k - 1].p.async_id & (RING - 1)];
         if (q.id == queue_[k - 1].p.async_id && r.n_leaves > q.n_leaves) max_leaf_growth_ = std::max<u64>(max_leaf_growth_, r.n_leaves - q.n_leaves);
@@ -1804,7 +1811,7 @@ int Map::shard_finish(const void* flags_reduced, int* retry) {
   const int persistent = sm_count() * 8;
   const GridDev g = grid.dev();
   buf_.gate = static_cast<const u32*>(flags_reduced);
-  launch_scan_kernel(k_apply_leaves, persistent, TPB, s, g, sp_, buf_);
+  launch_scan_kernel(k_apply_leaves, sm_count() * APPLY_MIN_BLOCKS, TPB, s, g, sp_, buf_);
   BNX_CUDA(cudaGetLastError());
   if (profiling) cudaEventRecord(ev_[4], s);
   BNX_CUDA(cudaMemcpyAsync(h_status_, d_sc_, sizeof(ScanCounters), cudaMemcpyDeviceToHost, s));
@@ -2059,7 +2066,7 @@ int Map::shard_insert(const void* points, i64 stride_bytes, i64 n, bool f64, u32
     if (!p2p) BNX_NCCL(api, api.AllReduce(flags, flags, 4, ncclUint32, ncclMax, static_cast<ncclComm_t>(comm_), s));
     if (async) {
       buf_.gate = p2p ? reinterpret_cast<const u32*>(mbox_) + MBOX_FLAGS4 : flags;
-      launch_scan_kernel(k_apply_leaves, sm_count() * 8, TPB, s, grid.dev(), sp_, buf_);
+      launch_scan_kernel(k_apply_leaves, sm_count() * APPLY_MIN_BLOCKS, TPB, s, grid.dev(), sp_, buf_);
       BNX_CUDA(cudaGetLastError());
       if (profiling) cudaEventRecord(ev_[4], s);
       buf_.gate = nullptr;
