@@ -211,6 +211,11 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def settle():
+        # destroying a map unmaps ~1 GB of pools; let the driver finish that before the next timed run starts
+        torch.cuda.synchronize()
+        time.sleep(0.3)
+
     dev_scans = [torch.from_numpy(p).cuda() for p, _ in scans]  # distinct 2 MiB buffers: > L2 in total for K >= 64
 
     # ---------------- pass 1: synchronous C-ABI call per scan with per-phase CUDA events (kernel shares, counters) ----
@@ -268,6 +273,7 @@ def run_gpu(args):
         assert m.active_count() == active, "pipelined and synchronous passes disagree"
         tt = m.totals()
         del m
+        settle()
     clocks = sampler.stop()
     ms = min(value_runs)
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -292,6 +298,7 @@ def run_gpu(args):
     if world == 1:
         # the host side of this pass (a Python loop on a shared VM core) is noisy: repeat once on a fresh map, keep both
         del m2
+        settle()
         m2 = capi.ProbabilisticMap(RES)
         for i in range(W):
             m2.insert_async(pinned[i], scans[i][1], MAX_RANGE)

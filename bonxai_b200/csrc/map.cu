@@ -388,8 +388,8 @@ __global__ void __launch_bounds__(TPB) k_resolve(GridDev g, ScanParams p, ScanBu
       winner = true;
     } else {
       const u32 slot = b.slot_of[i];  // NONE: the point was dropped by the fused pre-step
+      e = b.ep[i];                    // unconditional (coalesced): in flight together with the table look-up
       winner = slot != NONE && b.table[slot] == (p.packed ? ~i : i + 1u);
-      if (winner) e = b.ep[i];
     }
   }
   if (!PENDING) {
@@ -409,8 +409,10 @@ __global__ void __launch_bounds__(TPB) k_resolve(GridDev g, ScanParams p, ScanBu
     if (!PENDING) {
       if (leaf != NONE) {
         ci = ((u32)e.x & 7u) | (((u32)e.y & 7u) << 3) | (((u32)e.z & 7u) << 6);
-        const bool on = (leaf_active(g, leaf)[ci >> 6] >> (ci & 63)) & 1ull;
-        const u32 word = on ? reinterpret_cast<const u32*>(leaf_cells(g, leaf))[ci] : 0u;
+        // mask word and cell are loaded together (one round trip); the cell only counts if its bit is on
+        const u64 act = leaf_active(g, leaf)[ci >> 6];
+        const u32 raw = reinterpret_cast<const u32*>(leaf_cells(g, leaf))[ci];
+        const u32 word = ((act >> (ci & 63)) & 1ull) ? raw : 0u;
         stale = (word & 0xFu) == p.c;  // probabilistic_map.cpp:34 / :47 — skipped AND no ray is cast
       } else {
         stale = true;  // pool exhausted: the scan will be repeated
@@ -460,7 +462,14 @@ __global__ void __launch_bounds__(TPB) k_resolve(GridDev g, ScanParams p, ScanBu
     // the leaf's HIT mask; a miss endpoint gets exactly the update of a ray cell (max(p + miss, clamp_min), stamp), so
     // it simply joins the touched mask. Either way the leaf is listed for the apply pass.
     unsigned long long* word = reinterpret_cast<unsigned long long*>(e.w ? leaf_touched(g, leaf) : leaf_hit(g, leaf)) + (ci >> 6);
-    mark_bits(g, leaf, word, 1ull << (ci & 63), p.seq, &b.sc->n_touched, b.touched, p.touched_cap);
+    atomicOr(word, 1ull << (ci & 63));  // result unused. Resolve runs before any ray is marked: nearly every endpoint leaf
+    // is touched here for the first time in this scan, so ONE lane per distinct leaf of the warp installs the stamp and
+    // lists the leaf (the words themselves need no test and no return value).
+    const u32 grp = __match_any_sync(eballot, leaf);
+    if ((int)lane == __ffs(grp) - 1 && atomicExch(leaf_stamp(g, leaf), p.seq) != p.seq) {
+      const u32 at = atomicAdd(&b.sc->n_touched, 1u);
+      if (at < p.touched_cap) b.touched[at] = leaf;
+    }
   }
   if (mine) {
     const unsigned long long at = s_base + s_warp[warp] + (incl - mine);
