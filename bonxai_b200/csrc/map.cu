@@ -1107,10 +1107,8 @@ Map::~Map() {
   }
   for (auto& st : sets_)
     if (st.classified) cudaEventDestroy(st.classified);
-  for (int k = 0; k < 2; ++k) {
-    if (ev_copied_[k]) cudaEventDestroy(ev_copied_[k]);
-    if (ev_consumed_[k]) cudaEventDestroy(ev_consumed_[k]);
-  }
+  for (auto& e : x_copied_)
+    if (e) cudaEventDestroy(e);
   if (h_ring_) cudaFreeHost(h_ring_);
   p2p_close_peers();
   if (mbox_) cudaFree(mbox_);
@@ -1152,10 +1150,7 @@ int Map::init(double resolution) {
   BNX_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
   BNX_CUDA(cudaStreamCreateWithFlags(&pre_stream_, cudaStreamNonBlocking));
   for (auto& st : sets_) BNX_CUDA(cudaEventCreateWithFlags(&st.classified, cudaEventDisableTiming));
-  for (int k = 0; k < 2; ++k) {
-    BNX_CUDA(cudaEventCreateWithFlags(&ev_copied_[k], cudaEventDisableTiming));
-    BNX_CUDA(cudaEventCreateWithFlags(&ev_consumed_[k], cudaEventDisableTiming));
-  }
+  for (auto& e : x_copied_) BNX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   buf_.poison = &grid.dev().ctr->error;
   buf_.ring = d_ring_;
   return reserve_scan(0, 16, 1.0);
@@ -1650,20 +1645,28 @@ int Map::shard_begin(const void* points, i64 stride_bytes, i64 n, bool f64, u32 
   int stage_slot = -1;
   if (where == BNX_HOST && n > 0) {
     if (lean) {
-      // double-buffered staging on a copy stream: the copy of scan k+1 overlaps the kernels of scan k. Sized from
-      // n_max, which is the same on every rank (growing it drains, and draining a sharded map is collective).
-      stage_slot = (int)(shard_async_id_ & 1u);
+      // staging ring on a copy stream: at most SHARD_QUEUE scans are in flight between two (collective) drains, so
+      // slot id mod (SHARD_QUEUE + 2) is free when scan id is enqueued and the copy needs no dependency at all: it runs
+      // as early as the host enqueues it. Sized from n_max, which is the same on every rank (growing it drains).
+      stage_slot = (int)(shard_async_id_ % (u32)SHARD_STAGES);
       const size_t need = (size_t)std::max<i64>(n, shard_n_max_) * stride_bytes;
-      if (need > b_stage_[stage_slot].bytes) {
+      if (need > x_stage_bytes_) {
+        // draining may replay queued scans through nested (synchronous) shard_insert calls: keep this call's state
+        const u32 keep_id = shard_async_id_;
+        const i64 keep_n_max = shard_n_max_;
         BNX_TRY(drain());
-        BNX_TRY(b_stage_[stage_slot].reserve(need));
-        stage_used_[stage_slot] = false;
+        shard_async_ = true;
+        shard_async_id_ = keep_id;
+        shard_n_max_ = keep_n_max;
+        staged_p2p_ = send_records == nullptr;
+        BNX_TRY(reserve_scan(std::max<i64>(n, slots), stride_bytes, max_range, cap_records));  // buf_ points at the sender-side table again
+        for (auto& st : x_stage_) BNX_TRY(st.reserve(need));
+        x_stage_bytes_ = x_stage_[0].bytes;
       }
-      if (stage_used_[stage_slot]) BNX_CUDA(cudaStreamWaitEvent(copy_stream_, ev_consumed_[stage_slot], 0));
-      BNX_CUDA(cudaMemcpyAsync(b_stage_[stage_slot].p, points, (size_t)n * stride_bytes, cudaMemcpyHostToDevice, copy_stream_));
-      BNX_CUDA(cudaEventRecord(ev_copied_[stage_slot], copy_stream_));
-      BNX_CUDA(cudaStreamWaitEvent(s, ev_copied_[stage_slot], 0));
-      d_points = b_stage_[stage_slot].p;
+      BNX_CUDA(cudaMemcpyAsync(x_stage_[stage_slot].p, points, (size_t)n * stride_bytes, cudaMemcpyHostToDevice, copy_stream_));
+      BNX_CUDA(cudaEventRecord(x_copied_[stage_slot], copy_stream_));
+      BNX_CUDA(cudaStreamWaitEvent(s, x_copied_[stage_slot], 0));
+      d_points = x_stage_[stage_slot].p;
     } else {
       BNX_TRY(b_pts_.reserve((size_t)n * stride_bytes));
       BNX_CUDA(cudaMemcpyAsync(b_pts_.p, points, (size_t)n * stride_bytes, cudaMemcpyHostToDevice, s));
@@ -1726,10 +1729,6 @@ int Map::shard_begin(const void* points, i64 stride_bytes, i64 n, bool f64, u32 
       launch_classify<false, true>(true, blocks, s, pts, 16u, p, buf_);
     } else {
       launch_classify<false, false>(true, blocks, s, pts, (u32)stride_bytes, p, buf_);
-    }
-    if (stage_slot >= 0) {
-      BNX_CUDA(cudaEventRecord(ev_consumed_[stage_slot], s));  // classify is the only reader of the points
-      stage_used_[stage_slot] = true;
     }
   }
   // always launched: its last block writes the block headers (counts) and, with mailboxes, the arrival stamps
@@ -2035,7 +2034,7 @@ int Map::shard_insert(const void* points, i64 stride_bytes, i64 n, bool f64, u32
   const NcclApi& api = nccl_api(nullptr);
   cudaStream_t s = grid.stream();
   if (!async) BNX_TRY(drain());
-  if (async && squeue_.size() >= 64) BNX_TRY(drain());  // same count on every rank: draining stays collective
+  if (async && squeue_.size() >= SHARD_QUEUE) BNX_TRY(drain());  // same count on every rank: draining stays collective
   // equal-split exchange buffers (all ranks compute the same capacities from n_max)
   const i64 want_rec = std::max<i64>(cap_rec_, n_max + 2);
   if (want_p2p_) {

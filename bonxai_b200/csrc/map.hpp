@@ -227,9 +227,12 @@ class Map {
   size_t done_upto_ = 0;                       // queue_ entries whose record has been seen
   u64 max_leaf_growth_ = 2048;                 // largest per-scan leaf allocation seen so far (head-room estimate)
   cudaStream_t copy_stream_ = nullptr;
-  cudaEvent_t ev_copied_[2] = {nullptr, nullptr}, ev_consumed_[2] = {nullptr, nullptr};
-  bool stage_used_[2] = {false, false};
-  DevBuf b_stage_[2];
+  // sharded pipelined insert with host input: H2D staging ring on the copy stream
+  static constexpr size_t SHARD_QUEUE = 64;               // scans between two collective drains
+  static constexpr int SHARD_STAGES = (int)SHARD_QUEUE + 2;
+  DevBuf x_stage_[SHARD_STAGES];
+  cudaEvent_t x_copied_[SHARD_STAGES] = {};
+  size_t x_stage_bytes_ = 0;
   int build_params(i64 n, const double origin[3], double max_range, ScanParams* out);
   int launch_scan(const void* d_points, i64 stride_bytes, bool f64, ScanParams& p, bool first_attempt);
   int launch_front(cudaStream_t s, const void* d_points, i64 stride_bytes, bool f64, ScanParams& p);  // clear + classify

@@ -30,9 +30,14 @@ def main():
         parts = split_points(len(pts), world)
         lo, hi = parts[rank]
         n_max = max(h - l for l, h in parts)
-        dev = torch.from_numpy(pts[lo:hi]).cuda()
-        keep.append(dev)
-        sm.insert(capi.DevPtr(dev.data_ptr()), hi - lo, 16, lo, n_max, origin, 40.0, use_async=(mode == "async"))
+        if scan % 2 == 0:
+            dev = torch.from_numpy(pts[lo:hi]).cuda()
+            keep.append(dev)
+            sm.insert(capi.DevPtr(dev.data_ptr()), hi - lo, 16, lo, n_max, origin, 40.0, use_async=(mode == "async"))
+        else:  # host input: staged through the copy-stream ring when pipelined
+            host = np.ascontiguousarray(pts[lo:hi])
+            keep.append(host)
+            sm.insert(host, hi - lo, 16, lo, n_max, origin, 40.0, use_async=(mode == "async"))
         if mode == "async" and scan % 3 != 2:
             if rank == 0:
                 om.insert(pts, origin, 40.0)
