@@ -352,7 +352,7 @@ def run_gpu(args):
             "sync_call": {"ms_per_step": sync_ms / K, "points_per_s": K * N_PTS / (sync_ms * 1e-3),
                           "host_buffers_ms_per_step": 1e3 * e2e_sync_s / K, "host_buffers_points_per_s": K * N_PTS / e2e_sync_s,
                           "note": "one synchronous bnx_map_insert_f32 per scan (the drop-in C++ insertPointCloud); value/e2e use the pipelined call"},
-            "roofline": {"bound": "hbm", "kernel": {"classify": "k_classify", "resolve": "k_resolve", "mark": "k_mark", "apply": "k_apply_endpoints+k_apply_leaves"}[dom],
+            "roofline": {"bound": "hbm", "kernel": {"classify": "k_classify", "resolve": "k_resolve", "mark": "k_mark", "apply": "k_apply_leaves"}[dom],
                          "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(dom), "algorithmic_bytes_per_launch": alg_bytes, "kernel_us": dom_us,
                          "kernel_share_of_step": phases[dom] / max(phases["total"], 1e-9),

@@ -4,20 +4,23 @@
 //            bonxai_map/src/probabilistic_map.cpp:30-54,77-106 (addHitPoint, addMissPoint, updateFreeCells).
 //
 // The reference walks points, then rays, sequentially and lets the per-cell update_id decide who updates a
-// cell. The same result is produced here by five data-parallel phases:
+// cell. The same result is produced here by four data-parallel phases:
 //   1 classify   fp64 range clip + posToCoord per point; a scan-local hash finds, per endpoint voxel, the
 //                LOWEST point index (the point the reference would have processed first: it decides hit/miss)
 //   2 resolve    one thread per winning point: find-or-create the leaf, stale test (update_id == c against the
-//                PRE-scan state), emit an endpoint record and — if the voxel differs from the origin's — a ray
-//                with its range in the flat space of 8-cell ray chunks
+//                PRE-scan state), set the endpoint's bit in the leaf's per-scan HIT mask (hit) or touched mask (miss)
+//                and — if the voxel differs from the origin's — emit a ray with its range in the flat space of
+//                8-cell ray chunks
 //   3 mark       the flat chunk space is walked by all threads: exact integer DDA restarted from the closed form
-//                at cell k0 = 8*chunk, setting bits in a per-leaf 512-bit "touched" mask (test before atomicOr)
-//   4 endpoints  hit/miss update + stamp of the endpoint cells
-//   5 apply      one warp per touched leaf: every touched cell whose update_id != c gets the clamped miss
-//                update and the stamp; endpoint cells were stamped in 4 and are skipped exactly like the
-//                reference's clearPoint skips them.
+//                at the chunk's first cell, setting bits in a per-leaf 512-bit "touched" mask (test before atomicOr)
+//   4 apply      one warp per touched leaf: hit endpoints get the clamped hit update, every other touched cell whose
+//                update_id != c the clamped miss update; all get the stamp. Hits win over ray misses exactly like in
+//                the reference, where the endpoints are stamped before any ray is cast.
 // Phases 1-3 never change a cell value, so a scan that runs out of pool space is simply repeated after the
-// pools have grown; phases 4-5 cannot fail.
+// pools have grown; phase 4 cannot fail.
+// The pipelined insert runs phase 1 (and the H2D copy) on its own stream, scans ahead of phases 2-4; the sharded
+// map (one shard per GPU) adds the stages around the two record exchanges, which are peer-memory stores + arrival
+// stamps.
 #include "map.hpp"
 
 #include "nccl_dyn.hpp"

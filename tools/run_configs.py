@@ -36,7 +36,7 @@ def sweep(args):
     from workloads import digest
 
     port = oracle.load("port")
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()  # a real stream: the NULL stream serialises the programmatic dependent launches
     for log2n in range(20, args.max_log2 + 1, 2 if args.max_log2 > 24 else 4):
         n = 1 << log2n
         for pattern in ("coherent_x", "coherent_z", "random"):
@@ -120,7 +120,7 @@ def depth(args):
     port = oracle.load("port")
     scans = [synth.depth_scan(s) for s in range(args.scans)]
     dev = [torch.from_numpy(p).cuda() for p, _ in scans]
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()  # a real stream: the NULL stream serialises the programmatic dependent launches
     # parity: the first scans against the CPU oracle (about 5 s of CPU each)
     gm, om = capi.ProbabilisticMap(0.01), port.map(0.01)
     cpu_s, tot = [], dict(N=0, E=0, V=0, U=0)
@@ -172,7 +172,7 @@ def city(args):
     import oracle
     from workloads import digest
 
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()  # a real stream: the NULL stream serialises the programmatic dependent launches
     m = capi.ProbabilisticMap(0.1)
     m.set_stream(stream.cuda_stream)
     om = oracle.load("port").map(0.1)
