@@ -47,9 +47,9 @@ def load_peaks():
 
 def ncu_traffic(phase: str):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the phase's kernel, from the committed ncu --set full
-    capture (profiles/r1_ncu_summary.json); None if that file has no entry."""
+    capture of the current kernels (profiles/r1_ncu_summary_v4.json); None if that file has no entry."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_ncu_summary.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r1_ncu_summary_v4.json")) as f:
             k = json.load(f)["kernels"]
         name = {"classify": "k_classify<0, 1, 1>", "resolve": "k_resolve<0>", "mark": "k_mark<0>", "apply": "k_apply_leaves"}[phase]
         e = k[name]
