@@ -6,7 +6,15 @@ owner, exchange 2 (ray cells to the owner of *their* root), endpoint apply befor
 protocol itself (who decides what, in which order, with which two exchanges) is checked against the CPU oracle
 without a GPU. Run by tests/test_shard_protocol_cpu.py with world_size 2 and 3.
 
-gloo has no all_to_all, so an exchange is an all_gather_object of the per-destination buckets.
+Two flavours of the exchanges (BNX_MODEL_EXCHANGE):
+  gather    an all_gather_object of the per-destination buckets (gloo has no all_to_all)
+  mailbox   the peer-memory protocol of the CUDA path, with POSIX shared memory standing in for NVLink-mapped device
+            memory: every rank owns a mailbox [stamps | inbox [world][cap]], a sender stores its records straight into
+            block [rank] of the OWNER's inbox, then the count into the block header, then its arrival stamp; the
+            receiver spins on the stamps of all senders and reads the blocks as one dense range. The inboxes are single
+            buffered: what makes that safe is the flag exchange at the end of every scan (nobody starts scan k+1 before
+            every rank has consumed scan k), exactly as in DESIGN.md §7. gloo is only used to hand the segment names
+            around and to collect the result.
 """
 import os
 import sys
@@ -52,9 +60,89 @@ def ray_cells(O, E):
     return (O + np.sign(d) * ((2 * k * np.abs(d) + m) // (2 * m))).astype(np.int32)
 
 
-def exchange(buckets):
-    """all-to-all through all_gather_object: buckets[o] goes to rank o; returns what every rank sent to me"""
+class Mailboxes:
+    """one mailbox per rank in shared memory; peers store into it one-sidedly"""
+    KINDS, COLS = 3, 4  # exchange 1, exchange 2, flags; a record = 4 x int64
+
+    def __init__(self, cap: int):
+        from multiprocessing import shared_memory
+        self.world, self.rank, self.cap = dist.get_world_size(), dist.get_rank(), cap
+        self.words = self.KINDS * self.world + 2 * self.world * (1 + cap * self.COLS)  # stamps + 2 inboxes with headers
+        name = f"bnx_mbox_{os.environ.get('MASTER_PORT', '0')}_{os.getpid()}"
+        self.mine = shared_memory.SharedMemory(create=True, size=self.words * 8, name=name)
+        np.ndarray((self.words,), np.int64, self.mine.buf)[:] = 0
+        names = [None] * self.world
+        dist.all_gather_object(names, name)  # the "IPC handles"
+        self.segs = [self.mine if r == self.rank else shared_memory.SharedMemory(name=names[r]) for r in range(self.world)]
+        self.box = [np.ndarray((self.words,), np.int64, seg.buf) for seg in self.segs]
+        self.seq = [0] * self.KINDS
+        dist.barrier()
+
+    def _block(self, owner: int, inbox: int, src: int) -> slice:
+        base = self.KINDS * self.world + (inbox * self.world + src) * (1 + self.cap * self.COLS)
+        return slice(base, base + 1 + self.cap * self.COLS)
+
+    def exchange(self, kind: int, buckets):
+        """buckets[o]: int64 (n, 4) records for owner o. Returns the records of all senders as one dense array."""
+        self.seq[kind] += 1
+        for o, rec in enumerate(buckets):
+            rec = np.asarray(rec, np.int64).reshape(-1, self.COLS)
+            assert len(rec) <= self.cap, "inbox overflow"
+            blk = self.box[o][self._block(o, kind, self.rank)]
+            blk[1:1 + rec.size] = rec.ravel()          # records first
+            blk[0] = len(rec)                           # then the header
+            self.box[o][kind * self.world + self.rank] = self.seq[kind]  # then the arrival stamp
+        mine = self.box[self.rank]
+        import time
+        t0 = time.time()
+        while any(mine[kind * self.world + src] < self.seq[kind] for src in range(self.world)):
+            assert time.time() - t0 < 60, "a peer never arrived"
+            time.sleep(0)
+        out = []
+        for src in range(self.world):  # dense range over the per-sender blocks
+            blk = mine[self._block(self.rank, kind, src)]
+            out.append(blk[1:1 + int(blk[0]) * self.COLS].reshape(-1, self.COLS).copy())
+        return out
+
+    def flags(self, mine_flag: int) -> int:
+        """the end-of-scan flag exchange: also the barrier that makes the single-buffered inboxes safe"""
+        kind = 2
+        self.seq[kind] += 1
+        for o in range(self.world):  # value and stamp share one word here (the CUDA path stores {flags, stamp} 16 bytes)
+            self.box[o][kind * self.world + self.rank] = self.seq[kind] * 4 + mine_flag
+        me = self.box[self.rank]
+        import time
+        t0 = time.time()
+        while any(me[kind * self.world + src] // 4 < self.seq[kind] for src in range(self.world)):
+            assert time.time() - t0 < 60, "a peer never arrived"
+            time.sleep(0)
+        return max(int(me[kind * self.world + src]) % 4 for src in range(self.world))
+
+    def close(self):
+        dist.barrier()
+        self.box = None
+        for r, seg in enumerate(self.segs):
+            seg.close()
+        self.mine.unlink()
+
+
+MBOX = None
+
+
+def exchange(buckets, kind=0):
+    """all-to-all: buckets[o] goes to rank o; returns what every rank sent to me"""
     world, rank = dist.get_world_size(), dist.get_rank()
+    if MBOX is not None:
+        packed = []
+        for b in buckets:
+            if isinstance(b, tuple):  # endpoint records: (cells (n,3), prio (n,))
+                packed.append(np.concatenate([b[0].astype(np.int64), b[1].astype(np.int64)[:, None]], axis=1))
+            else:                     # ray cells (n,3)
+                packed.append(np.concatenate([b.astype(np.int64), np.zeros((len(b), 1), np.int64)], axis=1))
+        got = MBOX.exchange(kind, packed)
+        if isinstance(buckets[0], tuple):
+            return [(g[:, :3].astype(np.int32), g[:, 3]) for g in got]
+        return [g[:, :3].astype(np.int32) for g in got]
     gathered = [None] * world
     dist.all_gather_object(gathered, buckets)
     return [gathered[src][rank] for src in range(world)]
@@ -68,7 +156,7 @@ def sharded_insert(shard: dict, c: int, pts_local, index_base, origin, max_range
     first.sort()
     own = owner_of(cells[first], world)
     rec = [(cells[first][own == o], (index_base + first[own == o]) * 2 + miss[first][own == o]) for o in range(world)]
-    got = exchange(rec)
+    got = exchange(rec, 0)
     # ---- stage B (owner): lowest GLOBAL index wins, stale test against MY shard, rays only for fresh endpoints
     ecells = np.concatenate([g[0] for g in got])
     eprio = np.concatenate([g[1] for g in got])
@@ -88,7 +176,7 @@ def sharded_insert(shard: dict, c: int, pts_local, index_base, origin, max_range
             for o in range(world):
                 out_cells[o].append(rc[ro == o])
     send = [np.unique(np.concatenate(b), axis=0) if b else np.zeros((0, 3), np.int32) for b in out_cells]
-    got = exchange(send)
+    got = exchange(send, 1)
     # ---- stage C (owner): endpoints first, then every ray cell whose id is not the current one
     for key, is_miss in endpoints:
         w = shard.get(key, 0)
@@ -102,12 +190,17 @@ def sharded_insert(shard: dict, c: int, pts_local, index_base, origin, max_range
             if (w & 0xF) != c:
                 p = (w >> 4) if w < 2**31 else ((w - 2**32) >> 4)
                 shard[key] = ((max(p + MISS, CMIN) << 4) | c) & 0xFFFFFFFF
+    if MBOX is not None:
+        assert MBOX.flags(0) == 0  # every rank has consumed both inboxes of this scan: they may be overwritten now
     return 1 if c == 3 else c + 1
 
 
 def main():
+    global MBOX
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
+    if os.environ.get("BNX_MODEL_EXCHANGE", "gather") == "mailbox":
+        MBOX = Mailboxes(cap=1 << 16)
     res, max_range = 0.25, 12.0
     shard, c = {}, 1
     scans = [synth.lidar_scan(s, beams=8, azimuths=96) for s in (0, 1, 1, 2, 0, 0)]  # repeats exercise the stale rule
@@ -129,8 +222,10 @@ def main():
             want = {tuple(int(v) for v in x): int(w) for x, w in zip(xyz, words)}
             assert union == want, f"scan {k}: sharded model differs from the oracle ({len(union)} vs {len(want)} cells)"
     dist.barrier()
+    if MBOX is not None:
+        MBOX.close()
     if rank == 0:
-        print("SHARD_MODEL_OK", world)
+        print("SHARD_MODEL_OK", world, "mailbox" if MBOX is not None else "gather")
     dist.destroy_process_group()
 
 

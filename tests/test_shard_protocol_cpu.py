@@ -10,12 +10,14 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("world,port", [(2, 29711), (3, 29712)])
-def test_shard_protocol_model_over_gloo(world, port):
-    env = dict(os.environ, OMP_NUM_THREADS="1")
+@pytest.mark.parametrize("world,port,exchange", [(2, 29711, "gather"), (3, 29712, "gather"), (2, 29713, "mailbox"), (3, 29714, "mailbox")])
+def test_shard_protocol_model_over_gloo(world, port, exchange):
+    """gather: the exchanges as collectives; mailbox: one-sided stores into the owners' (shared-memory) inboxes + arrival
+    stamps + the end-of-scan flag exchange, i.e. the peer-memory protocol of the CUDA path"""
+    env = dict(os.environ, OMP_NUM_THREADS="1", BNX_MODEL_EXCHANGE=exchange)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
                         "--master-port", str(port), os.path.join(ROOT, "tests", "shard_model.py")], capture_output=True, text=True, timeout=600, env=env)
-    assert r.returncode == 0 and f"SHARD_MODEL_OK {world}" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
+    assert r.returncode == 0 and f"SHARD_MODEL_OK {world} {exchange}" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
 
 
 def test_split_points_covers_every_index_once():
