@@ -96,7 +96,8 @@ inline void launch_scan_kernel(void (*kernel)(KArgs...), int blocks, int threads
 // ------------------------------------------------------------------------------------------------
 // peer-memory exchange primitives (sharded map)
 // ------------------------------------------------------------------------------------------------
-constexpr unsigned long long PEER_TIMEOUT_NS = 8000000000ull;  // a dead peer becomes ERR_PEER, never a hang
+// a dead peer becomes ERR_PEER, never a hang: 20 s by default, BNX_PEER_TIMEOUT_MS overrides (read when the map is sharded)
+__device__ unsigned long long g_peer_timeout_ns = 20000000000ull;
 
 __device__ __forceinline__ u32 ld_acquire_sys(const u32* p) {
   u32 v;
@@ -122,7 +123,7 @@ __device__ __forceinline__ void wait_arrivals(const u32* flags, u32 stride, u32 
       const unsigned long long t0 = global_ns();
       while ((int)(ld_acquire_sys(f) - seq) < 0) {
         if (*reinterpret_cast<volatile u32*>(err) & ERR_PEER) break;
-        if (global_ns() - t0 > PEER_TIMEOUT_NS) {
+        if (global_ns() - t0 > g_peer_timeout_ns) {
           atomicOr(err, ERR_PEER);
           break;
         }
@@ -1597,6 +1598,10 @@ int Map::drain() {
 // ------------------------------------------------------------------------------------------------
 int Map::shard_config(int rank, int world) {
   BNX_REQUIRE(world >= 1 && rank >= 0 && rank < world, "shard_config: bad rank/world");
+  if (const char* e = std::getenv("BNX_PEER_TIMEOUT_MS")) {
+    const unsigned long long ns = std::strtoull(e, nullptr, 10) * 1000000ull;
+    if (ns) BNX_CUDA(cudaMemcpyToSymbol(g_peer_timeout_ns, &ns, sizeof(ns)));
+  }
   rank_ = rank;
   world_ = world;
   if (world > 1 && !scratch_) {

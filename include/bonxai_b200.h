@@ -265,7 +265,7 @@ BNX_API int bnx_map_shard_insert(bnx_map_t* m, const void* points, int64_t strid
  * bnx_map_shard_comm_init + bnx_map_shard_insert do all of this themselves (handles all-gathered through NCCL,
  * mailboxes re-created collectively when an exchange overflowed) unless BNX_SHARD_EXCHANGE=nccl is set; NCCL then
  * only bootstraps. bnx_map_shard_exchange: 0 caller-run, 1 NCCL collectives, 2 peer memory. A peer that never
- * arrives turns into an error after 8 s, not a hang. */
+ * arrives turns into an error after 20 s (BNX_PEER_TIMEOUT_MS), not a hang. */
 BNX_API int bnx_map_shard_p2p_alloc(bnx_map_t* m, int64_t cap_records, int64_t cap_leaves, void* ipc_handle64, void** device_ptr);
 BNX_API int bnx_map_shard_p2p_attach(bnx_map_t* m, const void* ipc_handles, void* const* device_ptrs);
 BNX_API int bnx_map_shard_exchange(const bnx_map_t* m, int* kind);
