@@ -109,16 +109,17 @@ class Map {
     use_next_T_ = true;
   }
 
-  // ---- root-key sharding across processes (one map shard per GPU). The caller runs the two exchanges
-  // (all-to-all of the staged device buffers) between the stages; see bonxai_b200/sharded.py.
+  // ---- root-key sharding across processes (one map shard per GPU), as stages: with caller-owned exchange buffers the
+  // caller moves them between the stages; with mailboxes attached (NULL buffers) the kernels exchange by themselves.
   int shard_config(int rank, int world);
   int shard_begin(const void* points, i64 stride_bytes, i64 n, bool f64, u32 index_base, const double origin[3], double max_range,
                   void* send_records, i64 cap_records, int where);
   int shard_resolve_mark(const void* recv_records, void* send_leaves, i64 cap_leaves);
   int shard_merge(const void* recv_leaves, void* flags);
   int shard_finish(const void* flags_reduced, int* retry);
-  // the same protocol driven natively: NCCL send/recv all-to-all + all-reduce issued by the library on the map's
-  // stream (NCCL is resolved with dlopen). async: nothing synchronises; failures freeze all ranks at the same scan.
+  // the same protocol driven by the library: mailboxes (peer memory) set up over NCCL, or NCCL send/recv all-to-alls +
+  // all-reduce with BNX_SHARD_EXCHANGE=nccl (NCCL is resolved with dlopen). async: nothing synchronises; failures
+  // freeze all ranks at the same scan.
   static int nccl_unique_id(const char* nccl_path, void* out128);
   int shard_comm_init(const char* nccl_path, const void* unique_id128, int rank, int world);
   int shard_insert(const void* points, i64 stride_bytes, i64 n, bool f64, u32 index_base, i64 n_max, const double origin[3], double max_range,
@@ -147,45 +148,69 @@ class Map {
   double phase_us[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
  private:
+  // ---- one scan = launch_front (clear + classify) + launch_back (resolve, mark, apply)
   int reserve_scan(i64 n, i64 stride_bytes, double max_range, i64 table_n = -1);
   size_t tile_bytes(size_t np, double max_range) const;
-  int run_scan(const void* d_points, i64 stride_bytes, bool f64, const ScanParams& base, bool reuse_classify);
+  int build_params(i64 n, const double origin[3], double max_range, ScanParams* out);
+  int launch_front(cudaStream_t s, const void* d_points, i64 stride_bytes, bool f64, ScanParams& p);
+  int launch_back(cudaStream_t s, ScanParams& p, bool first_attempt);
+  int launch_scan(const void* d_points, i64 stride_bytes, bool f64, ScanParams& p, bool first_attempt);  // both, on the map's stream
+  int run_scan(const void* d_points, i64 stride_bytes, bool f64, const ScanParams& base, bool reuse_classify);  // synchronous, with retries
+  void account(const ScanCounters& st, i64 n, i64 pending, i64 retries);
 
   ScanBuffers buf_ = {};
-  DevBuf b_pts_, b_rays_, b_tiles_, b_touched_, b_pending_, b_q_xyz_, b_q_out_;
+  DevBuf b_pts_, b_rays_, b_tiles_, b_touched_, b_touched2_, b_pending_, b_q_xyz_, b_q_out_;
   // Scratch written BEFORE a scan touches the map (classify: endpoints, their dedupe table, the counters) exists once
   // per scan in flight: the pipelined insert classifies on its own stream, many scans ahead of the map updates.
+  // The synchronous and the sharded paths use set 0.
   struct ScratchSet {
     DevBuf ep, slot, table, stage;  // table = [ScanCounters | table u32[slots] | keys u64[slots]]; stage = H2D staging
     u64 clean_slots = 0;            // dedupe-table slots known to be zero (left clean by the set's previous scan)
-    bool sc_clean = false, t1_clean = false;
-    cudaEvent_t classified = nullptr;
+    bool sc_clean = false, t1_clean = false;  // sharded pipeline: counters / sender-side table known to be zero
+    cudaEvent_t classified = nullptr;         // front half of the set's scan done
   };
-  static constexpr int SETS = 34;  // MAX_IN_FLIGHT + 2: the set of scan id - SETS is free when scan id is enqueued
+  static constexpr int SETS = 34;  // scans in flight (<= 32) + 2: the set of scan id - SETS is free when scan id is enqueued
   ScratchSet sets_[SETS];
   int set_ = 0, sets_active_ = SETS;
   i64 sets_n_ = -1;              // points every active set is sized for (pipelined insert)
   size_t sets_stage_bytes_ = 0;  // H2D staging bytes every active set holds
   ScratchSet& S() { return sets_[set_]; }
-  cudaStream_t pre_stream_ = nullptr;  // H2D copy + classify of the pipelined insert
-  ScanCounters* d_sc_ = nullptr;    // head of b_table_: counters + dedupe table are cleared by ONE memset
+  ScanCounters* d_sc_ = nullptr;      // head of the current set's table buffer: counters + dedupe table are cleared by ONE memset
   ScanCounters* h_status_ = nullptr;  // pinned
-  u32 n_pending_ = 0;
+  u32 n_pending_ = 0;                 // queued addHitPoint / addMissPoint endpoints
   float next_T_[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
   bool use_next_T_ = false;
+  u32 seq_ = 0;  // scan serial number (leaf stamps)
+  cudaEvent_t ev_[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // profiling
+
+  // ---- pipelined insert
+  static constexpr u32 RING = 1024;
+  struct Queued {
+    ScanParams p;
+    const void* points;
+    i64 stride;
+    bool f64;
+    int where;
+  };
+  std::vector<Queued> queue_;
+  AsyncRecord* h_ring_ = nullptr;  // pinned + mapped: one record per scan, written by the device
+  AsyncRecord* d_ring_ = nullptr;
+  u32 async_next_ = 0;
+  size_t done_upto_ = 0;        // queue_ entries whose record has been seen
+  u64 max_leaf_growth_ = 2048;  // largest per-scan leaf allocation seen so far (head-room estimate)
+  cudaStream_t pre_stream_ = nullptr;  // front halves: H2D copy + classify
+
+  // ---- sharded map
   int rank_ = 0, world_ = 1;
-  Grid* scratch_ = nullptr;  // sharded: staging grid for cells whose root another rank owns (masks only)
-  ScanParams sp_ = {};       // sharded: parameters of the scan in flight
+  Grid* scratch_ = nullptr;  // staging grid for cells whose root another rank owns (masks only)
+  ScanParams sp_ = {};       // parameters of the scan in flight
   i64 shard_retries_ = 0;
-  void* comm_ = nullptr;  // ncclComm_t
-  DevBuf x_send1_, x_recv1_, x_send2_, x_recv2_, x_flags_;
-  i64 cap_rec_ = 0, cap_leaf_ = 1 << 13;
-  bool staged_p2p_ = false;  // the scan in flight uses the mailboxes
+  bool staged_p2p_ = false;   // the scan in flight uses the mailboxes
   bool shard_async_ = false;  // the scan being enqueued is pipelined (set by shard_insert around the stages)
   u32 shard_async_id_ = 0, shard_attempt_ = 0;
   i64 shard_n_max_ = 0;
   bool t2_clean_ = false;  // pipelined: receiver table known to be zero
-  DevBuf b_table2_;  // receiver-side dedupe table of the sharded map
+  DevBuf b_table2_;        // receiver-side dedupe table
   void shard_phase_times();
   struct ShardQueued {
     const void* points;
@@ -196,8 +221,13 @@ class Map {
     int where;
   };
   std::vector<ShardQueued> squeue_;
-  int all_to_all(const void* send, void* recv, size_t block_bytes);
   int shard_drain();
+  // NCCL: bootstrap of the mailboxes, and the exchange itself with BNX_SHARD_EXCHANGE=nccl
+  void* comm_ = nullptr;  // ncclComm_t
+  DevBuf x_send1_, x_recv1_, x_send2_, x_recv2_, x_flags_, x_handles_;
+  i64 cap_rec_ = 0, cap_leaf_ = 1 << 13;
+  int all_to_all(const void* send, void* recv, size_t block_bytes);
+  // peer-memory exchange
   int p2p_collective_setup(i64 cap_records, i64 cap_leaves);
   void p2p_close_peers();
   int upload_boxes();
@@ -206,41 +236,18 @@ class Map {
   std::vector<void*> mbox_retired_;  // replaced mailboxes stay allocated until the map dies (a slow peer may still map them)
   void* peer_base_[MAX_PEERS] = {};
   bool peer_ipc_[MAX_PEERS] = {};
-  bool p2p_ready_ = false;
+  bool p2p_ready_ = false, want_p2p_ = false;
   u32 xseq1_ = 0, xseq2_ = 0;  // arrival stamps: every rank enqueues the same sequence of exchanges
   PeerBoxes px_host_ = {}, px_uploaded_ = {};
-  bool px_uploaded_valid_ = false, want_p2p_ = false;
-  DevBuf b_px_, x_handles_;
-  // pipelined insert
-  static constexpr u32 RING = 1024;
-  struct Queued {
-    ScanParams p;
-    const void* points;
-    i64 stride;
-    bool f64;
-    int where;
-  };
-  std::vector<Queued> queue_;
-  AsyncRecord* h_ring_ = nullptr;  // pinned + mapped
-  AsyncRecord* d_ring_ = nullptr;
-  u32 async_next_ = 0;
-  size_t done_upto_ = 0;                       // queue_ entries whose record has been seen
-  u64 max_leaf_growth_ = 2048;                 // largest per-scan leaf allocation seen so far (head-room estimate)
-  cudaStream_t copy_stream_ = nullptr;
-  // sharded pipelined insert with host input: H2D staging ring on the copy stream
-  static constexpr size_t SHARD_QUEUE = 64;               // scans between two collective drains
+  bool px_uploaded_valid_ = false;
+  DevBuf b_px_;
+  // pipelined insert with host input: H2D staging ring on a copy stream
+  static constexpr size_t SHARD_QUEUE = 64;  // scans between two collective drains
   static constexpr int SHARD_STAGES = (int)SHARD_QUEUE + 2;
+  cudaStream_t copy_stream_ = nullptr;
   DevBuf x_stage_[SHARD_STAGES];
   cudaEvent_t x_copied_[SHARD_STAGES] = {};
   size_t x_stage_bytes_ = 0;
-  int build_params(i64 n, const double origin[3], double max_range, ScanParams* out);
-  int launch_scan(const void* d_points, i64 stride_bytes, bool f64, ScanParams& p, bool first_attempt);
-  int launch_front(cudaStream_t s, const void* d_points, i64 stride_bytes, bool f64, ScanParams& p);  // clear + classify
-  int launch_back(cudaStream_t s, ScanParams& p, bool first_attempt);                                  // resolve, mark, apply
-  void account(const ScanCounters& st, i64 n, i64 pending, i64 retries);
-  DevBuf b_touched2_;
-  u32 seq_ = 0;
-  cudaEvent_t ev_[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 }  // namespace bnx
