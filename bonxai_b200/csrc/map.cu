@@ -1417,7 +1417,7 @@ int Map::insert_async(const void* points, i64 stride_bytes, i64 n, bool f64, con
   // how many scratch sets (= scans in flight + 2) does this scan size allow? (2 GiB of scratch at most)
   {
     const size_t np = (size_t)n + 32;
-    const size_t set_bytes = np * 20 + SC_BYTES + table_slots(n) * 12 + (where == BNX_HOST ? (size_t)n * stride_bytes : 0);
+    const size_t set_bytes = np * 20 + SC_BYTES + table_slots(n) * 12 + (size_t)n * stride_bytes;  // staging counted for any input: host and device scans may alternate
     const int want = (int)std::min<size_t>(SETS, std::max<size_t>(4, (2ull << 30) / std::max<size_t>(set_bytes, 1)));
     if (want != sets_active_) {
       BNX_TRY(drain());  // the id -> set mapping changes: nothing may be in flight
