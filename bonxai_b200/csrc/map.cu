@@ -37,7 +37,7 @@ namespace {
 constexpr int TPB = 256;
 constexpr u32 CHUNK = 8;  // ray cells per work item
 #ifndef MARK_MIN_BLOCKS
-#define MARK_MIN_BLOCKS 8
+#define MARK_MIN_BLOCKS 6
 #endif
 constexpr unsigned long long CHUNK_FIELD = (1ull << 40) - 1ull;
 constexpr u32 RING_SIZE = 1024;  // entries of the pipelined-insert record ring (Map::RING)
@@ -1320,7 +1320,7 @@ int Map::launch_back(cudaStream_t s, ScanParams& p, bool first_attempt) {
   if (n_pending_) launch_scan_kernel(k_resolve<1>, blocks_for(n_pending_), TPB, s, g, p, buf_, n_pending_);
   if (n > 0) launch_scan_kernel(k_resolve<0>, blocks_for(n), TPB, s, g, p, buf_, (u32)n);
   if (profiling && first_attempt) cudaEventRecord(ev_[3], s);
-  launch_scan_kernel(k_mark<false>, persistent, TPB, s, g, g, p, buf_);
+  launch_scan_kernel(k_mark<false>, sm_count() * MARK_MIN_BLOCKS, TPB, s, g, g, p, buf_);
   if (profiling && first_attempt) cudaEventRecord(ev_[4], s);
   launch_scan_kernel(k_apply_leaves, sm_count() * APPLY_MIN_BLOCKS, TPB, s, g, p, buf_);
   BNX_CUDA(cudaGetLastError());
@@ -1794,7 +1794,7 @@ int Map::shard_resolve_mark(const void* recv_records, void* send_leaves, i64 cap
   const int rblocks = blocks_for(std::min<i64>(slots, 2 * (i64)p.rec_cap));
   launch_scan_kernel(k_shard_dedupe, rblocks, TPB, s, p, buf_, slots, table1, lean ? (u32)(t1 * 12 / 16) : 0u);
   launch_scan_kernel(k_resolve<2>, rblocks, TPB, s, g, p, buf_, slots);
-  launch_scan_kernel(k_mark<true>, persistent, TPB, s, g, gs, p, buf_);
+  launch_scan_kernel(k_mark<true>, sm_count() * MARK_MIN_BLOCKS, TPB, s, g, gs, p, buf_);
   launch_scan_kernel(k_shard_emit, persistent, TPB, s, gs, p, buf_);
   BNX_CUDA(cudaGetLastError());
   if (profiling) cudaEventRecord(ev_[2], s);

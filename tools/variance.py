@@ -5,7 +5,7 @@ import bench
 from bonxai_b200 import capi
 import torch
 
-K, W, R = 300, 10, 6
+K, W, R = 300, 10, 5
 scans = bench.gen_scans(0, K + W)
 dev = [torch.from_numpy(p).cuda() for p, _ in scans]
 pinned = [torch.from_numpy(p).pin_memory().numpy() for p, _ in scans]
