@@ -300,6 +300,27 @@ def test_async_pipeline_equals_sync(bnx, port):
     check_scan(gm, om, "sync after async")
 
 
+def test_async_pipeline_wraps_the_scratch_ring(bnx, port):
+    """more scans in one queue than there are scratch sets (34): every set is reused, host and device inputs and two
+    scan sizes alternate; the map must still equal the oracle bit for bit"""
+    import torch
+    gm, om = bnx.ProbabilisticMap(0.1), port.map(0.1)
+    keep = []
+    for scan in range(90):
+        pts, origin = synth.lidar_scan(scan, beams=16, azimuths=256 if scan % 5 else 512)
+        if scan % 2:
+            t = torch.from_numpy(pts).cuda()
+            keep.append(t)
+            gm.insert_async(bnx.DevPtr(t.data_ptr()), origin, 30.0, n=len(pts), stride_bytes=16)
+        else:
+            keep.append(pts)
+            gm.insert_async(pts, origin, 30.0)
+        om.insert(pts, origin, 30.0)
+    gm.sync()
+    assert_same_dump(gm.dump(), om.dump(), "after 90 pipelined scans")
+    assert gm.totals()["U"] > 0 and gm.update_count() == 1  # 90 scans: the counter cycled 30 times
+
+
 def test_async_pipeline_freeze_and_replay(bnx, port, monkeypatch):
     """tiny pools: a queued scan runs short, the device freezes the pipeline, sync() grows and replays: still exact"""
     monkeypatch.setenv("BNX_INIT_LEAF_MB", "2")
