@@ -608,7 +608,7 @@ int Grid::init(double voxel_size, int ib, int lb, int cbytes) {
   d.inner = static_cast<u32*>(inner_arena_.base());
   BNX_TRY(grow_root_table(1ull << 14));
   BNX_TRY(ensure_inner_capacity(env_mb("BNX_INIT_INNER_MB", 16) / (d.inner_stride * 4)));
-  BNX_TRY(ensure_leaf_capacity(env_mb("BNX_INIT_LEAF_MB", 512) / d.leaf_stride));
+  BNX_TRY(ensure_leaf_capacity(env_mb("BNX_INIT_LEAF_MB", 1024) / d.leaf_stride));
   return sync();
 }
 
