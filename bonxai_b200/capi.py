@@ -29,7 +29,7 @@ SYMBOLS = [
     "bnx_grid_create", "bnx_grid_destroy", "bnx_grid_set_stream", "bnx_grid_sync", "bnx_grid_info",
     "bnx_grid_pos_to_coord", "bnx_grid_coord_to_pos", "bnx_grid_set_values", "bnx_grid_get_values",
     "bnx_grid_get_or_create", "bnx_grid_update_values", "bnx_grid_set_on", "bnx_grid_set_off", "bnx_grid_is_on",
-    "bnx_grid_active_count", "bnx_grid_dump", "bnx_grid_clear", "bnx_grid_release_unused", "bnx_grid_mem_usage",
+    "bnx_grid_active_count", "bnx_grid_digest", "bnx_grid_dump", "bnx_grid_clear", "bnx_grid_release_unused", "bnx_grid_mem_usage",
     "bnx_grid_stats", "bnx_grid_serialize", "bnx_grid_deserialize",
     "bnx_map_create", "bnx_map_destroy", "bnx_map_set_stream", "bnx_map_sync", "bnx_map_grid", "bnx_map_set_options",
     "bnx_map_get_options", "bnx_map_insert_f32", "bnx_map_insert_f64", "bnx_map_add_hit", "bnx_map_add_miss",
@@ -38,7 +38,7 @@ SYMBOLS = [
     "bnx_map_publish_occupied_f32", "bnx_map_insert_transformed_f32", "bnx_map_insert_async_f32", "bnx_map_insert_async_f64", "bnx_map_totals",
     "bnx_map_shard_config", "bnx_map_shard_begin", "bnx_map_shard_resolve_mark", "bnx_map_shard_merge", "bnx_map_shard_finish",
     "bnx_nccl_unique_id", "bnx_map_shard_comm_init", "bnx_map_shard_insert",
-    "bnx_map_shard_p2p_alloc", "bnx_map_shard_p2p_attach", "bnx_map_shard_exchange",
+    "bnx_map_shard_p2p_alloc", "bnx_map_shard_p2p_attach", "bnx_map_shard_exchange", "bnx_map_shard_host_init", "bnx_map_shard_stats",
 ]
 
 
@@ -113,6 +113,46 @@ def _where(*ws):
     if any(w != ws[0] for w in ws):
         raise ValueError("host and device buffers cannot be mixed in one call")
     return ws[0]
+
+
+def _mix64(h):
+    h = h ^ (h >> np.uint64(33))
+    h = h * np.uint64(0xFF51AFD7ED558CCD)
+    h = h ^ (h >> np.uint64(33))
+    h = h * np.uint64(0xC4CEB9FE1A85EC53)
+    return h ^ (h >> np.uint64(33))
+
+
+def digest_of_dump(xyz, values):
+    """bnx_grid_digest restated in numpy for a host dump (xyz int32 (n,3), values any fixed-size dtype):
+    (sum, xor, count) over mix64(hash3(x,y,z) + FNV1a64(value bytes) * 0x9E3779B97F4A7C15), all mod 2^64"""
+    xyz = np.ascontiguousarray(xyz, np.int32).reshape(-1, 3)
+    vals = np.ascontiguousarray(values)
+    n = len(xyz)
+    if n == 0:
+        return 0, 0, 0
+    with np.errstate(over="ignore"):
+        x, y, z = (xyz[:, k].view(np.uint32).astype(np.uint64) for k in range(3))
+        h = x * np.uint64(0x9E3779B97F4A7C15)
+        h = h ^ (y * np.uint64(0xC2B2AE3D27D4EB4F) + (h >> np.uint64(29)))
+        h = h ^ (z * np.uint64(0x165667B19E3779F9) + (h << np.uint64(7)))
+        h = _mix64(h)
+        raw = vals.view(np.uint8).reshape(n, -1)
+        f = np.full(n, 0xCBF29CE484222325, np.uint64)
+        for k in range(raw.shape[1]):
+            f = (f ^ raw[:, k].astype(np.uint64)) * np.uint64(0x100000001B3)
+        d = _mix64(h + f * np.uint64(0x9E3779B97F4A7C15))
+        return int(d.sum(dtype=np.uint64)), int(np.bitwise_xor.reduce(d)), n
+
+
+def combine_digests(digests):
+    """digest of the union of disjoint shards"""
+    s = x = c = 0
+    for a, b, n in digests:
+        s = (s + a) & 0xFFFFFFFFFFFFFFFF
+        x ^= b
+        c += n
+    return s, x, c
 
 
 class VoxelGrid:
@@ -228,6 +268,13 @@ class VoxelGrid:
         n = C.c_int64()
         _check(self.lib.bnx_grid_active_count(self.h, C.byref(n)))
         return n.value
+
+    def digest(self):
+        """order-independent digest (sum, xor, count) of all (coord, value) pairs, computed on the device
+        (bnx_grid_digest); `digest_of_dump` below is the same function of a host dump"""
+        out = (C.c_uint64 * 3)()
+        _check(self.lib.bnx_grid_digest(self.h, out))
+        return int(out[0]), int(out[1]), int(out[2])
 
     def dump(self, sort=True):
         """forEachCell as arrays: (xyz int32 (n,3), values). Sorted by (x,y,z) for comparison by default."""
@@ -411,6 +458,15 @@ class ProbabilisticMap:
 
     def dump(self, sort=True):
         return self._grid.dump(sort)
+
+    def digest(self):
+        return self._grid.digest()
+
+    def shard_stats(self):
+        a = (C.c_int64 * 8)()
+        _check(self.lib.bnx_map_shard_stats(self.h, a))
+        return dict(attempts=a[0], replays=a[1], mailbox_setups=a[2], drains=a[3], sync_retries=a[4], leaf_inbox_cap=a[5],
+                    leaf_inbox_max_fill=a[6], scans=a[7])
 
     def counters(self):
         a = (C.c_int64 * 8)()

@@ -154,6 +154,7 @@ int bnx_grid_is_on(bnx_grid_t* h, const int32_t* xyz, int64_t n, uint8_t* out, i
   GRID_CALL(h, is_on(xyz, n, out, where));
 }
 int bnx_grid_active_count(bnx_grid_t* h, int64_t* count) { GRID_CALL(h, active_count(count)); }
+int bnx_grid_digest(bnx_grid_t* h, uint64_t out[3]) { GRID_CALL(h, digest(reinterpret_cast<u64*>(out))); }
 int bnx_grid_dump(bnx_grid_t* h, int32_t* xyz, void* values, int64_t cap, int64_t* count, int where) {
   GRID_CALL(h, dump(xyz, nullptr, values, cap, count, where, -1, 0));
 }
@@ -264,7 +265,9 @@ int bnx_map_insert_transformed_f32(bnx_map_t* h, const void* points, int64_t str
   const double o[3] = {(double)origin[0], (double)origin[1], (double)origin[2]};
   if (!async) BNX_TRY(h->m.drain());
   h->m.set_next_transform(sensor_to_world);
-  return async ? h->m.insert_async(points, stride_bytes, n, false, o, max_range, where) : h->m.insert(points, stride_bytes, n, false, o, max_range, where);
+  const int st = async ? h->m.insert_async(points, stride_bytes, n, false, o, max_range, where) : h->m.insert(points, stride_bytes, n, false, o, max_range, where);
+  h->m.clear_next_transform();  // a call that failed before it consumed the transform must not leave it to the next insert
+  return st;
 }
 int bnx_map_totals(bnx_map_t* h, int64_t out[4]) {
   BNX_HANDLE(h);
@@ -362,6 +365,17 @@ int bnx_map_shard_p2p_attach(bnx_map_t* h, const void* ipc_handles, void* const*
   BNX_HANDLE(h);
   DeviceGuard dg(h->m.grid.device);
   return h->m.p2p_attach(ipc_handles, device_ptrs);
+}
+int bnx_map_shard_host_init(bnx_map_t* h, int rank, int world, bnx_allgather_fn allgather, void* ctx) {
+  BNX_HANDLE(h);
+  DeviceGuard dg(h->m.grid.device);
+  return h->m.shard_host_init(rank, world, reinterpret_cast<Map::AllGatherFn>(allgather), ctx);
+}
+int bnx_map_shard_stats(bnx_map_t* h, int64_t out[8]) {
+  BNX_HANDLE(h);
+  BNX_REQUIRE(out != nullptr, "null output");
+  std::memcpy(out, h->m.shard_stats, sizeof(int64_t) * 8);
+  return BNX_OK;
 }
 int bnx_map_shard_exchange(const bnx_map_t* h, int* kind) {
   BNX_HANDLE(h);

@@ -253,6 +253,49 @@ __global__ void __launch_bounds__(TPB) k_count_active(GridDev g, u32 n_leaves, u
   }
 }
 
+// Order-independent digest of forEachCell's (coord, value) pairs: {sum, xor, count} of
+// mix64(hash3(x, y, z) + FNV-1a(value bytes) * 0x9E3779B97F4A7C15) over every ON cell. Equal digests <=> equal dumps (up to a
+// 2^-64 collision), and digests of disjoint shards add up (sum, count) / xor (xor): full-size parity checks and the
+// sharded bench compare maps without moving them to the host. One warp per leaf, coalesced cell rows.
+__global__ void __launch_bounds__(TPB) k_digest(GridDev g, u32 n_leaves, unsigned long long* out3) {
+  const u32 lane = threadIdx.x & 31;
+  const u32 warps = gridDim.x * (TPB / 32);
+  const u32 cells = 1u << (3 * g.lb), lm = (1u << g.lb) - 1u;
+  unsigned long long sum = 0, x = 0, cnt = 0;
+  for (u32 leaf = blockIdx.x * (TPB / 32) + (threadIdx.x >> 5); leaf < n_leaves; leaf += warps) {
+    const unsigned char* lp = leaf_ptr(g, leaf);
+    const int4 hdr = *reinterpret_cast<const int4*>(lp);
+    if (!(hdr.w & 1)) continue;
+    const u64* act = reinterpret_cast<const u64*>(lp + g.off_active);
+    for (u32 ci = lane; ci < cells; ci += 32) {
+      if (!((act[ci >> 6] >> (ci & 63)) & 1ull)) continue;
+      const unsigned char* v = lp + g.off_cells + (size_t)ci * g.cell_bytes;
+      u64 f = 0xCBF29CE484222325ull;
+      if (g.cell_bytes == 4) {
+        const u32 w = *reinterpret_cast<const u32*>(v);
+        for (int k = 0; k < 4; ++k) f = (f ^ ((w >> (8 * k)) & 0xFFu)) * 0x100000001B3ull;
+      } else {
+        for (u32 k = 0; k < g.cell_bytes; ++k) f = (f ^ v[k]) * 0x100000001B3ull;
+      }
+      const i32 cx = hdr.x | (i32)(ci & lm), cy = hdr.y | (i32)((ci >> g.lb) & lm), cz = hdr.z | (i32)((ci >> (2 * g.lb)) & lm);
+      const u64 h = mix64(hash3(cx, cy, cz) + f * 0x9E3779B97F4A7C15ull);
+      sum += h;
+      x ^= h;
+      ++cnt;
+    }
+  }
+  for (int o = 16; o; o >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    x ^= __shfl_xor_sync(0xffffffffu, x, o);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  if (lane == 0 && cnt) {
+    atomicAdd(&out3[0], sum);
+    atomicXor(&out3[1], x);
+    atomicAdd(&out3[2], cnt);
+  }
+}
+
 // forEachCell (bonxai.hpp:704-743) / getOccupiedVoxels / getFreeVoxels (probabilistic_map.cpp:108-126)
 // as a compaction: per-leaf predicate masks -> popcount -> block prefix -> one atomicAdd per block.
 // pred < 0: every ON cell. pred 0/2: CellT word with probability_log > / < thr.
@@ -972,6 +1015,23 @@ int Grid::active_count(i64* count) {
   BNX_CUDA(cudaMemcpyAsync(h_count_, d_count_, 8, cudaMemcpyDeviceToHost, stream_));
   BNX_TRY(sync());
   *count = (i64)h_count_[0];
+  return BNX_OK;
+}
+
+int Grid::digest(u64 out[3]) {
+  BNX_REQUIRE(out != nullptr, "digest: null output");
+  GridCounters c;
+  BNX_TRY(read_counters(&c));
+  const u32 n_leaves = std::min(c.n_leaves, dev_.leaf_cap);
+  BNX_CUDA(cudaMemsetAsync(d_count_, 0, 24, stream_));
+  if (n_leaves) {
+    const int blocks = std::max(1, std::min<int>((int)ceil_div(n_leaves, TPB / 32), sm_count() * 8));
+    note_launch(), k_digest<<<blocks, TPB, 0, stream_>>>(dev_, n_leaves, reinterpret_cast<unsigned long long*>(d_count_));
+    BNX_CUDA(cudaGetLastError());
+  }
+  BNX_CUDA(cudaMemcpyAsync(h_count_, d_count_, 24, cudaMemcpyDeviceToHost, stream_));
+  BNX_TRY(sync());
+  for (int k = 0; k < 3; ++k) out[k] = h_count_[k];
   return BNX_OK;
 }
 

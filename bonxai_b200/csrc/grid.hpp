@@ -63,6 +63,8 @@ class Grid {
 
   // ---- whole-grid operations
   int active_count(i64* count);
+  // order-independent digest {sum, xor, count} of all (coord, value) pairs (see k_digest)
+  int digest(u64 out[3]);
   // pred: -1 all ON cells; BNX_OCCUPIED/BNX_FREE: CellT probability_log >/< thr (map grids only).
   // xyz_out (int32 triplets) or pos_out (double triplets, coord*resolution); values optional.
   int dump(i32* xyz, double* pos, void* values, i64 cap, i64* count, int where, int pred, i32 thr);

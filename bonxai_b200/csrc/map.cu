@@ -203,12 +203,21 @@ __global__ void __launch_bounds__(TPB) k_classify(const unsigned char* __restric
   pdl_enter();
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.n || *b.poison) return;
+  // Non-finite points leave the cloud here, in every flavour: the reference's callers remove them before
+  // insertPointCloud (bonxai_ros/src/bonxai_server.cpp:148-154) because the reference itself has undefined behaviour
+  // on them ((int32)floor(NaN), a ray of 2^31 cells); a defined "dropped" beats a platform-dependent voxel.
   double px, py, pz;
   if (F64) {
     const double* q = reinterpret_cast<const double*>(pts + (size_t)i * stride);
     px = q[0];
     py = q[1];
     pz = q[2];
+    if (!(isfinite(px) && isfinite(py) && isfinite(pz))) {
+      b.ep[i] = make_int4(0, 0, 0, 2);
+      b.slot_of[i] = NONE;
+      atomicAdd(&b.sc->n_dropped, 1u);
+      return;
+    }
   } else {
     float fx, fy, fz;
     if (VEC4) {
@@ -222,16 +231,16 @@ __global__ void __launch_bounds__(TPB) k_classify(const unsigned char* __restric
       fy = q[1];
       fz = q[2];
     }
+    if (!(isfinite(fx) && isfinite(fy) && isfinite(fz))) {
+      b.ep[i] = make_int4(0, 0, 0, 2);
+      b.slot_of[i] = NONE;
+      atomicAdd(&b.sc->n_dropped, 1u);
+      return;
+    }
     if (p.use_transform) {
-      // the ROS caller's pre-step (bonxai_ros/src/bonxai_server.cpp:148-171): non-finite points leave the cloud, the
-      // rest goes through pcl::transformPointCloud in float. Association of PCL's SSE kernel on x86-64:
+      // the ROS caller's pre-step (bonxai_ros/src/bonxai_server.cpp:148-171): after the non-finite filter the cloud
+      // goes through pcl::transformPointCloud in float. Association of PCL's SSE kernel on x86-64:
       // x*c0 + (y*c1 + (z*c2 + c3)), every product and sum rounded on its own (no FMA).
-      if (!(isfinite(fx) && isfinite(fy) && isfinite(fz))) {
-        b.ep[i] = make_int4(0, 0, 0, 2);
-        b.slot_of[i] = NONE;
-        atomicAdd(&b.sc->n_dropped, 1u);
-        return;
-      }
       const float tx = __fadd_rn(__fmul_rn(fx, p.T[0]), __fadd_rn(__fmul_rn(fy, p.T[1]), __fadd_rn(__fmul_rn(fz, p.T[2]), p.T[3])));
       const float ty = __fadd_rn(__fmul_rn(fx, p.T[4]), __fadd_rn(__fmul_rn(fy, p.T[5]), __fadd_rn(__fmul_rn(fz, p.T[6]), p.T[7])));
       const float tz = __fadd_rn(__fmul_rn(fx, p.T[8]), __fadd_rn(__fmul_rn(fy, p.T[9]), __fadd_rn(__fmul_rn(fz, p.T[10]), p.T[11])));
@@ -723,27 +732,33 @@ __global__ void __launch_bounds__(TPB) k_clear_touched(GridDev g, ScanBuffers b,
 // phase 4 / 5: apply
 // ------------------------------------------------------------------------------------------------
 // the reduced flags as seen by the apply pass (block-uniform; ends with a __syncthreads in the peer-memory flavour)
-__device__ __forceinline__ void read_gate(const ScanParams& p, const ScanBuffers& b, u32& pool, u32& ovf) {
-  __shared__ u32 s_gate[2];
+// fill = the largest number of leaf records any rank sent to any owner in this scan (equal on every rank: the host uses
+// it to grow the leaf inboxes collectively, at a drain, BEFORE they overflow)
+__device__ __forceinline__ void read_gate(const ScanParams& p, const ScanBuffers& b, u32& pool, u32& ovf, u32& fill) {
+  __shared__ u32 s_gate[3];
   pool = 0;
   ovf = 0;
+  fill = 0;
   if (!b.gate) return;
   if (!b.my_flags) {  // all-reduced by the caller or by NCCL
     pool = b.gate[0];
     ovf = b.gate[1];
+    fill = b.gate[2];
     return;
   }
   const u32* base = b.gate + (p.xseq2 & 1u) * (MAX_PEERS * 4);
-  if (threadIdx.x < 2) s_gate[threadIdx.x] = 0;
+  if (threadIdx.x < 3) s_gate[threadIdx.x] = 0;
   wait_arrivals(base + 3, 4, p.world, p.xseq2, const_cast<u32*>(b.poison));
   if (threadIdx.x < p.world) {
     const uint4 v = __ldcg(reinterpret_cast<const uint4*>(base) + threadIdx.x);
     if (v.x) atomicOr(&s_gate[0], v.x);
     if (v.y) atomicOr(&s_gate[1], v.y);
+    if (v.z) atomicMax(&s_gate[2], v.z);
   }
   __syncthreads();
   pool = s_gate[0];
   ovf = s_gate[1];
+  fill = s_gate[2];
 }
 
 // One warp per listed leaf: hit endpoints (addHitPoint, probabilistic_map.cpp:30-41) and the union of all rays + miss
@@ -755,12 +770,13 @@ __device__ __forceinline__ void read_gate(const ScanParams& p, const ScanBuffers
 __global__ void __launch_bounds__(TPB, APPLY_MIN_BLOCKS) k_apply_leaves(GridDev g, ScanParams p, ScanBuffers b) {
   pdl_enter();
   // last kernel of the scan: the host reads counters + grid counters with one copy
-  u32 gate_pool, gate_ovf;
-  read_gate(p, b, gate_pool, gate_ovf);
+  u32 gate_pool, gate_ovf, gate_fill;
+  read_gate(p, b, gate_pool, gate_ovf, gate_fill);
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     b.sc->gc = *g.ctr;
     b.sc->gate_pool = gate_pool;
     b.sc->gate_ovf = gate_ovf;
+    b.sc->gate_fill = gate_fill;
   }
   const bool skip = (g.ctr->error | b.sc->overflow | gate_pool | gate_ovf) != 0u;
   const u32 n = skip ? 0u : min(b.sc->n_touched, p.touched_cap);
@@ -853,6 +869,7 @@ __global__ void __launch_bounds__(TPB, APPLY_MIN_BLOCKS) k_apply_leaves(GridDev 
   r->n_touched = sc->n_touched;
   r->n_points = p.n;
   r->n_dropped = sc->n_dropped;
+  r->leaf_fill = gate_fill;
   r->sum_m = sc->sum_m;
   r->ray_chunk = sc->ray_chunk;
   __threadfence_system();
@@ -987,11 +1004,13 @@ __global__ void __launch_bounds__(TPB) k_shard_emit(GridDev gs, ScanParams p, Sc
 // (values first, then the stamp); the apply kernel ORs the table itself. Threads 0..world-1 of one block.
 __device__ __forceinline__ void shard_flags(const GridDev& g, const GridDev& gs, const ScanParams& p, const ScanBuffers& b, u32* flags) {
   const u32 f0 = g.ctr->error | (gs.ctr->error << 8), f1 = b.sc->overflow;
+  u32 f2 = 0;  // fullest leaf-record block this rank sent
+  for (u32 o = 0; o < p.world; ++o) f2 = max(f2, *reinterpret_cast<const volatile u32*>(&b.sc->cnt2[o]));
   if (b.px->flag[0] == nullptr) {
     if (threadIdx.x == 0) {
       flags[0] = f0;
       flags[1] = f1;
-      flags[2] = 0;
+      flags[2] = f2;
       flags[3] = 0;
     }
     return;
@@ -1000,6 +1019,7 @@ __device__ __forceinline__ void shard_flags(const GridDev& g, const GridDev& gs,
     u32* dst = b.px->flag[threadIdx.x] + MBOX_FLAGS4 + (p.xseq2 & 1u) * (MAX_PEERS * 4) + p.rank * 4;
     dst[0] = f0;
     dst[1] = f1;
+    dst[2] = f2;
     __threadfence_system();
     st_release_sys(dst + 3, p.xseq2);
   }
@@ -1233,6 +1253,10 @@ int Map::build_params(i64 n, const double origin[3], double max_range, ScanParam
   return BNX_OK;
 }
 
+// bytes of host memory a strided cloud really occupies: up to the z of the last point, not n * stride (x may sit at a
+// non-zero offset inside the caller's point type, and the base pointer handed in is &points[0].x)
+static size_t cloud_bytes(i64 n, i64 stride_bytes, bool f64) { return n > 0 ? (size_t)(n - 1) * (size_t)stride_bytes + (f64 ? 24u : 12u) : 0u; }
+
 static int check_insert_args(const void* points, i64 stride_bytes, i64 n, bool f64, const double origin[3], i64 pending) {
   BNX_REQUIRE(n >= 0 && n + pending < (1ll << 24), "insert: at most 2^24-1 points per scan");
   BNX_REQUIRE(n == 0 || points != nullptr, "insert: null points");
@@ -1255,7 +1279,7 @@ int Map::insert(const void* points, i64 stride_bytes, i64 n, bool f64, const dou
   const void* d_points = points;
   if (where == BNX_HOST && n > 0) {
     BNX_TRY(b_pts_.reserve((size_t)n * stride_bytes));
-    BNX_CUDA(cudaMemcpyAsync(b_pts_.p, points, (size_t)n * stride_bytes, cudaMemcpyHostToDevice, s));
+    BNX_CUDA(cudaMemcpyAsync(b_pts_.p, points, cloud_bytes(n, stride_bytes, f64), cudaMemcpyHostToDevice, s));
     d_points = b_pts_.p;
   }
   ScanParams p;
@@ -1372,17 +1396,18 @@ int Map::run_scan(const void* d_points, i64 stride_bytes, bool f64, const ScanPa
     BNX_CUDA(cudaStreamSynchronize(s));
     const ScanCounters st = *h_status_;
     if (st.gc.error == 0 && st.overflow == 0) break;
-    // phases 4/5 skipped themselves: nothing was applied. Grow what was short and repeat from phase 2.
-    if (st.overflow & OVF_CHUNKS) {
-      set_error("insert: more than 2^32 ray chunks in one scan");
-      return BNX_ERR_UNSUPPORTED;
-    }
+    // phases 4/5 skipped themselves: nothing was applied. Drop the marks of the failed attempt (they must never reach a
+    // later scan's apply pass), grow what was short and repeat from phase 2.
     if (st.n_touched) {
       note_launch(), k_clear_touched<<<persistent, TPB, 0, s>>>(grid.dev(), buf_, std::min(st.n_touched, p.touched_cap));
       BNX_CUDA(cudaGetLastError());
       BNX_CUDA(cudaStreamSynchronize(s));
     }
     if (st.gc.error) BNX_TRY(grid.recover(st.gc));
+    if (st.overflow & OVF_CHUNKS) {  // the map is unchanged and clean: the scan is refused, later scans are not affected
+      set_error("insert: more than 2^32 ray chunks in one scan");
+      return BNX_ERR_UNSUPPORTED;
+    }
     if (st.overflow & OVF_TILES) {
       const u64 chunks = st.ray_chunk & CHUNK_FIELD;
       BNX_TRY(b_tiles_.reserve((size_t)(chunks / 32 + 64) * 4));
@@ -1413,14 +1438,14 @@ int Map::insert_async(const void* points, i64 stride_bytes, i64 n, bool f64, con
   BNX_TRY(check_insert_args(points, stride_bytes, n, f64, origin, n_pending_));
   if (n_pending_ || world_ > 1) return insert(points, stride_bytes, n, f64, origin, max_range, where);  // rare paths stay synchronous
   cudaStream_t s = grid.stream();
-  if (queue_.size() >= RING / 2) BNX_TRY(drain());
+  if (queue_.size() >= RING / 2) BNX_TRY(drain(false));
   // how many scratch sets (= scans in flight + 2) does this scan size allow? (2 GiB of scratch at most)
   {
     const size_t np = (size_t)n + 32;
     const size_t set_bytes = np * 20 + SC_BYTES + table_slots(n) * 12 + (size_t)n * stride_bytes;  // staging counted for any input: host and device scans may alternate
     const int want = (int)std::min<size_t>(SETS, std::max<size_t>(4, (2ull << 30) / std::max<size_t>(set_bytes, 1)));
     if (want != sets_active_) {
-      BNX_TRY(drain());  // the id -> set mapping changes: nothing may be in flight
+      BNX_TRY(drain(false));  // the id -> set mapping changes: nothing may be in flight
       sets_active_ = want;
     }
   }
@@ -1445,7 +1470,7 @@ int Map::insert_async(const void* points, i64 stride_bytes, i64 n, bool f64, con
       __builtin_ia32_pause();
 #endif
     }
-    if (!seen) BNX_TRY(drain());  // the stream is idle but the record never came (a frozen or failed pipeline)
+    if (!seen) BNX_TRY(drain(false));  // the stream is idle but the record never came (a frozen or failed pipeline)
   }
   // head-room check on the newest published record: grow early, so that a queued scan (almost) never runs short
   if (!queue_.empty()) {
@@ -1458,7 +1483,7 @@ int Map::insert_async(const void* points, i64 stride_bytes, i64 n, bool f64, con
       const u64 leaves_ahead = (u64)r.n_leaves + ahead * max_leaf_growth_, inner_ahead = (u64)r.n_inner + ahead * 64;
       const u64 roots_ahead = (u64)r.n_roots + ahead * 64;
       if (r.error || leaves_ahead * 2 > g.leaf_cap || inner_ahead * 2 > g.inner_cap || roots_ahead * 2 > (u64)g.root_mask + 1) {
-        BNX_TRY(drain());
+        BNX_TRY(drain(false));
         // grow for what the refilled pipeline may allocate before the next look, not only for what is in use now
         // (otherwise the same check drains again and again without growing anything)
         const u64 full = (u64)sets_active_ * max_leaf_growth_;
@@ -1475,11 +1500,11 @@ int Map::insert_async(const void* points, i64 stride_bytes, i64 n, bool f64, con
   // buffers shared by all scans in flight (stream-ordered use) must not be reallocated under them
   if ((size_t)grid.dev().leaf_cap * 4 > b_touched_.bytes || ((size_t)n + 32) * sizeof(int4) > b_rays_.bytes ||
       tile_bytes((size_t)n + 32, max_range) > b_tiles_.bytes) {
-    BNX_TRY(drain());
+    BNX_TRY(drain(false));
   }
   // all scratch sets are sized together, up front: an allocation in the middle of the pipeline would synchronise the device
   if (n > sets_n_ || (where == BNX_HOST && (size_t)n * stride_bytes > sets_stage_bytes_)) {
-    BNX_TRY(drain());
+    BNX_TRY(drain(false));
     sets_n_ = std::max<i64>(sets_n_, n + n / 8);
     if (where == BNX_HOST) sets_stage_bytes_ = std::max<size_t>(sets_stage_bytes_, (size_t)(n + n / 8) * stride_bytes);
     const int keep = set_;
@@ -1506,7 +1531,7 @@ int Map::insert_async(const void* points, i64 stride_bytes, i64 n, bool f64, con
   const void* d_points = points;
   if (where == BNX_HOST && n > 0) {
     BNX_TRY(S().stage.reserve((size_t)n * stride_bytes));
-    BNX_CUDA(cudaMemcpyAsync(S().stage.p, points, (size_t)n * stride_bytes, cudaMemcpyHostToDevice, pre_stream_));
+    BNX_CUDA(cudaMemcpyAsync(S().stage.p, points, cloud_bytes(n, stride_bytes, f64), cudaMemcpyHostToDevice, pre_stream_));
     d_points = S().stage.p;
   }
   {
@@ -1522,8 +1547,22 @@ int Map::insert_async(const void* points, i64 stride_bytes, i64 n, bool f64, con
   return BNX_OK;
 }
 
-int Map::drain() {
+// report: hand a deferred error (a scan the pipeline refused) to the caller. insert_async drains with report = false —
+// the scan being enqueued must not be lost to the failure of an earlier one; the next synchronising call reports it.
+int Map::drain(bool report) {
   if (!squeue_.empty()) return shard_drain();
+  const int st = drain_queue();
+  if (st != BNX_OK) return st;
+  if (report && deferred_ != BNX_OK) {
+    const int d = deferred_;
+    deferred_ = BNX_OK;
+    set_error(deferred_msg_);
+    return d;
+  }
+  return BNX_OK;
+}
+
+int Map::drain_queue() {
   if (queue_.empty()) return BNX_OK;
   cudaStream_t s = grid.stream();
   GridCounters gc;
@@ -1563,10 +1602,6 @@ int Map::drain() {
   if (!gc.error) return grid.maintain(gc);
   // the failed scan's touched list is still intact (later scans skipped themselves): drop its marks, grow, replay
   const ScanCounters st = *h_status_;
-  if (st.overflow & OVF_CHUNKS) {
-    set_error("insert: more than 2^32 ray chunks in one scan");
-    return BNX_ERR_UNSUPPORTED;
-  }
   if (st.n_touched) {
     note_launch(), k_clear_touched<<<sm_count() * 8, TPB, 0, s>>>(grid.dev(), buf_, std::min<u32>(st.n_touched, (u32)(b_touched_.bytes / 4)));
     BNX_CUDA(cudaGetLastError());
@@ -1579,16 +1614,23 @@ int Map::drain() {
     buf_.tile_first = b_tiles_.as<u32>();
   }
   set_ = 0;
-  for (size_t k = done; k < q.size(); ++k) {
+  // a scan with more ray chunks than the counters can hold is refused (reported below); the scans queued behind it are
+  // replayed like after any other failure
+  const bool refused = (st.overflow & OVF_CHUNKS) != 0u;
+  for (size_t k = done + (refused ? 1 : 0); k < q.size(); ++k) {
     const Queued& e = q[k];
     BNX_TRY(reserve_scan(e.p.n, e.stride, e.p.max_range));
     const void* d_points = e.points;
     if (e.where == BNX_HOST && e.p.n > 0) {
       BNX_TRY(b_pts_.reserve((size_t)e.p.n * e.stride));
-      BNX_CUDA(cudaMemcpyAsync(b_pts_.p, e.points, (size_t)e.p.n * e.stride, cudaMemcpyHostToDevice, s));
+      BNX_CUDA(cudaMemcpyAsync(b_pts_.p, e.points, cloud_bytes(e.p.n, e.stride, e.f64), cudaMemcpyHostToDevice, s));
       d_points = b_pts_.p;
     }
     BNX_TRY(run_scan(d_points, e.stride, e.f64, e.p, false));  // keeps the update_id this scan was queued with
+  }
+  if (refused) {
+    deferred_ = BNX_ERR_UNSUPPORTED;
+    deferred_msg_ = "insert: more than 2^32 ray chunks in one scan (that scan was dropped, the others are applied)";
   }
   return BNX_OK;
 }
@@ -1671,13 +1713,13 @@ int Map::shard_begin(const void* points, i64 stride_bytes, i64 n, bool f64, u32 
         for (auto& st : x_stage_) BNX_TRY(st.reserve(need));
         x_stage_bytes_ = x_stage_[0].bytes;
       }
-      BNX_CUDA(cudaMemcpyAsync(x_stage_[stage_slot].p, points, (size_t)n * stride_bytes, cudaMemcpyHostToDevice, copy_stream_));
+      BNX_CUDA(cudaMemcpyAsync(x_stage_[stage_slot].p, points, cloud_bytes(n, stride_bytes, f64), cudaMemcpyHostToDevice, copy_stream_));
       BNX_CUDA(cudaEventRecord(x_copied_[stage_slot], copy_stream_));
       BNX_CUDA(cudaStreamWaitEvent(s, x_copied_[stage_slot], 0));
       d_points = x_stage_[stage_slot].p;
     } else {
       BNX_TRY(b_pts_.reserve((size_t)n * stride_bytes));
-      BNX_CUDA(cudaMemcpyAsync(b_pts_.p, points, (size_t)n * stride_bytes, cudaMemcpyHostToDevice, s));
+      BNX_CUDA(cudaMemcpyAsync(b_pts_.p, points, cloud_bytes(n, stride_bytes, f64), cudaMemcpyHostToDevice, s));
       d_points = b_pts_.p;
     }
   }
@@ -1789,6 +1831,7 @@ int Map::shard_resolve_mark(const void* recv_records, void* send_leaves, i64 cap
   t2_clean_ = lean;
   p.clean16 = lean ? 1u : 0u;
   ++shard_attempt_;
+  ++shard_stats[0];
   const GridDev g = grid.dev(), gs = scratch_->dev();
   // a rank receives about one slice worth of records; the kernels loop if it is (much) more
   const int rblocks = blocks_for(std::min<i64>(slots, 2 * (i64)p.rec_cap));
@@ -1843,10 +1886,7 @@ int Map::shard_finish(const void* flags_reduced, int* retry) {
   }
   if (any_pool | any_ovf) {
     // some rank ran short: nobody applied. Every rank drops this attempt's marks; the short ones grow.
-    if (any_ovf & OVF_CHUNKS) {
-      set_error("insert: more than 2^32 ray chunks in one scan");
-      return BNX_ERR_UNSUPPORTED;
-    }
+    ++shard_stats[4];
     if (++shard_retries_ > 48) {
       set_error("sharded insert: node pools could not be grown enough for this scan");
       return BNX_ERR_NOMEM;
@@ -1860,6 +1900,10 @@ int Map::shard_finish(const void* flags_reduced, int* retry) {
     GridCounters sgc;
     BNX_TRY(scratch_->read_counters(&sgc));
     if (sgc.error) BNX_TRY(scratch_->recover(sgc));
+    if (any_ovf & OVF_CHUNKS) {  // refused on every rank (the flags are reduced); the shards are unchanged and clean
+      set_error("insert: more than 2^32 ray chunks in one scan");
+      return BNX_ERR_UNSUPPORTED;
+    }
     if (st.overflow & OVF_TILES) {
       const u64 chunks = st.ray_chunk & CHUNK_FIELD;
       BNX_TRY(b_tiles_.reserve((size_t)(chunks / 32 + 64) * 4));
@@ -1878,6 +1922,8 @@ int Map::shard_finish(const void* flags_reduced, int* retry) {
   counters[6] = (i64)(st.ray_chunk >> 40);
   counters[7] = (i64)(st.ray_chunk & CHUNK_FIELD);
   if (++update_count == 4) update_count = 1;
+  ++shard_stats[7];
+  note_leaf_fill(st.gate_fill);
   GridCounters sgc;
   BNX_TRY(scratch_->read_counters(&sgc));
   BNX_TRY(scratch_->maintain(sgc));
@@ -1974,10 +2020,20 @@ int Map::p2p_attach(const void* handles, void* const* local_ptrs) {
 // native driver: every rank (re)creates its mailbox and the IPC handles travel through one NCCL all-gather.
 // Collective: all ranks call it at the same point of the protocol with the same capacities.
 int Map::p2p_collective_setup(i64 cap_records, i64 cap_leaves) {
-  const NcclApi& api = nccl_api(nullptr);
   cudaStream_t s = grid.stream();
   unsigned char mine[64];
   BNX_TRY(p2p_alloc(cap_records, cap_leaves, mine, nullptr));
+  ++shard_stats[2];
+  shard_stats[5] = cap_leaves;
+  if (host_gather_) {
+    std::vector<unsigned char> all((size_t)world_ * 64);
+    if (host_gather_(host_gather_ctx_, mine, all.data(), 64) != 0) {
+      set_error("sharded map: the caller's all-gather failed while exchanging the mailbox handles");
+      return BNX_ERR_CUDA;
+    }
+    return p2p_attach(all.data(), nullptr);
+  }
+  const NcclApi& api = nccl_api(nullptr);
   BNX_TRY(x_handles_.reserve((size_t)world_ * 64));
   BNX_CUDA(cudaMemcpyAsync(x_handles_.as<unsigned char>() + (size_t)rank_ * 64, mine, 64, cudaMemcpyHostToDevice, s));
   BNX_NCCL(api, api.AllGather(x_handles_.as<unsigned char>() + (size_t)rank_ * 64, x_handles_.p, 64, ncclChar, static_cast<ncclComm_t>(comm_), s));
@@ -2021,6 +2077,25 @@ int Map::shard_comm_init(const char* nccl_path, const void* unique_id128, int ra
   return BNX_OK;
 }
 
+int Map::shard_host_init(int rank, int world, AllGatherFn fn, void* ctx) {
+  BNX_REQUIRE(fn != nullptr, "shard_host_init: null all-gather callback");
+  BNX_REQUIRE(world >= 2 && world <= MAX_PEERS, "shard_host_init: 2..16 ranks");
+  BNX_TRY(shard_config(rank, world));
+  host_gather_ = fn;
+  host_gather_ctx_ = ctx;
+  want_p2p_ = true;
+  BNX_TRY(x_flags_.reserve(64));
+  return BNX_OK;
+}
+
+// the leaf inboxes are doubled as soon as a scan filled one of them half way (decided from a value that is the same on
+// every rank, at a point every rank reaches with the same scans behind it: the mailboxes are replaced collectively by
+// the next insert), so that an overflow — a frozen pipeline and a synchronous replay — stays the exception
+void Map::note_leaf_fill(u32 fill) {
+  shard_stats[6] = std::max<i64>(shard_stats[6], fill);
+  while ((i64)fill * 2 > cap_leaf_) cap_leaf_ *= 2;
+}
+
 // block o of `send` goes to rank o, block r of `recv` comes from rank r: grouped ncclSend/ncclRecv over NVLink
 int Map::all_to_all(const void* send, void* recv, size_t block_bytes) {
   const NcclApi& api = nccl_api(nullptr);
@@ -2037,7 +2112,7 @@ int Map::all_to_all(const void* send, void* recv, size_t block_bytes) {
 
 int Map::shard_insert(const void* points, i64 stride_bytes, i64 n, bool f64, u32 index_base, i64 n_max, const double origin[3], double max_range,
                       int where, bool async) {
-  BNX_REQUIRE(comm_ != nullptr && world_ > 1, "shard_insert: call shard_comm_init first");
+  BNX_REQUIRE((comm_ != nullptr || host_gather_ != nullptr) && world_ > 1, "shard_insert: call shard_comm_init / shard_host_init first");
   BNX_REQUIRE(n_max >= n, "shard_insert: n_max must be the largest slice of the scan over all ranks");
   const NcclApi& api = nccl_api(nullptr);
   cudaStream_t s = grid.stream();
@@ -2137,8 +2212,11 @@ int Map::shard_drain() {
     done = 0;
     while (done < q.size() && q[done].async_id != gc.failed_id) ++done;
   }
+  ++shard_stats[3];
+  shard_stats[7] += (i64)done;
   for (size_t k = 0; k < done; ++k) {
     const AsyncRecord& r = h_ring_[q[k].async_id & (RING - 1)];
+    drain_max_fill_ = std::max(drain_max_fill_, r.leaf_fill);
     counters[0] = q[k].n;
     counters[1] = r.n_endpoints;
     counters[2] = (i64)r.sum_m;
@@ -2149,12 +2227,15 @@ int Map::shard_drain() {
     counters[7] = (i64)(r.ray_chunk & CHUNK_FIELD);
     for (int j = 0; j < 4; ++j) totals[j] += counters[j];
   }
+  note_leaf_fill(drain_max_fill_);  // the records carry the max over ranks: every rank takes the same decision here
+  drain_max_fill_ = 0;
   GridCounters sgc;
   BNX_TRY(scratch_->read_counters(&sgc));
   if (!gc.error) {
     BNX_TRY(scratch_->maintain(sgc));
     return grid.maintain(gc);
   }
+  ++shard_stats[1];
   if (gc.error & ERR_PEER) {
     set_error("sharded insert: a peer rank did not reach an exchange point in time");
     return BNX_ERR_CUDA;
@@ -2162,10 +2243,6 @@ int Map::shard_drain() {
   // every rank is frozen at the same scan (the flags were all-reduced): drop its marks, grow what was short on
   // this rank, then replay the rest of the queue with synchronous (collective) inserts
   const ScanCounters st = *h_status_;
-  if ((st.overflow | gc.failed_ovf) & OVF_CHUNKS) {
-    set_error("insert: more than 2^32 ray chunks in one scan");
-    return BNX_ERR_UNSUPPORTED;
-  }
   if (st.n_touched) {
     note_launch(), k_clear_touched<<<sm_count() * 8, TPB, 0, s>>>(grid.dev(), buf_, std::min<u32>(st.n_touched, (u32)(b_touched_.bytes / 4)));
     BNX_CUDA(cudaGetLastError());
@@ -2173,6 +2250,10 @@ int Map::shard_drain() {
   }
   BNX_TRY(grid.recover(gc));
   if (sgc.error) BNX_TRY(scratch_->recover(sgc));
+  if ((st.overflow | gc.failed_ovf) & OVF_CHUNKS) {  // refused on every rank; the scans queued behind it are dropped with it
+    set_error("insert: more than 2^32 ray chunks in one scan");
+    return BNX_ERR_UNSUPPORTED;
+  }
   if ((st.overflow | gc.failed_ovf) & OVF_TILES) {
     const u64 chunks = st.ray_chunk & CHUNK_FIELD;
     BNX_TRY(b_tiles_.reserve((size_t)(std::max<u64>(chunks, b_tiles_.bytes / 4 * 32) * 2 / 32 + 64) * 4));

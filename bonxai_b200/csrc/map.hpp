@@ -61,7 +61,7 @@ struct ScanCounters {
   u32 done1, done2;              // last-block tickets of the two producing kernels
   u32 gate_pool, gate_ovf;       // sharded: the reduced error flags the apply pass acted on
   u32 done3;                     // last-block ticket of the merge kernel
-  u32 pad_;
+  u32 gate_fill;                 // sharded: fullest leaf-record block of the scan over all ranks
 };
 static_assert(sizeof(ScanCounters) % 16 == 0, "cleared in 16-byte units");
 
@@ -71,7 +71,8 @@ struct AsyncRecord {
   u32 n_endpoints, n_changed, n_touched, n_points;
   unsigned long long sum_m, ray_chunk;
   u32 n_dropped;
-  u32 pad[2];
+  u32 leaf_fill;  // sharded: fullest leaf-record block of the scan over all ranks (same value on every rank)
+  u32 pad;
   volatile u32 id;  // written last
 };
 static_assert(sizeof(AsyncRecord) == 64, "one record per 64 bytes");
@@ -108,6 +109,7 @@ class Map {
     for (int k = 0; k < 12; ++k) next_T_[k] = T16[k];
     use_next_T_ = true;
   }
+  void clear_next_transform() { use_next_T_ = false; }
 
   // ---- root-key sharding across processes (one map shard per GPU), as stages: with caller-owned exchange buffers the
   // caller moves them between the stages; with mailboxes attached (NULL buffers) the kernels exchange by themselves.
@@ -131,12 +133,20 @@ class Map {
   int p2p_alloc(i64 cap_records, i64 cap_leaves, void* ipc_handle64, void** local_ptr);
   int p2p_attach(const void* handles, void* const* local_ptrs);
   int exchange_kind() const { return p2p_ready_ ? 2 : (comm_ ? 1 : 0); }  // 0 caller, 1 NCCL, 2 peer memory
+  // bootstrap without NCCL: the caller supplies the all-gather that hands the 64-byte mailbox handles around (any
+  // transport: gloo, MPI, a socket). fn(ctx, send, recv, bytes_per_rank) gathers `bytes_per_rank` bytes of HOST memory
+  // from every rank into recv[world][bytes_per_rank]; it is collective. Peer memory is the only exchange then.
+  typedef int (*AllGatherFn)(void* ctx, const void* send, void* recv, i64 bytes_per_rank);
+  int shard_host_init(int rank, int world, AllGatherFn fn, void* ctx);
+  // what the sharded pipeline really did: {resolve_mark attempts, frozen-pipeline replays, mailbox (re)creations,
+  // collective drains, synchronous retries, leaf-inbox capacity, largest leaf-inbox fill seen, scans inserted}
+  i64 shard_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   i64 mailbox_cap(int which) const { return which ? mbox_cap_leaf_ : mbox_cap_rec_; }
 
   // ---- pipelined insert: enqueue a scan and return; drain() completes everything queued (growing pools and
   // replaying from the first scan that ran short, if any). Input buffers must stay valid until drain().
   int insert_async(const void* points, i64 stride_bytes, i64 n, bool f64, const double origin[3], double max_range, int where);
-  int drain();
+  int drain(bool report = true);
   i64 totals[4] = {0, 0, 0, 0};  // cumulative N, E, V, U over every scan inserted so far
   int query(const i32* xyz, i64 n, int kind, u8* out, int where);
 
@@ -193,6 +203,9 @@ class Map {
     int where;
   };
   std::vector<Queued> queue_;
+  int drain_queue();
+  int deferred_ = BNX_OK;  // error of a pipelined scan that was refused, reported by the next synchronising call
+  std::string deferred_msg_;
   AsyncRecord* h_ring_ = nullptr;  // pinned + mapped: one record per scan, written by the device
   AsyncRecord* d_ring_ = nullptr;
   u32 async_next_ = 0;
@@ -224,9 +237,13 @@ class Map {
   int shard_drain();
   // NCCL: bootstrap of the mailboxes, and the exchange itself with BNX_SHARD_EXCHANGE=nccl
   void* comm_ = nullptr;  // ncclComm_t
+  AllGatherFn host_gather_ = nullptr;  // caller-supplied bootstrap (instead of NCCL)
+  void* host_gather_ctx_ = nullptr;
+  u32 drain_max_fill_ = 0;  // largest leaf-inbox fill (max over ranks, so equal on every rank) since the last drain
   DevBuf x_send1_, x_recv1_, x_send2_, x_recv2_, x_flags_, x_handles_;
-  i64 cap_rec_ = 0, cap_leaf_ = 1 << 13;
+  i64 cap_rec_ = 0, cap_leaf_ = 1 << 16;  // 80-B leaf records per sender block; doubled at a collective drain when half full
   int all_to_all(const void* send, void* recv, size_t block_bytes);
+  void note_leaf_fill(u32 fill);
   // peer-memory exchange
   int p2p_collective_setup(i64 cap_records, i64 cap_leaves);
   void p2p_close_peers();

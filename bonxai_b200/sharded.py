@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import sys
 
 import numpy as np
 
@@ -134,7 +135,10 @@ class ShardedMap:
     """one rank of a map sharded over torch.distributed ranks (one process per GPU). torch.distributed is only used to
     hand the NCCL unique id around; the per-scan exchanges are issued by the library itself (bnx_map_shard_insert)."""
 
-    def __init__(self, resolution: float, group=None):
+    def __init__(self, resolution: float, group=None, bootstrap: str = "nccl"):
+        """bootstrap="nccl": the mailbox handles travel through one NCCL all-gather issued by the library (needs one GPU
+        per rank); bootstrap="host": through torch.distributed.all_gather on `group` (any backend, e.g. gloo) handed to
+        the library as a callback (bnx_map_shard_host_init) — ranks may then share a GPU."""
         import torch
         import torch.distributed as dist
         self.torch, self.dist, self.group = torch, dist, group
@@ -143,6 +147,23 @@ class ShardedMap:
         self.map = capi.ProbabilisticMap(resolution)
         self.lib = self.map.lib
         self.map.set_stream(torch.cuda.current_stream().cuda_stream)
+        if bootstrap == "host":
+            world = self.world
+
+            def gather(ctx, send, recv, nbytes):
+                try:
+                    mine = torch.frombuffer(bytearray(C.string_at(send, nbytes)), dtype=torch.uint8)
+                    parts = [torch.empty(nbytes, dtype=torch.uint8) for _ in range(world)]
+                    dist.all_gather(parts, mine, group=group)
+                    C.memmove(recv, b"".join(bytes(p.tolist()) for p in parts), nbytes * world)
+                    return 0
+                except Exception as e:  # noqa: BLE001
+                    print("bootstrap all-gather failed:", repr(e), file=sys.stderr)
+                    return 1
+
+            self._gather_cb = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64)(gather)  # keep alive
+            capi._check(self.lib.bnx_map_shard_host_init(self.map.h, self.rank, self.world, self._gather_cb, None))
+            return
         path = nccl_library_path().encode()
         uid = torch.zeros(128, dtype=torch.uint8)
         if self.rank == 0:
@@ -181,6 +202,21 @@ class ShardedMap:
 
     def totals(self):
         return self.map.totals()
+
+    def stats(self):
+        """what the sharded pipeline really did (bnx_map_shard_stats)"""
+        return self.map.shard_stats()
+
+    def digest(self):
+        """digest of the WHOLE map (all shards): collective — (sum, xor, count) combined over the ranks"""
+        s, x, c = self.map.digest()
+        # 64-bit values travel as pairs of 32-bit halves (no unsigned 64-bit reductions in torch.distributed)
+        t = self.torch.tensor([s & 0xFFFFFFFF, s >> 32, x & 0xFFFFFFFF, x >> 32, c], dtype=self.torch.int64)
+        if self.dist.get_backend(self.group) == "nccl":
+            t = t.cuda()
+        parts = [self.torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(parts, t, group=self.group)
+        return capi.combine_digests([(int(p[0]) | (int(p[1]) << 32), int(p[2]) | (int(p[3]) << 32), int(p[4])) for p in parts])
 
 
 class LocalShardGroup:

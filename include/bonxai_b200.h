@@ -106,6 +106,12 @@ BNX_API int bnx_grid_is_on(bnx_grid_t* g, const int32_t* xyz, int64_t n, uint8_t
 
 /* activeCellsCount, bonxai.hpp:689-701 */
 BNX_API int bnx_grid_active_count(bnx_grid_t* g, int64_t* count);
+/* Order-independent digest of what forEachCell (bonxai.hpp:704-743) would visit: out = {sum, xor, count} over all ON
+ * cells of mix64(hash3(x, y, z) + FNV1a64(value bytes) * 0x9E3779B97F4A7C15) (arithmetic mod 2^64; the functions are
+ * spelled out in tests/digest.py). Two grids hold the same (coord, value) set iff their digests agree (up to a 2^-64
+ * collision); the digests of disjoint shards combine by + / ^ / +. Lets full-size maps be compared with the oracle or
+ * across GPUs without copying them to the host. */
+BNX_API int bnx_grid_digest(bnx_grid_t* g, uint64_t out[3]);
 /* forEachCell, bonxai.hpp:704-743: all ON cells as (coord, value) pairs in unspecified order (the
  * reference's order is unordered_map order). *count always receives the number of ON cells; when
  * cap < *count nothing is written and BNX_ERR_CAPACITY is returned. xyz/values may be NULL to count. */
@@ -269,6 +275,18 @@ BNX_API int bnx_map_shard_insert(bnx_map_t* m, const void* points, int64_t strid
 BNX_API int bnx_map_shard_p2p_alloc(bnx_map_t* m, int64_t cap_records, int64_t cap_leaves, void* ipc_handle64, void** device_ptr);
 BNX_API int bnx_map_shard_p2p_attach(bnx_map_t* m, const void* ipc_handles, void* const* device_ptrs);
 BNX_API int bnx_map_shard_exchange(const bnx_map_t* m, int* kind);
+/* Bootstrap without NCCL (instead of bnx_nccl_unique_id + bnx_map_shard_comm_init): the caller supplies the collective
+ * that hands the 64-byte mailbox handles around — allgather(ctx, send, recv, bytes) must gather `bytes` bytes of HOST
+ * memory from every rank into recv[world][bytes] and return 0 (any transport: gloo, MPI, a socket). Peer memory is then
+ * the only exchange. Ranks may share one GPU (CUDA IPC works between processes on the same device), which is how the
+ * multi-process protocol is tested on a single-GPU box. */
+typedef int (*bnx_allgather_fn)(void* ctx, const void* send, void* recv, int64_t bytes_per_rank);
+BNX_API int bnx_map_shard_host_init(bnx_map_t* m, int rank, int world, bnx_allgather_fn allgather, void* ctx);
+/* What the sharded pipeline of this rank really did so far: {resolve_mark attempts, frozen-pipeline replays, mailbox
+ * (re)creations, collective drains, synchronous retries, leaf-inbox capacity (records per sender), fullest leaf-inbox
+ * block seen (max over ranks), scans completed}. A healthy run has attempts == scans, replays == retries == 0 and ONE
+ * mailbox creation. */
+BNX_API int bnx_map_shard_stats(bnx_map_t* m, int64_t out[8]);
 
 #ifdef __cplusplus
 }

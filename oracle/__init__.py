@@ -135,6 +135,17 @@ class OracleLib:
         return OracleMap(self, resolution)
 
 
+def digest_pairs(xyz: np.ndarray, words: np.ndarray):
+    """(sum, xor, count) digest of an unsorted dump of 4-byte cells — the C spelling of bnx_grid_digest (a helper of
+    the port library; capi.digest_of_dump is the numpy spelling, tests/test_digest.py the plain-Python one)"""
+    lib = C.CDLL(PORT_SO)
+    xyz = np.ascontiguousarray(xyz, np.int32)
+    words = np.ascontiguousarray(words).view(np.uint32)
+    out = (C.c_uint64 * 3)()
+    lib.orc_digest_pairs(_ptr(xyz, _i32p), _ptr(words, _u32p), C.c_int64(len(words)), out)
+    return int(out[0]), int(out[1]), int(out[2])
+
+
 def sort_dump(xyz: np.ndarray, vals: np.ndarray):
     """Canonical order for comparing forEachCell dumps (the reference's order is unspecified)."""
     if len(xyz) == 0:
@@ -207,6 +218,9 @@ class OracleGrid:
         got = self.o.lib.orc_grid_dump(self.h, _ptr(xyz, _i32p), _ptr(vals, _u32p), n)
         assert got == n
         return sort_dump(xyz, vals) if sort else (xyz, vals)
+
+    def digest(self):
+        return digest_pairs(*self.dump(sort=False))
 
     def clear(self, opt: int):
         self.o.lib.orc_grid_clear(self.h, opt)
@@ -297,6 +311,9 @@ class OracleMap:
         got = self.o.lib.orc_map_dump(self.h, _ptr(xyz, _i32p), _ptr(words, _u32p), n)
         assert got == n
         return sort_dump(xyz, words) if sort else (xyz, words)
+
+    def digest(self):
+        return digest_pairs(*self.dump(sort=False))
 
     def counters(self):
         a = (C.c_int64 * 4)()

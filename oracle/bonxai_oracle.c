@@ -640,3 +640,32 @@ void orc_map_track_updates(void* mp, int enable) {
   (void)enable; /* always counted */
 }
 double orc_map_last_insert_seconds(void* mp) { return ((PMap*)mp)->last_seconds; }
+
+/* ---- test helper, not a restatement of anything in the reference: the order-independent digest of a dump
+ * ({sum, xor, count} of mix64(hash3(x,y,z) + FNV1a64(word bytes) * 0x9E3779B97F4A7C15), see include/bonxai_b200.h
+ * bnx_grid_digest) so that full-size maps of either oracle can be compared with the GPU's without sorting. */
+static uint64_t dg_mix64(uint64_t h) {
+  h ^= h >> 33;
+  h *= 0xFF51AFD7ED558CCDull;
+  h ^= h >> 33;
+  h *= 0xC4CEB9FE1A85EC53ull;
+  h ^= h >> 33;
+  return h;
+}
+void orc_digest_pairs(const int32_t* xyz, const uint32_t* words, int64_t n, uint64_t out[3]) {
+  uint64_t sum = 0, x = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    uint64_t h = (uint64_t)(uint32_t)xyz[3 * i] * 0x9E3779B97F4A7C15ull;
+    h ^= (uint64_t)(uint32_t)xyz[3 * i + 1] * 0xC2B2AE3D27D4EB4Full + (h >> 29);
+    h ^= (uint64_t)(uint32_t)xyz[3 * i + 2] * 0x165667B19E3779F9ull + (h << 7);
+    h = dg_mix64(h);
+    uint64_t f = 0xCBF29CE484222325ull;
+    for (int k = 0; k < 4; ++k) f = (f ^ ((words[i] >> (8 * k)) & 0xFFu)) * 0x100000001B3ull;
+    h = dg_mix64(h + f * 0x9E3779B97F4A7C15ull);
+    sum += h;
+    x ^= h;
+  }
+  out[0] = sum;
+  out[1] = x;
+  out[2] = (uint64_t)n;
+}

@@ -97,6 +97,10 @@ void orc_map_track_updates(void* m, int enable);
  * bonxai_map/benchmark/benchmark_kitti.cpp:146-152) */
 double orc_map_last_insert_seconds(void* m);
 
+/* test helper (port library only): order-independent digest {sum, xor, count} of n (coord, 4-byte word) pairs, the
+ * function bnx_grid_digest computes on the device (include/bonxai_b200.h) */
+void orc_digest_pairs(const int32_t* xyz, const uint32_t* words, int64_t n, uint64_t out[3]);
+
 #ifdef __cplusplus
 }
 #endif

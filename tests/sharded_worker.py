@@ -17,10 +17,18 @@ from bonxai_b200.sharded import ShardedMap, split_points  # noqa: E402
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    # BNX_SHARD_BOOTSTRAP=host: the processes find each other over gloo and hand the mailbox handles to the library
+    # through a callback, so the ranks may share GPUs (CUDA IPC between processes on one device): the same mailbox
+    # kernels, ld.acquire.sys / st.release.sys stamps and freeze + replay logic as on an NVLink box
+    host = os.environ.get("BNX_SHARD_BOOTSTRAP", "nccl") == "host"
+    local = local % torch.cuda.device_count()
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if host:
+        dist.init_process_group("gloo")
+    else:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     mode = os.environ.get("BNX_SHARD_TEST_MODE", "sync")
-    sm = ShardedMap(0.1)
+    sm = ShardedMap(0.1, bootstrap="host" if host else "nccl")
     if rank == 0:
         import oracle
         om = oracle.load("port").map(0.1)
@@ -54,9 +62,16 @@ def main():
             assert np.array_equal(gx[order], ox) and np.array_equal(gw[order], ow), f"scan {scan}: sharded map differs from the oracle"
     want = os.environ.get("BNX_SHARD_EXCHANGE", "p2p")
     assert sm.exchange_kind() == want, (sm.exchange_kind(), want)
+    # the digest of the sharded map (combined over the ranks on the device side) equals the digest of the oracle's dump
+    dig = sm.digest()
+    if rank == 0:
+        assert dig == capi.digest_of_dump(*om.dump()), "digest of the sharded map differs from the oracle's"
+    st = sm.stats()
+    if os.environ.get("BNX_EXPECT_REPLAY") == "1":
+        assert st["replays"] + st["sync_retries"] > 0, st
     dist.barrier()
     if rank == 0:
-        print("SHARDED_OK", world, sm.exchange_kind())
+        print("SHARDED_OK", world, sm.exchange_kind(), st)
     dist.destroy_process_group()
 
 

@@ -233,7 +233,77 @@ def test_lidar_sequence(bnx, port):
         gm.insert(pts, origin, 50.0)
         om.insert(pts, origin, 50.0)
         check_scan(gm, om, f"lidar scan {scan}")
-    assert gm.counters()["retries"] == 0 or True
+        assert gm.counters()["retries"] == 0, "the default pools must hold a LiDAR scan without a retry"
+
+
+def test_non_finite_points_are_dropped(bnx, any_oracle):
+    """NaN / inf coordinates are undefined behaviour in the reference ((int32)floor(NaN)); its callers filter them
+    (bonxai_ros/src/bonxai_server.cpp:148-154). Here they leave the cloud inside the classify kernel, in every input
+    flavour: the result equals the oracle fed with the filtered cloud (the order of the survivors is unchanged)."""
+    rng = np.random.default_rng(17)
+    for layout in ("f32x3", "f32x4", "f64"):
+        pts = rng.normal(0, 2.0, (6000, 3))
+        bad = rng.choice(6000, 300, replace=False)
+        pts[bad[:100], 0] = np.nan
+        pts[bad[100:200], 1] = np.inf
+        pts[bad[200:], 2] = -np.inf
+        pts[0] = pts[1]  # a duplicate voxel whose first point survives
+        if layout == "f64":
+            cloud = pts.copy()
+        else:
+            cloud = np.zeros((6000, 3 if layout == "f32x3" else 4), np.float32)
+            cloud[:, :3] = pts
+        good = np.isfinite(cloud[:, :3]).all(axis=1)
+        gm, om = bnx.ProbabilisticMap(0.1), any_oracle.map(0.1)
+        for k in range(2):
+            gm.insert(cloud, [0.05 * k, 0, 0], 4.0)
+            om.insert(np.ascontiguousarray(cloud[good]), [0.05 * k, 0, 0], 4.0)
+            check_scan(gm, om, f"{layout} scan {k}")
+        assert gm.counters()["N"] == int(good.sum())
+        gm.insert_async(cloud, [0.2, 0, 0], 4.0)
+        om.insert(np.ascontiguousarray(cloud[good]), [0.2, 0, 0], 4.0)
+        check_scan(gm, om, f"{layout} pipelined", counters=False)
+
+
+def test_refused_scan_leaves_the_map_clean(bnx, port):
+    """a ray of more chunks than the scan counters can hold (max_range = inf and one far-away garbage point) is refused
+    with BNX_ERR_UNSUPPORTED; the marks its first phases left behind must not leak into later scans, and scans queued
+    behind it in the pipeline are still applied"""
+    rng = np.random.default_rng(23)
+    inf = float("inf")
+    good = rng.normal(0, 2.0, (70000, 3)).astype(np.float32)
+    bad = good.copy()
+    bad[5] = [3.0e7, 1.0e7, 0.0]  # 3e8 cells at 0.1 m: more than 2^40 / 70000 chunks of 8 cells
+    nxt = rng.normal(0, 2.0, (50000, 3)).astype(np.float32)
+    empty = np.zeros((0, 3), np.float32)
+    # synchronous call: the refused scan does not consume an update id
+    gm, om = bnx.ProbabilisticMap(0.1), port.map(0.1)
+    gm.insert(good, [0, 0, 0], inf)
+    om.insert(good, [0, 0, 0], inf)
+    with pytest.raises(bnx.BonxaiError) as err:
+        gm.insert(bad, [0, 0, 0], inf)
+    assert err.value.status == 5
+    check_scan(gm, om, "right after the refused scan", counters=False)
+    for k in range(3):
+        gm.insert(nxt, [0.1 * k, 0, 0], 6.0)
+        om.insert(nxt, [0.1 * k, 0, 0], 6.0)
+        check_scan(gm, om, f"scan {k} after the refused one")
+    # pipelined call: the refused scan has consumed its update id (an empty insert does the same to the oracle); the
+    # scan queued behind it is applied; the error is reported by the next synchronising call
+    gm, om = bnx.ProbabilisticMap(0.1), port.map(0.1)
+    gm.insert_async(good, [0, 0, 0], inf)
+    gm.insert_async(bad, [0, 0, 0], inf)
+    gm.insert_async(nxt, [0.3, 0, 0], inf)
+    with pytest.raises(bnx.BonxaiError) as err:
+        gm.sync()
+    assert err.value.status == 5
+    om.insert(good, [0, 0, 0], inf)
+    om.insert(empty, [0, 0, 0], 1.0)
+    om.insert(nxt, [0.3, 0, 0], inf)
+    check_scan(gm, om, "pipeline with a refused scan in the middle", counters=False)
+    gm.insert(nxt, [0.1, 0, 0], 6.0)
+    om.insert(nxt, [0.1, 0, 0], 6.0)
+    check_scan(gm, om, "scan after the refused one (pipelined)")
 
 
 def test_depth_scan_reduced(bnx, port):

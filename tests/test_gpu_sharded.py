@@ -82,6 +82,23 @@ def test_local_shard_group_growth_and_small_exchange_buffers(bnx, port, monkeypa
     assert g.attempts > 2  # pools and the leaf exchange buffer had to grow
 
 
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("mode,tiny", [("sync", False), ("async", False), ("async", True)])
+def test_processes_sharing_one_gpu(bnx, mode, tiny, world):
+    """the native driver (bnx_map_shard_insert) with one PROCESS per rank, all on GPU 0: mailboxes mapped through CUDA
+    IPC, arrival stamps with st.release.sys / ld.acquire.sys, handles all-gathered by a caller-supplied callback (gloo)
+    instead of NCCL (which refuses two ranks on one device). Synchronous, pipelined, and pipelined with pools so small
+    that a queued scan runs short and all ranks freeze + replay. The kernels of the processes time-slice the GPU, so
+    every exchange waits for a context switch: slow, but it is the protocol of the NVLink box."""
+    env = dict(os.environ, BNX_SHARD_TEST_MODE=mode, BNX_SHARD_BOOTSTRAP="host", BNX_SHARD_EXCHANGE="p2p", BNX_PEER_TIMEOUT_MS="120000")
+    if tiny:
+        env.update(BNX_INIT_LEAF_MB="2", BNX_INIT_INNER_MB="0", BNX_EXPECT_REPLAY="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+                        "--master-port", str(29621 + world), os.path.join(ROOT, "tests", "sharded_worker.py")], capture_output=True, text=True, timeout=900,
+                       env=env)
+    assert r.returncode == 0 and "SHARDED_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
 @pytest.mark.parametrize("exchange", ["p2p", "nccl"])
 @pytest.mark.parametrize("mode,tiny", [("sync", False), ("async", False), ("async", True)])
 def test_nccl_two_ranks(bnx, mode, tiny, exchange):
