@@ -167,6 +167,33 @@ def time_cpu(scans, warmup: int):
     return total, len(scans) - warmup, kind, capi.digest_of_dump(*m.dump())
 
 
+def run_dropin(scans, warmup: int):
+    """e2e through the drop-in C++ headers: tools/cpp/dropin_bench.cpp (built against include/ + the library) inserts the
+    same scans with the reference's own call, Bonxai::ProbabilisticMap::insertPointCloud(std::vector<PointXYZ>, origin,
+    max_range), synchronously, from a pageable std::vector and from a PinnedAllocator vector, and with the publisher's
+    post-step after every insert (bonxai_ros/src/bonxai_server.cpp:176-186,217-251). Separate process, own CUDA context."""
+    import tempfile
+    from bonxai_b200 import build as b
+    try:
+        exe = b.build_tools()
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": f"could not build tools/cpp/dropin_bench.cpp: {e!r}"}
+    out = {}
+    with tempfile.NamedTemporaryFile(suffix=".bin", dir="/tmp") as f:
+        f.write(np.array([len(scans), len(scans[0][0])], np.int64).tobytes())
+        for pts, origin in scans:
+            f.write(np.asarray(origin, np.float32).tobytes())
+            f.write(np.ascontiguousarray(pts, np.float32).tobytes())
+        f.flush()
+        for mode in ("vector", "pinned", "publish", "publish_ref"):
+            r = subprocess.run([exe, f.name, repr(RES), repr(MAX_RANGE), str(warmup), mode], capture_output=True, text=True, timeout=600)
+            if r.returncode != 0:
+                out[mode] = {"error": (r.stderr or r.stdout)[-300:]}
+                continue
+            out[mode] = json.loads(r.stdout.strip().splitlines()[-1])
+    return out
+
+
 REFERENCE_BUDGET_S = 60.0  # CPU seconds of timed inserts the reference arm may spend (the sample is bounded, the per-step rate is not)
 
 
@@ -411,6 +438,16 @@ def run_gpu(args):
             line["parity_in_run"] = bool(dig_gpu == dig_cpu)
             line["parity"] = {"scans": n_cpu, "oracle": kind, "active_cells": dig_gpu[2], "gpu_digest_equals_oracle": dig_gpu == dig_cpu,
                               "passes_agree": bool(digests_agree)}
+            if not args.no_dropin:
+                dd = run_dropin(scans, W)
+                line["e2e_dropin"] = {
+                    "call": "Bonxai::ProbabilisticMap::insertPointCloud(std::vector<PointXYZ>, origin, max_range) through include/ (C++), "
+                            "synchronous per scan, separate process",
+                    "pageable_vector": dd.get("vector"), "pinned_allocator_vector": dd.get("pinned"),
+                    "ratio_to_pipelined_step": (dd["pinned"]["us_per_scan"] / (1e3 * ms_max / K)) if "us_per_scan" in dd.get("pinned", {}) else None}
+                line["e2e_insert_publish"] = {
+                    "call": "insertPointCloud + the publisher post-step after EVERY scan (bonxai_server.cpp:176-186,217-251)",
+                    "fused_publish_occupied_f32": dd.get("publish"), "reference_style_getOccupiedVoxels_loop": dd.get("publish_ref")}
             line["cpu_baseline"] = {"value": n * N_PTS / secs_cpu, "unit": "points/s", "cores": 1, "kind": kind,
                                     "sample": f"scans 2..{n_cpu - 1} of the same sequence ({n} scans, {secs_cpu:.1f} s), single thread",
                                     "ms_per_step": 1e3 * secs_cpu / n}
@@ -665,6 +702,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-scans", type=int, default=60, help="scans timed for the cpu_baseline (about 10-15 s)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-dropin", action="store_true", help="skip the C++ drop-in arm (e2e_dropin / e2e_insert_publish)")
     ap.add_argument("--mode", default="sharded", choices=["sharded", "replicas"],
                     help="N > 1: one root-key-sharded map (default) or N independent maps")
     args = ap.parse_args()

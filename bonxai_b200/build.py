@@ -61,5 +61,21 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+DROPIN_BENCH = os.path.join(ROOT, "build", "dropin_bench")
+
+
+def build_tools(force: bool = False) -> str:
+    """the C++ caller bench.py times for `e2e_dropin` (tools/cpp/dropin_bench.cpp against include/ + the library)"""
+    src = os.path.join(ROOT, "tools", "cpp", "dropin_bench.cpp")
+    deps = [src, LIB] + [os.path.join(dp, f) for dp, _, fs in os.walk(os.path.join(ROOT, "include")) for f in fs]
+    if not force and os.path.exists(DROPIN_BENCH) and all(os.path.getmtime(d) <= os.path.getmtime(DROPIN_BENCH) for d in deps):
+        return DROPIN_BENCH
+    os.makedirs(os.path.dirname(DROPIN_BENCH), exist_ok=True)
+    subprocess.run(["g++", "-std=c++17", "-O2", "-I", os.path.join(ROOT, "include"), src, "-L", PKG, "-lbonxai_b200",
+                    "-Wl,-rpath,$ORIGIN/../bonxai_b200", "-o", DROPIN_BENCH], check=True)
+    return DROPIN_BENCH
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_tools(force="--force" in sys.argv))

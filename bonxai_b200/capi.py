@@ -34,7 +34,7 @@ SYMBOLS = [
     "bnx_map_create", "bnx_map_destroy", "bnx_map_set_stream", "bnx_map_sync", "bnx_map_grid", "bnx_map_set_options",
     "bnx_map_get_options", "bnx_map_insert_f32", "bnx_map_insert_f64", "bnx_map_add_hit", "bnx_map_add_miss",
     "bnx_map_query", "bnx_map_get_voxels", "bnx_map_get_voxel_points", "bnx_map_counters", "bnx_map_update_count",
-    "bnx_map_set_profiling", "bnx_map_phase_times",
+    "bnx_map_set_profiling", "bnx_map_phase_times", "bnx_map_set_marking",
     "bnx_map_publish_occupied_f32", "bnx_map_insert_transformed_f32", "bnx_map_insert_async_f32", "bnx_map_insert_async_f64", "bnx_map_totals",
     "bnx_map_shard_config", "bnx_map_shard_begin", "bnx_map_shard_resolve_mark", "bnx_map_shard_merge", "bnx_map_shard_finish",
     "bnx_nccl_unique_id", "bnx_map_shard_comm_init", "bnx_map_shard_insert",
@@ -477,6 +477,10 @@ class ProbabilisticMap:
         v = C.c_int()
         _check(self.lib.bnx_map_update_count(self.h, C.byref(v)))
         return v.value
+
+    def set_marking(self, mode: str):
+        """"auto": dense window when the range allows it; "sparse": per-scan marks always inside the leaves"""
+        _check(self.lib.bnx_map_set_marking(self.h, {"auto": 0, "sparse": 1}[mode]))
 
     def set_profiling(self, enable=True):
         _check(self.lib.bnx_map_set_profiling(self.h, int(enable)))

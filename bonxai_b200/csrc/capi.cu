@@ -395,6 +395,11 @@ int bnx_map_update_count(const bnx_map_t* h, int* value) {
   *value = (int)h->m.update_count;
   return BNX_OK;
 }
+int bnx_map_set_marking(bnx_map_t* h, int mode) {
+  BNX_HANDLE(h);
+  DeviceGuard dg(h->m.grid.device);
+  return h->m.set_marking(mode);
+}
 int bnx_map_set_profiling(bnx_map_t* h, int enable) {
   BNX_HANDLE(h);
   h->m.profiling = enable != 0;

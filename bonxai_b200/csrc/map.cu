@@ -41,7 +41,7 @@ constexpr u32 CHUNK = 8;  // ray cells per work item
 #endif
 constexpr unsigned long long CHUNK_FIELD = (1ull << 40) - 1ull;
 constexpr u32 RING_SIZE = 1024;  // entries of the pipelined-insert record ring (Map::RING)
-constexpr u32 OVF_TILES = 1u, OVF_CHUNKS = 2u, OVF_RECORDS = 4u, OVF_LEAVES = 8u;
+constexpr u32 OVF_TILES = 1u, OVF_CHUNKS = 2u, OVF_RECORDS = 4u, OVF_LEAVES = 8u, OVF_WINDOW = 16u;
 
 inline int blocks_for(i64 n, int tpb = TPB) { return (int)std::max<i64>(1, ceil_div(n, tpb)); }
 
@@ -370,7 +370,17 @@ __device__ __forceinline__ u32 shard_table_mask(const ScanParams& p, u32 receive
 //         queued; it only needs its ray).
 // MODE 2: sharded map — one thread per received endpoint record (dense range over the [world][rec_cap] inbox);
 //         w = global point index << 1 | type, winner = lowest w of its voxel.
-template <int MODE>
+// dense window: index of the leaf block (lx, ly, lz) [voxel >> 3]; NONE if it lies outside (cannot happen for cells
+// within max_range of the origin: reported as an overflow, never written)
+__device__ __forceinline__ u32 dense_block(const ScanParams& p, int lx, int ly, int lz) {
+  const u32 bx = (u32)(lx - p.W0x), by = (u32)(ly - p.W0y), bz = (u32)(lz - p.W0z);
+  if (bx >= p.D || by >= p.D || bz >= p.D) return NONE;
+  return (bz * p.D + by) * p.D + bx;
+}
+
+// DENSE: the scan's marks (touched + hit bits) live in the dense window, not in the leaves: resolve only READS the map
+// (no leaf is created here; a voxel without a leaf is simply unknown, hence not stale).
+template <int MODE, bool DENSE>
 __global__ void __launch_bounds__(TPB) k_resolve(GridDev g, ScanParams p, ScanBuffers b, u32 count) {
   pdl_enter();
   constexpr bool PENDING = MODE == 1;
@@ -413,22 +423,22 @@ __global__ void __launch_bounds__(TPB) k_resolve(GridDev g, ScanParams p, ScanBu
     if (winner) {
       const u32 peers = __match_any_sync(want, e.x >> 3) & __match_any_sync(want, e.y >> 3) & __match_any_sync(want, e.z >> 3);
       const int leader = __ffs(peers) - 1;
-      if ((int)lane == leader) leaf = leaf_find_or_create(g, e.x, e.y, e.z);
+      if ((int)lane == leader) leaf = DENSE ? leaf_find(g, e.x, e.y, e.z) : leaf_find_or_create(g, e.x, e.y, e.z);
       leaf = __shfl_sync(peers, leaf, leader);
     }
   }
   if (winner) {
     bool stale = false;
     if (!PENDING) {
+      ci = ((u32)e.x & 7u) | (((u32)e.y & 7u) << 3) | (((u32)e.z & 7u) << 6);
       if (leaf != NONE) {
-        ci = ((u32)e.x & 7u) | (((u32)e.y & 7u) << 3) | (((u32)e.z & 7u) << 6);
         // mask word and cell are loaded together (one round trip); the cell only counts if its bit is on
         const u64 act = leaf_active(g, leaf)[ci >> 6];
         const u32 raw = reinterpret_cast<const u32*>(leaf_cells(g, leaf))[ci];
         const u32 word = ((act >> (ci & 63)) & 1ull) ? raw : 0u;
         stale = (word & 0xFu) == p.c;  // probabilistic_map.cpp:34 / :47 — skipped AND no ray is cast
       } else {
-        stale = true;  // pool exhausted: the scan will be repeated
+        stale = !DENSE;  // sparse: pool exhausted, the scan will be repeated; dense: no leaf = unknown cell = not stale
       }
     }
     if (!stale) {
@@ -470,7 +480,21 @@ __global__ void __launch_bounds__(TPB) k_resolve(GridDev g, ScanParams p, ScanBu
   }
   __syncthreads();
   if (threadIdx.x == 0 && s_m) atomicAdd(&b.sc->sum_m, s_m);
-  if (is_end && !PENDING) {
+  if (DENSE && is_end && !PENDING) {
+    // the same, with the marks in the dense window: hit bits in the second half of the block's line
+    const u32 blk = dense_block(p, e.x >> 3, e.y >> 3, e.z >> 3);
+    const u32 grp = __match_any_sync(eballot, blk);  // one lane per distinct block lists it
+    if (blk == NONE) {
+      atomicOr(&b.sc->overflow, OVF_WINDOW);
+    } else {
+      atomicOr(b.dense + (size_t)blk * 16 + (e.w ? 0u : 8u) + (ci >> 6), 1ull << (ci & 63));
+      if ((int)lane == __ffs(grp) - 1 && atomicExch(b.dstamp + blk, p.seq) != p.seq) {
+        const u32 at = atomicAdd(&b.sc->n_touched, 1u);
+        if (at < p.dlist_cap) b.touched[at] = blk;
+      }
+    }
+  }
+  if (!DENSE && is_end && !PENDING) {
     // addHitPoint / addMissPoint (probabilistic_map.cpp:30-54) deferred to the apply pass: a hit endpoint sets its bit in
     // the leaf's HIT mask; a miss endpoint gets exactly the update of a ray cell (max(p + miss, clamp_min), stamp), so
     // it simply joins the touched mask. Either way the leaf is listed for the apply pass.
@@ -492,9 +516,9 @@ __global__ void __launch_bounds__(TPB) k_resolve(GridDev g, ScanParams p, ScanBu
       atomicOr(&b.sc->overflow, OVF_CHUNKS);
     } else {
       b.rays[ray] = make_int4(e.x, e.y, e.z, (int)(u32)cb);
-      // every 32-chunk tile whose first chunk lies inside this ray learns its owner
-      const u32 t0 = ((u32)cb + 31u) >> 5, t1 = ((u32)cb + chunks - 1u) >> 5;
-      for (u32 t = t0; t <= t1; ++t) {
+      // every 32-chunk tile whose first chunk lies inside this ray learns its owner (the dense mark kernel needs no tiles)
+      const u32 t0 = ((u32)cb + 31u) >> 5, t1 = DENSE ? 0u : ((u32)cb + chunks - 1u) >> 5;
+      for (u32 t = t0; t <= t1 && !DENSE; ++t) {
         if (t < p.tile_cap) {
           b.tile_first[t] = ray;
         } else {
@@ -718,6 +742,204 @@ __global__ void __launch_bounds__(TPB, MARK_MIN_BLOCKS) k_mark(GridDev g, GridDe
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// phase 3, dense flavour: rays marked into the dense window
+// ------------------------------------------------------------------------------------------------
+// Work item = (group of 32 consecutive rays, chunk index j): lane l walks chunk j of ray 32 g + l. Consecutive rays come
+// from consecutive points of the scan, i.e. they are angular neighbours: close to the sensor their chunk j lies in the SAME
+// leaf blocks (that is where the 3.4x redundancy of the marking comes from), so the lanes' (block, word) segments are
+// merged inside the warp (__match_any_sync + __reduce_or_sync) and ONE lane per distinct word tests / ORs it. The address
+// of a word is pure arithmetic on the block coordinates: no root, inner-node or leaf look-up, and no leaf is created here.
+#ifndef MARKD_MIN_BLOCKS
+#define MARKD_MIN_BLOCKS 6
+#endif
+#ifndef APPLY_MIN_BLOCKS
+#define APPLY_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(TPB, MARKD_MIN_BLOCKS) k_mark_dense(ScanParams p, ScanBuffers b, u32 jmax) {
+  pdl_enter();
+  __shared__ unsigned long long s_bits[CHUNK][TPB];
+  __shared__ unsigned char s_key[CHUNK][TPB];
+  const u32 n_rays = (u32)(b.sc->ray_chunk >> 40);
+  if (b.sc->overflow | *b.poison) return;
+  if (p.clean16) {  // pipelined insert: leave the dedupe table zeroed for the next scan's k_classify (its last reader is done)
+    uint4* tab = reinterpret_cast<uint4*>(b.table);
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < p.clean16; i += gridDim.x * blockDim.x) tab[i] = make_uint4(0, 0, 0, 0);
+  }
+  const u32 lane = threadIdx.x & 31;
+  const u32 warps = gridDim.x * (TPB / 32);
+  const u32 groups = (n_rays + 31u) >> 5;
+  const u64 tiles = (u64)groups * jmax;
+  for (u64 tile = blockIdx.x * (TPB / 32) + (threadIdx.x >> 5); tile < tiles; tile += warps) {
+    const u32 grp = (u32)(tile / jmax), j = (u32)(tile % jmax);
+    const u32 r = grp * 32u + lane;
+    u32 nseg = 0;
+    int lx0 = 0, ly0 = 0, lz0 = 0, sx = 1, sy = 1, sz = 1;
+    if (r < n_rays) {
+      const int4 ray = b.rays[r];
+      const RayGeom rg = ray_geom(p, ray.x, ray.y, ray.z);
+      if (j < rg.chunks) {
+        u32 k0, k1;
+        chunk_range(rg, j, k0, k1);
+        sx = rg.sx;
+        sy = rg.sy;
+        sz = rg.sz;
+        nseg = walk_chunk<int>(p, rg, k0, k1, lx0, ly0, lz0, s_bits, s_key);  // the window bounds m far below 2^29
+      }
+    }
+    const u32 nmax = __reduce_max_sync(0xffffffffu, nseg);
+    if (nmax == 0u) continue;  // every ray of the group ends before chunk j
+    const u32 par0 = ((u32)lx0 & 1u) | (((u32)ly0 & 1u) << 1) | (((u32)lz0 & 1u) << 2);
+    for (u32 sgi = 0; sgi < nmax; ++sgi) {
+      const bool has = sgi < nseg;
+      const u32 act = __ballot_sync(0xffffffffu, has);
+      if (!has) continue;
+      const u32 key = s_key[sgi][threadIdx.x];
+      const unsigned long long bits = s_bits[sgi][threadIdx.x];
+      const u32 q = (key >> 3) ^ par0, w = key & 7u;  // q: which axes have crossed into the neighbouring leaf block
+      const u32 blk = dense_block(p, lx0 + ((q & 1u) ? sx : 0), ly0 + ((q & 2u) ? sy : 0), lz0 + ((q & 4u) ? sz : 0));
+      const u32 wkey = blk == NONE ? NONE : blk * 8u + w;
+      const u32 peers = __match_any_sync(act, wkey);
+      const u32 lo = __reduce_or_sync(peers, (u32)bits), hi = __reduce_or_sync(peers, (u32)(bits >> 32));
+      if ((int)lane != __ffs(peers) - 1) continue;
+      if (blk == NONE) {
+        atomicOr(&b.sc->overflow, OVF_WINDOW);
+        continue;
+      }
+      const unsigned long long all = ((unsigned long long)hi << 32) | lo;
+      unsigned long long* word = b.dense + (size_t)blk * 16 + w;
+      const unsigned long long cur = *word;  // test first: a stale L1 line only costs a redundant atomic
+      if ((cur & all) == all) continue;
+      if (cur != 0ull) {
+        atomicOr(word, all);  // result unused: a fire-and-forget reduction
+      } else if (atomicOr(word, all) == 0ull && atomicExch(b.dstamp + blk, p.seq) != p.seq) {
+        const u32 at = atomicAdd(&b.sc->n_touched, 1u);
+        if (at < p.dlist_cap) b.touched[at] = blk;
+      }
+    }
+  }
+}
+
+// phase 4, dense flavour: one warp per listed block. The leaf is found — or created: the only place of a dense scan where
+// the map grows — then the block's line of marks is applied to its cells exactly like k_apply_leaves does, and cleared.
+// A block whose leaf cannot be created (pool exhausted: error bit set) keeps its marks; the host grows the pool and runs
+// this kernel again over the same list: blocks that were applied have empty lines and are skipped, so every cell is
+// still updated exactly once ("resume", not "repeat").
+__global__ void __launch_bounds__(TPB, APPLY_MIN_BLOCKS) k_apply_dense(GridDev g, ScanParams p, ScanBuffers b, u32 resume) {
+  pdl_enter();
+  // frozen pipeline (an earlier scan ran short) or a scan that overflowed its scratch: nothing is applied
+  const bool skip = ((resume ? 0u : g.ctr->error) | b.sc->overflow) != 0u;
+  const u32 n = skip ? 0u : min(b.sc->n_touched, p.dlist_cap);
+  const u32 lane = threadIdx.x & 31;
+  const u32 warps = gridDim.x * (TPB / 32);
+  u32 changed = 0;
+  u32 t = blockIdx.x * (TPB / 32) + (threadIdx.x >> 5);
+  u32 blk_n = t < n ? b.touched[t] : NONE;
+  for (; t < n; t += warps) {
+    const u32 blk = blk_n;
+    blk_n = t + warps < n ? b.touched[t + warps] : NONE;
+    u32* line = reinterpret_cast<u32*>(b.dense + (size_t)blk * 16);
+    // lane j < 16 holds 32-bit half j of the touched and of the hit mask = the bits of cell row j
+    u32 th = 0, hh = 0;
+    if (lane < 16) {
+      th = line[lane];
+      hh = line[16 + lane];
+    }
+    if (__ballot_sync(0xffffffffu, (th | hh) != 0u) == 0u) continue;  // applied by an earlier attempt
+    u32 leaf = NONE;
+    if (lane == 0) {
+      const u32 bx = blk % p.D, by = (blk / p.D) % p.D, bz = blk / (p.D * p.D);
+      leaf = leaf_find_or_create(g, (p.W0x + (int)bx) << 3, (p.W0y + (int)by) << 3, (p.W0z + (int)bz) << 3);
+    }
+    leaf = __shfl_sync(0xffffffffu, leaf, 0);
+    if (leaf == NONE) continue;  // pool exhausted: the marks stay, the host grows the pool and resumes
+    unsigned char* lp = leaf_ptr(g, leaf);
+    u32 ah = 0;
+    if (lane < 16) ah = reinterpret_cast<const u32*>(lp + g.off_active)[lane];
+    // lane owns cells it*32 + lane, it = 0..15 (coalesced 128-B rows); bit `it` of mine/on/hit = that cell touched/ON/hit
+    u32 mine = 0, on = 0, hit = 0;
+#pragma unroll
+    for (u32 j = 0; j < 16; ++j) {
+      const u32 t32 = __shfl_sync(0xffffffffu, th, j), a32 = __shfl_sync(0xffffffffu, ah, j), h32 = __shfl_sync(0xffffffffu, hh, j);
+      mine |= ((t32 >> lane) & 1u) << j;
+      on |= ((a32 >> lane) & 1u) << j;
+      hit |= ((h32 >> lane) & 1u) << j;
+    }
+    mine |= hit;
+    u32* cells = reinterpret_cast<u32*>(lp + g.off_cells);
+#pragma unroll
+    for (u32 half = 0; half < 2; ++half) {
+      u32 word[8];
+#pragma unroll
+      for (u32 it = 0; it < 8; ++it) word[it] = ((mine & on) >> (half * 8 + it)) & 1u ? cells[(half * 8 + it) * 32 + lane] : 0u;
+#pragma unroll
+      for (u32 it = 0; it < 8; ++it) {
+        const u32 r = half * 8 + it;
+        if ((hit >> r) & 1u) {
+          const i32 prob = min(((i32)word[it] >> 4) + p.hit, p.cmax);
+          cells[r * 32 + lane] = ((u32)prob << 4) | p.c;
+          ++changed;
+        } else if (((mine >> r) & 1u) && (word[it] & 0xFu) != p.c) {
+          const i32 prob = max(((i32)word[it] >> 4) + p.miss, p.cmin);
+          cells[r * 32 + lane] = ((u32)prob << 4) | p.c;
+          ++changed;
+        }
+      }
+    }
+    if (lane < 16) reinterpret_cast<u32*>(lp + g.off_active)[lane] = ah | th | hh;
+    line[lane] = 0u;  // 32 lanes x 4 B: the whole line of marks
+  }
+  for (int o = 16; o; o >>= 1) changed += __shfl_xor_sync(0xffffffffu, changed, o);
+  if (lane == 0 && changed) atomicAdd(&b.sc->n_changed, changed);
+  // The LAST block to get here leaves the grid counters next to the scan's (the host reads both with one copy) and,
+  // pipelined, publishes the scan's record to the host ring (zero copy). A pool that ran out during this kernel has set
+  // the grid's error bits: every later scan in the queue skips itself until the host has grown the pool and resumed
+  // this scan.
+  __shared__ bool s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicAdd(&g.ctr->done_blocks, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!s_last || threadIdx.x != 0) return;
+  g.ctr->done_blocks = 0;
+  __threadfence();
+  {
+    const volatile u32* src = reinterpret_cast<const volatile u32*>(g.ctr);
+    u32* dst = reinterpret_cast<u32*>(&b.sc->gc);
+    for (u32 k = 0; k < sizeof(GridCounters) / 4; ++k) dst[k] = src[k];
+  }
+  if (p.async_id == NONE || resume) return;
+  const volatile ScanCounters* sc = b.sc;
+  u32 err = g.ctr->error;
+  if (sc->overflow && !err) {
+    err = ERR_SCAN;
+    atomicOr(&g.ctr->error, ERR_SCAN);
+  }
+  if (err && g.ctr->failed_id == NONE) g.ctr->failed_ovf = sc->overflow;
+  if (err && g.ctr->failed_id == NONE) g.ctr->failed_id = p.async_id;
+  AsyncRecord* r = b.ring + (p.async_id & (RING_SIZE - 1u));
+  r->error = err;
+  r->n_leaves = g.ctr->n_leaves;
+  r->n_inner = g.ctr->n_inner;
+  r->n_roots = g.ctr->n_roots;
+  r->n_endpoints = sc->n_endpoints;
+  r->n_changed = sc->n_changed;
+  r->n_touched = sc->n_touched;
+  r->n_points = p.n;
+  r->n_dropped = sc->n_dropped;
+  r->leaf_fill = 0;
+  r->sum_m = sc->sum_m;
+  r->ray_chunk = sc->ray_chunk;
+  __threadfence_system();
+  r->id = p.async_id;
+  if (!err) {  // healthy: hand zeroed counters to the next scan (a failed scan's counters stay for the host)
+    uint4* z = reinterpret_cast<uint4*>(b.sc);
+    for (u32 k = 0; k < sizeof(ScanCounters) / 16; ++k) z[k] = make_uint4(0, 0, 0, 0);
+  }
+}
+
 // retry path only: a failed attempt leaves touched bits behind; the list of that attempt says where
 __global__ void __launch_bounds__(TPB) k_clear_touched(GridDev g, ScanBuffers b, u32 n) {
   pdl_enter();
@@ -764,9 +986,6 @@ __device__ __forceinline__ void read_gate(const ScanParams& p, const ScanBuffers
 // One warp per listed leaf: hit endpoints (addHitPoint, probabilistic_map.cpp:30-41) and the union of all rays + miss
 // endpoints (clearPoint / addMissPoint, :43-54,81-89). Hit endpoints are never stale (resolve filtered them) and win
 // over ray cells, like the reference where they are stamped before any ray is cast.
-#ifndef APPLY_MIN_BLOCKS
-#define APPLY_MIN_BLOCKS 4
-#endif
 __global__ void __launch_bounds__(TPB, APPLY_MIN_BLOCKS) k_apply_leaves(GridDev g, ScanParams p, ScanBuffers b) {
   pdl_enter();
   // last kernel of the scan: the host reads counters + grid counters with one copy
@@ -1144,6 +1363,14 @@ Map::~Map() {
     if (e) cudaEventDestroy(e);
 }
 
+bool Map::sync_via_ring() {
+  static const bool v = [] {
+    const char* e = std::getenv("BNX_SYNC_RING");
+    return !(e && std::strcmp(e, "0") == 0);
+  }();
+  return v;
+}
+
 static i32 logods_host(float prob) {  // probabilistic_map.hpp:34-36
   return (i32)(1e6 * std::log(prob / (1.0 - prob)));
 }
@@ -1249,6 +1476,7 @@ int Map::build_params(i64 n, const double origin[3], double max_range, ScanParam
     if (std::fabs((double)p.Ox) + reach < lim && std::fabs((double)p.Oy) + reach < lim && std::fabs((double)p.Oz) + reach < lim) p.packed = 1;
   }
   p.hash_mask = (u32)(table_slots(n) - 1);
+  BNX_TRY(reserve_dense(p));
   *out = p;
   return BNX_OK;
 }
@@ -1256,6 +1484,71 @@ int Map::build_params(i64 n, const double origin[3], double max_range, ScanParam
 // bytes of host memory a strided cloud really occupies: up to the z of the last point, not n * stride (x may sit at a
 // non-zero offset inside the caller's point type, and the base pointer handed in is &points[0].x)
 static size_t cloud_bytes(i64 n, i64 stride_bytes, bool f64) { return n > 0 ? (size_t)(n - 1) * (size_t)stride_bytes + (f64 ? 24u : 12u) : 0u; }
+
+// Dense marking window: every endpoint and every ray cell of a scan lies within max_range of the origin, so
+// when that ball — in 8^3 leaf blocks — is small enough, the per-scan marks go to a dense array addressed by arithmetic
+// (one 128-B line per block) instead of into the leaves. BNX_DENSE=0 forces the leaf-resident ("sparse") marks, which also
+// serve max_range = inf, huge ranges and grids with other inner/leaf bits. The buffers are allocated (and zeroed) once
+// per window size; the apply pass leaves every line it used zeroed again.
+static u32 dense_max_blocks_per_axis() {
+  static const u32 v = [] {
+    const char* e = std::getenv("BNX_DENSE");
+    if (e && std::strcmp(e, "0") == 0) return 0u;
+    size_t mb = 2048;
+    if (const char* m = std::getenv("BNX_DENSE_MAX_MB")) mb = (size_t)std::strtoull(m, nullptr, 10);
+    u32 d = 8;
+    while ((size_t)(d + 8) * (d + 8) * (d + 8) * 128 <= (mb << 20)) d += 8;
+    return d;
+  }();
+  return v;
+}
+
+int Map::set_marking(int mode) {
+  BNX_REQUIRE(mode == 0 || mode == 1, "set_marking: 0 (automatic) or 1 (sparse)");
+  BNX_TRY(drain());
+  force_sparse_ = mode == 1;
+  return BNX_OK;
+}
+
+u32 Map::dense_dim(double max_range) const {
+  const u32 dmax = force_sparse_ ? 0u : dense_max_blocks_per_axis();
+  const GridDev g = grid.dev();
+  if (!dmax || g.ib != 2 || g.lb != 3 || !std::isfinite(max_range) || max_range < 0.0) return 0;
+  const double reach_d = std::ceil(max_range * grid.inv_resolution) + 3.0;  // |endpoint voxel - origin voxel| stays below this
+  if (reach_d > 8.0 * dmax) return 0;
+  const u32 D = (u32)((2 * (i64)reach_d) / 8 + 2);  // blocks per axis that cover [O - reach, O + reach] wherever O sits in its block
+  return D <= dmax ? D : 0;
+}
+
+int Map::reserve_dense(ScanParams& p) {
+  p.dense = 0;
+  const u32 D = dense_dim(p.max_range);
+  if (!D) return BNX_OK;
+  const i64 reach = (i64)(std::ceil(p.max_range * p.inv_res) + 3.0);
+  const i64 lim = (1ll << 30);
+  if (std::llabs((i64)p.Ox) + reach >= lim || std::llabs((i64)p.Oy) + reach >= lim || std::llabs((i64)p.Oz) + reach >= lim) return BNX_OK;
+  if (D > dense_D_) {
+    // (re)allocation: nothing may be in flight (the callers drain first when dense_need() says so)
+    const u32 Da = (D + 7u) & ~7u;
+    const size_t blocks = (size_t)Da * Da * Da;
+    b_dense_.release();
+    b_dstamp_.release();
+    b_dlist_.release();
+    BNX_TRY(b_dense_.reserve(blocks * 128));
+    BNX_TRY(b_dstamp_.reserve(blocks * 4));
+    BNX_TRY(b_dlist_.reserve(blocks * 4));
+    BNX_CUDA(cudaMemsetAsync(b_dense_.p, 0, b_dense_.bytes, grid.stream()));
+    BNX_CUDA(cudaMemsetAsync(b_dstamp_.p, 0, b_dstamp_.bytes, grid.stream()));
+    dense_D_ = Da;
+  }
+  p.dense = 1;
+  p.D = D;
+  p.W0x = (i32)((p.Ox - reach) >> 3);
+  p.W0y = (i32)((p.Oy - reach) >> 3);
+  p.W0z = (i32)((p.Oz - reach) >> 3);
+  p.dlist_cap = (u32)std::min<size_t>(b_dlist_.bytes / 4, 0xFFFFFFF0ull);
+  return BNX_OK;
+}
 
 static int check_insert_args(const void* points, i64 stride_bytes, i64 n, bool f64, const double origin[3], i64 pending) {
   BNX_REQUIRE(n >= 0 && n + pending < (1ll << 24), "insert: at most 2^24-1 points per scan");
@@ -1269,9 +1562,17 @@ static int check_insert_args(const void* points, i64 stride_bytes, i64 n, bool f
   return BNX_OK;
 }
 
+// The synchronous insertPointCloud (what the drop-in C++ header calls). Fast path: the scan goes through the pipelined
+// machinery — PDL launches, no memset, no counter copy — and the host then waits for the scan's record in the pinned
+// ring instead of synchronising the stream; a scan that ran short falls into the usual drain (grow + replay).
+// Queued addHitPoint/addMissPoint rays, a sharded map and per-phase profiling take the classic path below.
 int Map::insert(const void* points, i64 stride_bytes, i64 n, bool f64, const double origin[3], double max_range, int where) {
   BNX_TRY(check_insert_args(points, stride_bytes, n, f64, origin, n_pending_));
   BNX_TRY(drain());
+  if (!n_pending_ && world_ == 1 && !profiling && sync_via_ring()) {
+    BNX_TRY(insert_async(points, stride_bytes, n, f64, origin, max_range, where));
+    return complete_queue();
+  }
   set_ = 0;
   cudaStream_t s = grid.stream();
   if (profiling) cudaEventRecord(ev_[0], s);
@@ -1341,14 +1642,68 @@ int Map::launch_back(cudaStream_t s, ScanParams& p, bool first_attempt) {
   p.seq = ++seq_;
   p.tile_cap = (u32)std::min<size_t>(b_tiles_.bytes / 4, 0xFFFFFFFFull);
   p.touched_cap = (u32)std::min<size_t>(b_touched_.bytes / 4, 0xFFFFFFFFull);
-  if (n_pending_) launch_scan_kernel(k_resolve<1>, blocks_for(n_pending_), TPB, s, g, p, buf_, n_pending_);
-  if (n > 0) launch_scan_kernel(k_resolve<0>, blocks_for(n), TPB, s, g, p, buf_, (u32)n);
+  if (p.dense) {
+    buf_.dense = b_dense_.as<unsigned long long>();
+    buf_.dstamp = b_dstamp_.as<u32>();
+    buf_.touched = b_dlist_.as<u32>();
+    if (n_pending_) launch_scan_kernel(k_resolve<1, true>, blocks_for(n_pending_), TPB, s, g, p, buf_, n_pending_);
+    if (n > 0) launch_scan_kernel(k_resolve<0, true>, blocks_for(n), TPB, s, g, p, buf_, (u32)n);
+    if (profiling && first_attempt) cudaEventRecord(ev_[3], s);
+    // chunk indices a ray of this window can have: the first (partial) leaf block + one per 8 cells of the reach
+    const u32 jmax = (u32)(std::ceil(p.max_range * p.inv_res) + 3.0) / 8u + 2u;
+    launch_scan_kernel(k_mark_dense, sm_count() * MARKD_MIN_BLOCKS, TPB, s, p, buf_, jmax);
+    if (profiling && first_attempt) cudaEventRecord(ev_[4], s);
+    launch_scan_kernel(k_apply_dense, sm_count() * APPLY_MIN_BLOCKS, TPB, s, g, p, buf_, 0u);
+    BNX_CUDA(cudaGetLastError());
+    if (profiling && first_attempt) cudaEventRecord(ev_[5], s);
+    buf_.touched = b_touched_.as<u32>();
+    return BNX_OK;
+  }
+  if (n_pending_) launch_scan_kernel(k_resolve<1, false>, blocks_for(n_pending_), TPB, s, g, p, buf_, n_pending_);
+  if (n > 0) launch_scan_kernel(k_resolve<0, false>, blocks_for(n), TPB, s, g, p, buf_, (u32)n);
   if (profiling && first_attempt) cudaEventRecord(ev_[3], s);
   launch_scan_kernel(k_mark<false>, sm_count() * MARK_MIN_BLOCKS, TPB, s, g, g, p, buf_);
   if (profiling && first_attempt) cudaEventRecord(ev_[4], s);
   launch_scan_kernel(k_apply_leaves, sm_count() * APPLY_MIN_BLOCKS, TPB, s, g, p, buf_);
   BNX_CUDA(cudaGetLastError());
   if (profiling && first_attempt) cudaEventRecord(ev_[5], s);
+  return BNX_OK;
+}
+
+// a dense scan reported a scratch overflow (a mark outside its window: cannot happen by construction). Nothing was
+// applied; wipe the marks it left so that later scans stay exact, and fail loudly.
+__global__ void __launch_bounds__(TPB) k_clear_dense(ScanBuffers b, u32 n) {
+  const u32 lane = threadIdx.x & 31;
+  const u32 warps = gridDim.x * (TPB / 32);
+  for (u32 t = blockIdx.x * (TPB / 32) + (threadIdx.x >> 5); t < n; t += warps) reinterpret_cast<u32*>(b.dense + (size_t)b.touched[t] * 16)[lane] = 0u;
+}
+
+int Map::dense_internal_error(const ScanCounters& st, const ScanParams& p) {
+  cudaStream_t s = grid.stream();
+  buf_.dense = b_dense_.as<unsigned long long>();
+  buf_.touched = b_dlist_.as<u32>();
+  if (st.n_touched) {
+    note_launch(), k_clear_dense<<<sm_count() * 8, TPB, 0, s>>>(buf_, std::min(st.n_touched, p.dlist_cap));
+    BNX_CUDA(cudaGetLastError());
+    BNX_CUDA(cudaStreamSynchronize(s));
+  }
+  buf_.touched = b_touched_.as<u32>();
+  if (st.gc.error) BNX_TRY(grid.recover(st.gc));
+  set_error("insert: internal error, a ray cell fell outside the dense marking window (overflow bits " + std::to_string(st.overflow) + ")");
+  return BNX_ERR_CUDA;
+}
+
+// dense scans only: the apply pass ran out of leaves / inner nodes / root slots part-way. The pools have been grown;
+// run the pass again over the same list (lines of blocks that were applied are empty) until every block has its leaf.
+int Map::resume_apply(cudaStream_t s, ScanParams& p) {
+  const GridDev g = grid.dev();
+  buf_.dense = b_dense_.as<unsigned long long>();
+  buf_.dstamp = b_dstamp_.as<u32>();
+  buf_.touched = b_dlist_.as<u32>();
+  buf_.poison = &g.ctr->error;
+  note_launch(), k_apply_dense<<<sm_count() * APPLY_MIN_BLOCKS, TPB, 0, s>>>(g, p, buf_, 1u);
+  BNX_CUDA(cudaGetLastError());
+  buf_.touched = b_touched_.as<u32>();
   return BNX_OK;
 }
 
@@ -1386,7 +1741,25 @@ int Map::run_scan(const void* d_points, i64 stride_bytes, bool f64, const ScanPa
   p.clean16 = 0;  // a retry re-reads the dedupe table: the synchronous path clears it with its own memset
   const int persistent = sm_count() * 8;
   i64 retries = 0;
-  for (;; ++retries) {
+  if (p.dense) {
+    // dense marks: only the apply pass can run short (it is the one place where leaves are created); it is RESUMED over
+    // the same list after the pools have grown — blocks that were applied have empty lines
+    BNX_TRY(launch_scan(d_points, stride_bytes, f64, p, true));
+    for (;; ++retries) {
+      BNX_CUDA(cudaMemcpyAsync(h_status_, d_sc_, sizeof(ScanCounters), cudaMemcpyDeviceToHost, s));
+      BNX_CUDA(cudaStreamSynchronize(s));
+      const ScanCounters st = *h_status_;
+      if (st.overflow) return dense_internal_error(st, p);
+      if (st.gc.error == 0) break;
+      if (retries > 48) {
+        set_error("insert: node pools could not be grown enough for this scan");
+        return BNX_ERR_NOMEM;
+      }
+      BNX_TRY(grid.recover(st.gc));
+      BNX_TRY(resume_apply(s, p));
+    }
+  }
+  for (; !p.dense; ++retries) {
     if (retries > 48) {
       set_error("insert: node pools could not be grown enough for this scan");
       return BNX_ERR_NOMEM;
@@ -1502,6 +1875,7 @@ int Map::insert_async(const void* points, i64 stride_bytes, i64 n, bool f64, con
       tile_bytes((size_t)n + 32, max_range) > b_tiles_.bytes) {
     BNX_TRY(drain(false));
   }
+  if (dense_dim(max_range) > dense_D_) BNX_TRY(drain(false));  // the dense window is (re)allocated by build_params
   // all scratch sets are sized together, up front: an allocation in the middle of the pipeline would synchronise the device
   if (n > sets_n_ || (where == BNX_HOST && (size_t)n * stride_bytes > sets_stage_bytes_)) {
     BNX_TRY(drain(false));
@@ -1544,6 +1918,56 @@ int Map::insert_async(const void* points, i64 stride_bytes, i64 n, bool f64, con
   }
   queue_.push_back(q);
   if (++update_count == 4) update_count = 1;
+  return BNX_OK;
+}
+
+// the synchronous insert's wait: spin on the record of the newest queued scan (the device writes it into pinned host
+// memory when the scan's last kernel ends), then account for the queue without touching the streams
+int Map::complete_queue() {
+  if (queue_.empty()) return BNX_OK;
+  cudaStream_t s = grid.stream();
+  const u32 last_id = queue_.back().p.async_id;
+  const volatile AsyncRecord* r = &h_ring_[last_id & (RING - 1)];
+  unsigned spins = 0;
+  while (r->id != last_id) {
+    if (++spins > (1u << 12)) {  // never spin on a wedged device
+      if (cudaStreamQuery(s) != cudaErrorNotReady) break;
+      spins = 0;
+    }
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+  }
+  bool healthy = r->id == last_id && r->error == 0;
+  for (size_t k = 0; healthy && k < queue_.size(); ++k) {
+    const AsyncRecord& q = h_ring_[queue_[k].p.async_id & (RING - 1)];
+    healthy = q.id == queue_[k].p.async_id && q.error == 0;
+  }
+  if (!healthy) return drain();  // ran short (or refused): grow, replay, report
+  GridCounters gc = {};
+  for (size_t k = 0; k < queue_.size(); ++k) {
+    const AsyncRecord& q = h_ring_[queue_[k].p.async_id & (RING - 1)];
+    ScanCounters st = {};
+    st.n_endpoints = q.n_endpoints;
+    st.n_changed = q.n_changed;
+    st.n_touched = q.n_touched;
+    st.n_dropped = q.n_dropped;
+    st.sum_m = q.sum_m;
+    st.ray_chunk = q.ray_chunk;
+    account(st, queue_[k].p.n, 0, 0);
+    gc.n_leaves = q.n_leaves;
+    gc.n_inner = q.n_inner;
+    gc.n_roots = q.n_roots;
+  }
+  queue_.clear();
+  done_upto_ = 0;
+  // pool head-room for the next scans, from the record (no device read); growing synchronises, but only when it grows
+  const GridDev g = grid.dev();
+  if ((u64)gc.n_roots * 2 > (u64)g.root_mask + 1 || (u64)gc.n_leaves * 2 > g.leaf_cap || (u64)gc.n_inner * 2 > g.inner_cap) {
+    BNX_CUDA(cudaStreamSynchronize(s));
+    BNX_CUDA(cudaStreamSynchronize(pre_stream_));
+    return grid.maintain(gc);
+  }
   return BNX_OK;
 }
 
@@ -1600,6 +2024,46 @@ int Map::drain_queue() {
     account(st, q[k].p.n, 0, 0);
   }
   if (!gc.error) return grid.maintain(gc);
+  if (q[done].p.dense) {
+    // dense marks: the failed scan's apply pass ran out of pool space part-way (later scans skipped themselves, so its
+    // list and its window are intact): grow, RESUME the pass — applied blocks have empty lines — then replay the rest
+    ScanParams fp = q[done].p;
+    buf_.sc = d_sc_ = sets_[set_].table.as<ScanCounters>();
+    ScanCounters st = *h_status_;
+    if (st.overflow) {
+      BNX_TRY(dense_internal_error(st, fp));
+    }
+    GridCounters cur = gc;
+    i64 resumes = 0;
+    for (int attempt = 0;; ++attempt) {
+      ++resumes;
+      if (attempt > 48) {
+        set_error("insert: node pools could not be grown enough for this scan");
+        return BNX_ERR_NOMEM;
+      }
+      BNX_TRY(grid.recover(cur));
+      BNX_TRY(resume_apply(s, fp));
+      BNX_CUDA(cudaMemcpyAsync(h_status_, d_sc_, sizeof(ScanCounters), cudaMemcpyDeviceToHost, s));
+      BNX_CUDA(cudaStreamSynchronize(s));
+      st = *h_status_;
+      if (st.gc.error == 0) break;
+      cur = st.gc;
+    }
+    account(st, fp.n, 0, resumes);
+    set_ = 0;
+    for (size_t k = done + 1; k < q.size(); ++k) {
+      const Queued& e = q[k];
+      BNX_TRY(reserve_scan(e.p.n, e.stride, e.p.max_range));
+      const void* d_points = e.points;
+      if (e.where == BNX_HOST && e.p.n > 0) {
+        BNX_TRY(b_pts_.reserve((size_t)e.p.n * e.stride));
+        BNX_CUDA(cudaMemcpyAsync(b_pts_.p, e.points, cloud_bytes(e.p.n, e.stride, e.f64), cudaMemcpyHostToDevice, s));
+        d_points = b_pts_.p;
+      }
+      BNX_TRY(run_scan(d_points, e.stride, e.f64, e.p, false));  // keeps the update_id (and the window) it was queued with
+    }
+    return BNX_OK;
+  }
   // the failed scan's touched list is still intact (later scans skipped themselves): drop its marks, grow, replay
   const ScanCounters st = *h_status_;
   if (st.n_touched) {
@@ -1627,6 +2091,7 @@ int Map::drain_queue() {
       d_points = b_pts_.p;
     }
     BNX_TRY(run_scan(d_points, e.stride, e.f64, e.p, false));  // keeps the update_id this scan was queued with
+    if (k == done) ++counters[5];  // the attempt that froze the pipeline counts as a retry of this scan
   }
   if (refused) {
     deferred_ = BNX_ERR_UNSUPPORTED;
@@ -1836,7 +2301,7 @@ int Map::shard_resolve_mark(const void* recv_records, void* send_leaves, i64 cap
   // a rank receives about one slice worth of records; the kernels loop if it is (much) more
   const int rblocks = blocks_for(std::min<i64>(slots, 2 * (i64)p.rec_cap));
   launch_scan_kernel(k_shard_dedupe, rblocks, TPB, s, p, buf_, slots, table1, lean ? (u32)(t1 * 12 / 16) : 0u);
-  launch_scan_kernel(k_resolve<2>, rblocks, TPB, s, g, p, buf_, slots);
+  launch_scan_kernel(k_resolve<2, false>, rblocks, TPB, s, g, p, buf_, slots);
   launch_scan_kernel(k_mark<true>, sm_count() * MARK_MIN_BLOCKS, TPB, s, g, gs, p, buf_);
   launch_scan_kernel(k_shard_emit, persistent, TPB, s, gs, p, buf_);
   BNX_CUDA(cudaGetLastError());

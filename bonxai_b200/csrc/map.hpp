@@ -42,6 +42,10 @@ struct ScanParams {
   u32 xseq1, xseq2;            // sharded, peer-memory exchange: arrival stamps of this scan's exchange 1 / exchange 2 + flags
   u32 async_id;                // pipelined insert: serial of this scan (NONE for the synchronous path)
   u32 clean16;                 // pipelined insert: 16-byte units of dedupe table k_mark zeroes for the next scan
+  u32 dense;                   // 1: per-scan marks go to the dense window around the origin, 0: into the leaves
+  i32 W0x, W0y, W0z;           // dense window: leaf-block coordinates (voxel >> 3) of its corner
+  u32 D;                       // dense window: blocks per axis
+  u32 dlist_cap;               // dense window: entries of the touched-block list
   u32 use_transform;           // fused ROS pre-step: drop non-finite points, then T * p in float before classifying
   float T[12];                 // rows 0..2 of the 4x4 sensor->world matrix
 };
@@ -87,6 +91,8 @@ struct ScanBuffers {
   u32* touched;      // leaves first touched in this scan
   int4* pending;     // queued addHitPoint/addMissPoint endpoints (xyz, type)
   u32* touched2;     // sharded: scratch-grid leaves touched in this scan
+  unsigned long long* dense;  // dense window: per block {u64 touched[8]; u64 hit[8]} = one 128-B line, all zero between scans
+  u32* dstamp;       // dense window: per block, serial of the last scan that listed it
   const int4* recs;  // sharded: received endpoint records, [world][rec_cap], element 0 of a block = {count}
   const u32* gate;   // sharded: all-reduced error flags; the apply kernels skip when any is set (NULL otherwise)
   const u32* my_flags;  // sharded, peer-memory exchange: this rank's mailbox flag area (NULL: exchanges run by the caller)
@@ -110,6 +116,9 @@ class Map {
     use_next_T_ = true;
   }
   void clear_next_transform() { use_next_T_ = false; }
+  // where a scan keeps its per-scan marks: 0 = automatic (the dense window when the range allows it), 1 = always in the
+  // leaves ("sparse", the only flavour for max_range = inf or non-default grid bits)
+  int set_marking(int mode);
 
   // ---- root-key sharding across processes (one map shard per GPU), as stages: with caller-owned exchange buffers the
   // caller moves them between the stages; with mailboxes attached (NULL buffers) the kernels exchange by themselves.
@@ -170,6 +179,13 @@ class Map {
 
   ScanBuffers buf_ = {};
   DevBuf b_pts_, b_rays_, b_tiles_, b_touched_, b_touched2_, b_pending_, b_q_xyz_, b_q_out_;
+  DevBuf b_dense_, b_dstamp_, b_dlist_;  // dense marking window (allocated at the first scan that can use it)
+  bool force_sparse_ = false;
+  u32 dense_D_ = 0;                      // blocks per axis the window buffers are sized (and zeroed) for
+  int reserve_dense(ScanParams& p);      // decides p.dense and sizes the window
+  int resume_apply(cudaStream_t s, ScanParams& p);
+  int dense_internal_error(const ScanCounters& st, const ScanParams& p);
+  u32 dense_dim(double max_range) const;  // blocks per axis a scan of this range needs (0: not eligible)
   // Scratch written BEFORE a scan touches the map (classify: endpoints, their dedupe table, the counters) exists once
   // per scan in flight: the pipelined insert classifies on its own stream, many scans ahead of the map updates.
   // The synchronous and the sharded paths use set 0.
@@ -204,6 +220,8 @@ class Map {
   };
   std::vector<Queued> queue_;
   int drain_queue();
+  int complete_queue();
+  static bool sync_via_ring();  // BNX_SYNC_RING=0 restores the memset + copy + cudaStreamSynchronize flavour of insert()
   int deferred_ = BNX_OK;  // error of a pipelined scan that was refused, reported by the next synchronising call
   std::string deferred_msg_;
   AsyncRecord* h_ring_ = nullptr;  // pinned + mapped: one record per scan, written by the device

@@ -17,6 +17,22 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 DEFAULT_OPTS = [-405465, 847297, -1992430, 3476099, 0]
 
 
+@pytest.fixture(autouse=True, params=["auto", "sparse"])
+def marking(request, monkeypatch):
+    """every test of this file runs twice: with the automatic choice of where a scan keeps its marks (the dense window
+    whenever max_range is finite and small enough) and with the marks forced into the leaves (bnx_map_set_marking)"""
+    if request.param == "sparse":
+        from bonxai_b200 import capi
+        orig = capi.ProbabilisticMap.__init__
+
+        def init(self, *a, **k):
+            orig(self, *a, **k)
+            self.set_marking("sparse")
+
+        monkeypatch.setattr(capi.ProbabilisticMap, "__init__", init)
+    return request.param
+
+
 def check_scan(gm, om, what, counters=True):
     assert_same_dump(gm.dump(), om.dump(), what)
     if counters:
@@ -304,6 +320,31 @@ def test_refused_scan_leaves_the_map_clean(bnx, port):
     gm.insert(nxt, [0.1, 0, 0], 6.0)
     om.insert(nxt, [0.1, 0, 0], 6.0)
     check_scan(gm, om, "scan after the refused one (pipelined)")
+
+
+def test_dense_window_moves_and_resizes(bnx, port):
+    """the dense marking window follows the origin (far from 0, negative coordinates, jumps larger than the window) and is
+    re-allocated when max_range grows; scans with max_range = inf in between use the leaf-resident marks"""
+    rng = np.random.default_rng(31)
+    gm, om = bnx.ProbabilisticMap(0.05), port.map(0.05)
+    origins = [[0, 0, 0], [-37.3, 12.9, -3.3], [-37.1, 12.9, -3.3], [812.4, -955.6, 40.2], [812.4, -955.2, 40.2], [0.4, 0, 0]]
+    ranges = [2.0, 3.0, float("inf"), 3.0, 7.5, 1.0]
+    keep = []
+    for k, (o, r) in enumerate(zip(origins, ranges)):
+        pts = (rng.normal(0, 2.5, (30000, 3)) + o).astype(np.float32)
+        keep.append(pts)
+        if k % 2:
+            gm.insert_async(pts, o, r)
+        else:
+            gm.insert(pts, o, r)
+        om.insert(pts, np.float32(o), r)
+        check_scan(gm, om, f"scan {k} origin {o} range {r}", counters=False)
+    # exactly max_range away along an axis, and rays that start in the last cell of a leaf block
+    for o in ([0.799, 0.799, 0.799], [-0.001, -0.001, -0.001]):
+        pts = np.float32([[o[0] + 2.0, o[1], o[2]], [o[0], o[1] - 2.0, o[2]], [o[0], o[1], o[2] + 5.0], [o[0] - 1.99, o[1] + 0.3, o[2]]])
+        gm.insert(pts, o, 2.0)
+        om.insert(pts, np.float32(o), 2.0)
+        check_scan(gm, om, f"boundary rays from {o}")
 
 
 def test_depth_scan_reduced(bnx, port):
