@@ -61,6 +61,27 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_variant(tag: str, defines: list[str]) -> str:
+    """a tuning variant of the library (extra -D flags) as build/variants/libbonxai_b200_<tag>.so; load it with
+    BNX_LIB=<path>. Used for A/B measurements of kernel parameters on the GPU box."""
+    vdir = os.path.join(ROOT, "build", "variants", tag)
+    os.makedirs(vdir, exist_ok=True)
+    objs, procs = [], []
+    for src in SOURCES:
+        obj = os.path.join(vdir, src.replace(".cu", ".o"))
+        objs.append(obj)
+        cmd = [_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-c", os.path.join(CSRC, src), "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            sys.stderr.write(out)
+            raise RuntimeError(f"nvcc failed on {src} ({tag})")
+    lib = os.path.join(ROOT, "build", "variants", f"libbonxai_b200_{tag}.so")
+    subprocess.run([_nvcc(), "-shared", "-cudart", "static", "-Xlinker", "-ldl", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib, *objs], check=True)
+    return lib
+
+
 DROPIN_BENCH = os.path.join(ROOT, "build", "dropin_bench")
 
 

@@ -15,7 +15,8 @@ import os
 import numpy as np
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libbonxai_b200.so")
+# BNX_LIB selects another build of the same library (tuning variants made by bonxai_b200.build.build_variant)
+LIB_PATH = os.environ.get("BNX_LIB") or os.path.join(PKG, "libbonxai_b200.so")
 
 BNX_HOST, BNX_DEVICE = 0, 1
 BNX_CLEAR_MEMORY, BNX_SET_ALL_CELLS_OFF = 0, 1
@@ -479,8 +480,9 @@ class ProbabilisticMap:
         return v.value
 
     def set_marking(self, mode: str):
-        """"auto": dense window when the range allows it; "sparse": per-scan marks always inside the leaves"""
-        _check(self.lib.bnx_map_set_marking(self.h, {"auto": 0, "sparse": 1}[mode]))
+        """"sparse": per-scan marks inside the leaves; "dense": experimental dense window where the range allows it;
+        "default": sparse unless BNX_DENSE=1"""
+        _check(self.lib.bnx_map_set_marking(self.h, {"default": 0, "sparse": 1, "dense": 2}[mode]))
 
     def set_profiling(self, enable=True):
         _check(self.lib.bnx_map_set_profiling(self.h, int(enable)))

@@ -660,17 +660,23 @@ int Grid::sync() {
   return BNX_OK;
 }
 
-int Grid::ensure_leaf_capacity(u64 leaves) {
+u64 Grid::leaf_step(u64 live_leaves) const {
+  static const size_t step_bytes = env_mb("BNX_GROW_MB", 256);
+  return std::max<u64>(step_bytes / dev_.leaf_stride, live_leaves / 8) + 1;
+}
+u64 Grid::inner_step(u64 live_inner) const { return std::max<u64>((16u << 20) / (dev_.inner_stride * 4), live_inner / 8) + 1; }
+
+int Grid::ensure_leaf_capacity(u64 leaves, cudaStream_t zero_stream) {
   if (leaves <= dev_.leaf_cap) return BNX_OK;
   leaves = std::min<u64>(leaves, 0xFFFFFFF0ull);
-  BNX_TRY(leaf_arena_.grow_to((size_t)leaves * dev_.leaf_stride, stream_));
+  BNX_TRY(leaf_arena_.grow_to((size_t)leaves * dev_.leaf_stride, zero_stream ? zero_stream : stream_));
   dev_.leaf_cap = (u32)std::min<u64>(leaf_arena_.mapped() / dev_.leaf_stride, 0xFFFFFFF0ull);
   return BNX_OK;
 }
 
-int Grid::ensure_inner_capacity(u64 inner) {
+int Grid::ensure_inner_capacity(u64 inner, cudaStream_t zero_stream) {
   if (inner <= dev_.inner_cap) return BNX_OK;
-  BNX_TRY(inner_arena_.grow_to((size_t)inner * dev_.inner_stride * 4, stream_));
+  BNX_TRY(inner_arena_.grow_to((size_t)inner * dev_.inner_stride * 4, zero_stream ? zero_stream : stream_));
   dev_.inner_cap = (u32)std::min<u64>(inner_arena_.mapped() / (dev_.inner_stride * 4), 0xFFFFFFF0ull);
   return BNX_OK;
 }
@@ -716,17 +722,19 @@ int Grid::recover(const GridCounters& seen) {
   *h_ctr_ = fix;
   BNX_CUDA(cudaMemcpyAsync(d_ctr_, h_ctr_, sizeof(GridCounters), cudaMemcpyHostToDevice, stream_));
   BNX_CUDA(cudaStreamSynchronize(stream_));
-  if (seen.error & ERR_LEAF_POOL) BNX_TRY(ensure_leaf_capacity(std::max<u64>((u64)dev_.leaf_cap * 2, 1024)));
-  if (seen.error & ERR_INNER_POOL) BNX_TRY(ensure_inner_capacity(std::max<u64>((u64)dev_.inner_cap * 2, 1024)));
+  // a pool that actually ran out: two steps at once (the caller repeats until the work fits)
+  if (seen.error & ERR_LEAF_POOL) BNX_TRY(ensure_leaf_capacity((u64)dev_.leaf_cap + std::max<u64>(2 * leaf_step(dev_.leaf_cap), dev_.leaf_cap / 2)));
+  if (seen.error & ERR_INNER_POOL) BNX_TRY(ensure_inner_capacity((u64)dev_.inner_cap + std::max<u64>(2 * inner_step(dev_.inner_cap), dev_.inner_cap / 2)));
   if (seen.error & ERR_ROOT_TABLE) BNX_TRY(grow_root_table(root_slots_ * 4));
   return BNX_OK;
 }
 
 int Grid::maintain(const GridCounters& seen) {
   if ((u64)seen.n_roots * 2 > root_slots_) BNX_TRY(grow_root_table(root_slots_ * 4));
-  // keep half of each pool free so that the next batch rarely needs the retry path
-  if ((u64)seen.n_leaves * 2 > dev_.leaf_cap) BNX_TRY(ensure_leaf_capacity((u64)dev_.leaf_cap * 2));
-  if ((u64)seen.n_inner * 2 > dev_.inner_cap) BNX_TRY(ensure_inner_capacity((u64)dev_.inner_cap * 2));
+  // keep half a growth step of each pool free so that the next batch rarely needs the retry path
+  const u64 ls = leaf_step(seen.n_leaves), is = inner_step(seen.n_inner);
+  if ((u64)seen.n_leaves + ls / 2 > dev_.leaf_cap) BNX_TRY(ensure_leaf_capacity((u64)seen.n_leaves + ls));
+  if ((u64)seen.n_inner + is / 2 > dev_.inner_cap) BNX_TRY(ensure_inner_capacity((u64)seen.n_inner + is));
   return BNX_OK;
 }
 
@@ -1062,17 +1070,23 @@ int Grid::dump_points_f32(float* out, i64 stride_floats, int zfilter, double zmi
     }
     return BNX_OK;
   }
-  BNX_TRY(run(nullptr, 0));
+  if (!out || cap == 0) {  // count only
+    BNX_TRY(run(nullptr, 0));
+    *count = (i64)h_count_[0];
+    return BNX_OK;
+  }
+  // host output: ONE pass into a device staging buffer of the caller's capacity (the kernel counts every point and
+  // writes the first `cap`), then one copy of what was found. A caller that keeps some head-room over the previous
+  // count (the publisher runs after every scan) never needs the counting pass.
+  BNX_TRY(b_out_.reserve((size_t)cap * stride_floats * 4));
+  BNX_TRY(run(b_out_.as<float>(), (u64)cap));
   const i64 total = (i64)h_count_[0];
   *count = total;
-  if (!out || cap == 0) return BNX_OK;
   if (total > cap) {
     set_error("occupied points: output capacity too small");
     return BNX_ERR_CAPACITY;
   }
   if (total == 0) return BNX_OK;
-  BNX_TRY(b_out_.reserve((size_t)total * stride_floats * 4));
-  BNX_TRY(run(b_out_.as<float>(), (u64)total));
   BNX_CUDA(cudaMemcpyAsync(out, b_out_.p, (size_t)total * stride_floats * 4, cudaMemcpyDeviceToHost, stream_));
   return sync();
 }

@@ -89,8 +89,15 @@ class Grid {
   int recover(const GridCounters& seen);
   // proactive growth at quiet points (root table load factor, pool head-room)
   int maintain(const GridCounters& seen);
-  int ensure_leaf_capacity(u64 leaves);
-  int ensure_inner_capacity(u64 inner);
+  // zero_stream: where the new memory is zero-filled (default: the grid's stream). Mapping more memory behind the pools
+  // does not wait for running kernels (VMM), so a caller may grow AHEAD of need on a side stream while scans run and
+  // make its work stream wait for the fill.
+  int ensure_leaf_capacity(u64 leaves, cudaStream_t zero_stream = nullptr);
+  int ensure_inner_capacity(u64 inner, cudaStream_t zero_stream = nullptr);
+  // pools grow in fixed steps — max(BNX_GROW_MB (256), live / 8) — not by doubling: mapped memory stays within ~1.15x of
+  // the live nodes of a large map
+  u64 leaf_step(u64 live_leaves) const;
+  u64 inner_step(u64 live_inner) const;
   int grow_root_table(u64 min_slots);
 
   double resolution = 0.0, inv_resolution = 0.0;

@@ -333,6 +333,28 @@ __host__ __device__ __forceinline__ u32 shard_owner(int rx, int ry, int rz, u32 
   return (u32)((hash3(rx, ry, rz) >> 34) % world);
 }
 
+// 128-bit compare-and-swap (atom.cas.b128): claims a whole {x, y, z, best} slot of the receiver's any-coordinate dedupe
+// table at once, so a slot's key is never seen half-written
+__device__ __forceinline__ int4 cas128(int4* addr, int4 cmp, int4 val) {
+  const unsigned long long clo = ((unsigned long long)(u32)cmp.y << 32) | (u32)cmp.x, chi = ((unsigned long long)(u32)cmp.w << 32) | (u32)cmp.z;
+  const unsigned long long vlo = ((unsigned long long)(u32)val.y << 32) | (u32)val.x, vhi = ((unsigned long long)(u32)val.w << 32) | (u32)val.z;
+  unsigned long long olo, ohi;
+  asm volatile(
+      "{\n\t.reg .b128 c, v, o;\n\t"
+      "mov.b128 c, {%2, %3};\n\t"
+      "mov.b128 v, {%4, %5};\n\t"
+      "atom.global.cas.b128 o, [%6], c, v;\n\t"
+      "mov.b128 {%0, %1}, o;\n\t}"
+      : "=l"(olo), "=l"(ohi)
+      : "l"(clo), "l"(chi), "l"(vlo), "l"(vhi), "l"(addr)
+      : "memory");
+  return make_int4((int)(u32)olo, (int)(olo >> 32), (int)(u32)ohi, (int)(ohi >> 32));
+}
+// the best (= ~lowest w) entry of a receiver-table slot: packed flavour table[slot], any-coordinate flavour slot.w
+__device__ __forceinline__ u32 shard_slot_best(const ScanParams& p, const ScanBuffers& b, u32 slot) {
+  return p.packed ? b.table[slot] : b.table[(size_t)slot * 4 + 3];
+}
+
 // Sharded map, receiver side of exchange 1: the inbox is [world][rec_cap] records with the count in element 0 of every
 // block. The records of all blocks are addressed as ONE dense range 0..R-1 (block after block), so that the threads of
 // the receiving kernels are fully used whatever the split between the senders is.
@@ -402,7 +424,7 @@ __global__ void __launch_bounds__(TPB) k_resolve(GridDev g, ScanParams p, ScanBu
   if (MODE == 2) {
     received = shard_locate(p, b, i, winner, e);
     if (winner) {
-      winner = b.table[b.slot_of[i]] == ~(u32)e.w;
+      winner = shard_slot_best(p, b, b.slot_of[i]) == ~(u32)e.w;
       e.w &= 1;
     }
   } else if (i < count) {
@@ -483,15 +505,12 @@ __global__ void __launch_bounds__(TPB) k_resolve(GridDev g, ScanParams p, ScanBu
   if (DENSE && is_end && !PENDING) {
     // the same, with the marks in the dense window: hit bits in the second half of the block's line
     const u32 blk = dense_block(p, e.x >> 3, e.y >> 3, e.z >> 3);
-    const u32 grp = __match_any_sync(eballot, blk);  // one lane per distinct block lists it
+    const u32 grp = __match_any_sync(eballot, blk);  // one lane per distinct block sets its bit in the bitmap
     if (blk == NONE) {
       atomicOr(&b.sc->overflow, OVF_WINDOW);
     } else {
       atomicOr(b.dense + (size_t)blk * 16 + (e.w ? 0u : 8u) + (ci >> 6), 1ull << (ci & 63));
-      if ((int)lane == __ffs(grp) - 1 && atomicExch(b.dstamp + blk, p.seq) != p.seq) {
-        const u32 at = atomicAdd(&b.sc->n_touched, 1u);
-        if (at < p.dlist_cap) b.touched[at] = blk;
-      }
+      if ((int)lane == __ffs(grp) - 1) atomicOr(b.dbits + (blk >> 5), 1u << (blk & 31u));
     }
   }
   if (!DENSE && is_end && !PENDING) {
@@ -664,12 +683,16 @@ __global__ void __launch_bounds__(TPB, MARK_MIN_BLOCKS) k_mark(GridDev g, GridDe
       const u32 n16 = (shard_table_mask(p, shard_locate(p, b, NONE, f_, e_)) + 1u) / 4u;
       uint4* tab = reinterpret_cast<uint4*>(b.table);
       uint4* keys = reinterpret_cast<uint4*>(b.keys);
-      for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < 3u * n16; i += gridDim.x * blockDim.x) {
-        if (i < n16) {
-          tab[i] = make_uint4(0, 0, 0, 0);
-        } else {
-          keys[i - n16] = make_uint4(0, 0, 0, 0);
+      if (p.packed) {
+        for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < 3u * n16; i += gridDim.x * blockDim.x) {
+          if (i < n16) {
+            tab[i] = make_uint4(0, 0, 0, 0);
+          } else {
+            keys[i - n16] = make_uint4(0, 0, 0, 0);
+          }
         }
+      } else {  // 16-byte slots
+        for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < 4u * n16; i += gridDim.x * blockDim.x) tab[i] = make_uint4(0, 0, 0, 0);
       }
     } else {
       uint4* tab = reinterpret_cast<uint4*>(b.table);
@@ -745,21 +768,57 @@ __global__ void __launch_bounds__(TPB, MARK_MIN_BLOCKS) k_mark(GridDev g, GridDe
 // ------------------------------------------------------------------------------------------------
 // phase 3, dense flavour: rays marked into the dense window
 // ------------------------------------------------------------------------------------------------
-// Work item = (group of 32 consecutive rays, chunk index j): lane l walks chunk j of ray 32 g + l. Consecutive rays come
-// from consecutive points of the scan, i.e. they are angular neighbours: close to the sensor their chunk j lies in the SAME
-// leaf blocks (that is where the 3.4x redundancy of the marking comes from), so the lanes' (block, word) segments are
-// merged inside the warp (__match_any_sync + __reduce_or_sync) and ONE lane per distinct word tests / ORs it. The address
-// of a word is pure arithmetic on the block coordinates: no root, inner-node or leaf look-up, and no leaf is created here.
+// Work item = (group of 32 consecutive rays, stretch s): lane l walks cells [SEG s, SEG s + SEG) of ray 32 g + l with the
+// reference's own integer DDA (probabilistic_map.hpp:162-203), restarted ONCE per stretch from the closed form
+// cell_k = O + sign * floor((2 k |d| + m) / 2m) (residual error k |d| - pos m). While the cell stays in the same leaf
+// block and z slab its bit is ORed into a register; when that (block, slab) key changes the 64-bit word goes to the
+// dense window as ONE fire-and-forget reduction (red.or): the address is pure arithmetic on the block coordinates — no
+// root, inner-node or leaf look-up, nothing is created here — and nothing is read back, so the walk never waits for
+// memory. Which blocks were touched is recorded the same way, one bit per block in a bitmap the apply pass scans.
+// Compared with the leaf-resident flavour (8-cell chunks, one closed-form restart + segment stack + leaf look-ups +
+// test-and-set round trips per chunk) a visited cell costs a fraction of the instructions and no round trip.
 #ifndef MARKD_MIN_BLOCKS
 #define MARKD_MIN_BLOCKS 6
 #endif
 #ifndef APPLY_MIN_BLOCKS
 #define APPLY_MIN_BLOCKS 4
 #endif
-__global__ void __launch_bounds__(TPB, MARKD_MIN_BLOCKS) k_mark_dense(ScanParams p, ScanBuffers b, u32 jmax) {
+#ifndef MARK_SEG
+#define MARK_SEG 32
+#endif
+constexpr u32 SEG = MARK_SEG;  // cells per lane and work item
+
+// One finished (block, z slab) word of a lane. The word's address is pure arithmetic; the test-before-set that keeps
+// the hot words around the sensor from being hammered needs the word's current value, and waiting for that load is what
+// the walk must never do: the load is issued when a word is finished and its value is only looked at when the NEXT word
+// of the lane is finished, ~100 instructions later. A stale value costs a redundant red.or, never a missed bit.
+struct PendingWord {
+  unsigned long long* word;  // nullptr: nothing pending
+  unsigned long long bits, cur;
+  u32 blk;
+};
+__device__ __forceinline__ void commit_word(const ScanBuffers& b, const PendingWord& pw) {
+  if (pw.word == nullptr || (pw.cur & pw.bits) == pw.bits) return;
+  atomicOr(pw.word, pw.bits);  // result unused: red.or
+  // whoever turns a word non-zero saw it zero: the block's bit in the bitmap of touched blocks is set at least once
+  if (pw.cur == 0ull) atomicOr(b.dbits + (pw.blk >> 5), 1u << (pw.blk & 31u));
+}
+// key = bx | by << 10 | z slab << 20 | bz << 23, block coordinates relative to the window corner
+__device__ __forceinline__ void issue_word(const ScanParams& p, const ScanBuffers& b, u32 key, unsigned long long bits, PendingWord& pw) {
+  const u32 bx = key & 1023u, by = (key >> 10) & 1023u, w = (key >> 20) & 7u, bz = key >> 23;
+  pw.word = nullptr;
+  if (bx >= p.D || by >= p.D || bz >= p.D) {
+    atomicOr(&b.sc->overflow, OVF_WINDOW);
+    return;
+  }
+  pw.blk = (bz * p.D + by) * p.D + bx;
+  pw.word = b.dense + (size_t)pw.blk * 16 + w;
+  pw.bits = bits;
+  pw.cur = *pw.word;  // in flight until the next commit
+}
+
+__global__ void __launch_bounds__(TPB, MARKD_MIN_BLOCKS) k_mark_dense(ScanParams p, ScanBuffers b, u32 smax) {
   pdl_enter();
-  __shared__ unsigned long long s_bits[CHUNK][TPB];
-  __shared__ unsigned char s_key[CHUNK][TPB];
   const u32 n_rays = (u32)(b.sc->ray_chunk >> 40);
   if (b.sc->overflow | *b.poison) return;
   if (p.clean16) {  // pipelined insert: leave the dedupe table zeroed for the next scan's k_classify (its last reader is done)
@@ -769,62 +828,133 @@ __global__ void __launch_bounds__(TPB, MARKD_MIN_BLOCKS) k_mark_dense(ScanParams
   const u32 lane = threadIdx.x & 31;
   const u32 warps = gridDim.x * (TPB / 32);
   const u32 groups = (n_rays + 31u) >> 5;
-  const u64 tiles = (u64)groups * jmax;
-  for (u64 tile = blockIdx.x * (TPB / 32) + (threadIdx.x >> 5); tile < tiles; tile += warps) {
-    const u32 grp = (u32)(tile / jmax), j = (u32)(tile % jmax);
+  const u32 tiles = groups * smax;  // < 2^24 / 32 * 2^7
+  for (u32 tile = blockIdx.x * (TPB / 32) + (threadIdx.x >> 5); tile < tiles; tile += warps) {
+    // group-major order: the warps that run at the same time work at all distances from the sensor (the words next to
+    // the sensor are shared by every ray: few warps should be there at once)
+    const u32 grp = tile / smax, st = tile - grp * smax;
     const u32 r = grp * 32u + lane;
-    u32 nseg = 0;
-    int lx0 = 0, ly0 = 0, lz0 = 0, sx = 1, sy = 1, sz = 1;
+    const u32 k0 = st * SEG;
+    u32 m = 0, ax = 0, ay = 0, az = 0;
+    int sx = 1, sy = 1, sz = 1;
     if (r < n_rays) {
       const int4 ray = b.rays[r];
-      const RayGeom rg = ray_geom(p, ray.x, ray.y, ray.z);
-      if (j < rg.chunks) {
-        u32 k0, k1;
-        chunk_range(rg, j, k0, k1);
-        sx = rg.sx;
-        sy = rg.sy;
-        sz = rg.sz;
-        nseg = walk_chunk<int>(p, rg, k0, k1, lx0, ly0, lz0, s_bits, s_key);  // the window bounds m far below 2^29
+      const int dx = ray.x - p.Ox, dy = ray.y - p.Oy, dz = ray.z - p.Oz;  // the window bounds |d| far below 2^15
+      ax = (u32)abs(dx);
+      ay = (u32)abs(dy);
+      az = (u32)abs(dz);
+      sx = dx < 0 ? -1 : 1;
+      sy = dy < 0 ? -1 : 1;
+      sz = dz < 0 ? -1 : 1;
+      m = max(max(ax, ay), az);  // probabilistic_map.hpp:180: the ray has exactly m cells, the end cell is excluded
+    }
+    const u32 k1 = min(m, k0 + SEG);
+    const u32 steps = __reduce_max_sync(0xffffffffu, k1 > k0 ? k1 - k0 : 0u);
+    if (steps == 0u) continue;  // every ray of the group ends before this stretch
+    int x = p.Ox, y = p.Oy, z = p.Oz;
+    int ex = 0, ey = 0, ez = 0;
+    if (k0 && k0 < m) {
+      const u32 m2 = 2u * m;
+      const u32 px = (2u * k0 * ax + m) / m2, py = (2u * k0 * ay + m) / m2, pz = (2u * k0 * az + m) / m2;
+      ex = (int)(k0 * ax) - (int)(px * m);
+      ey = (int)(k0 * ay) - (int)(py * m);
+      ez = (int)(k0 * az) - (int)(pz * m);
+      x += sx * (int)px;
+      y += sy * (int)py;
+      z += sz * (int)pz;
+    }
+    const int em = (int)m, half = (int)((m + 1u) >> 1);  // (e << 1) >= m  <=>  e >= ceil(m / 2)
+    const int dax = (int)ax, day = (int)ay, daz = (int)az;
+    u32 key = NONE;
+    unsigned long long bits = 0ull;
+    PendingWord pw;
+    pw.word = nullptr;
+    pw.bits = pw.cur = 0ull;
+    pw.blk = 0u;
+    for (u32 c = 0; c < steps; ++c) {
+      if (k0 + c < k1) {
+        const u32 kc = ((u32)((x >> 3) - p.W0x) & 1023u) | (((u32)((y >> 3) - p.W0y) & 1023u) << 10) | (((u32)z & 7u) << 20) |
+                       ((u32)((z >> 3) - p.W0z) << 23);
+        if (kc != key) {
+          if (bits) {
+            commit_word(b, pw);
+            issue_word(p, b, key, bits, pw);
+          }
+          key = kc;
+          bits = 0ull;
+        }
+        bits |= 1ull << (((u32)x & 7u) | (((u32)y & 7u) << 3));
+        ex += dax;
+        ey += day;
+        ez += daz;
+        if (ex >= half) {
+          x += sx;
+          ex -= em;
+        }
+        if (ey >= half) {
+          y += sy;
+          ey -= em;
+        }
+        if (ez >= half) {
+          z += sz;
+          ez -= em;
+        }
       }
     }
-    const u32 nmax = __reduce_max_sync(0xffffffffu, nseg);
-    if (nmax == 0u) continue;  // every ray of the group ends before chunk j
-    const u32 par0 = ((u32)lx0 & 1u) | (((u32)ly0 & 1u) << 1) | (((u32)lz0 & 1u) << 2);
-    for (u32 sgi = 0; sgi < nmax; ++sgi) {
-      const bool has = sgi < nseg;
-      const u32 act = __ballot_sync(0xffffffffu, has);
-      if (!has) continue;
-      const u32 key = s_key[sgi][threadIdx.x];
-      const unsigned long long bits = s_bits[sgi][threadIdx.x];
-      const u32 q = (key >> 3) ^ par0, w = key & 7u;  // q: which axes have crossed into the neighbouring leaf block
-      const u32 blk = dense_block(p, lx0 + ((q & 1u) ? sx : 0), ly0 + ((q & 2u) ? sy : 0), lz0 + ((q & 4u) ? sz : 0));
-      const u32 wkey = blk == NONE ? NONE : blk * 8u + w;
-      const u32 peers = __match_any_sync(act, wkey);
-      const u32 lo = __reduce_or_sync(peers, (u32)bits), hi = __reduce_or_sync(peers, (u32)(bits >> 32));
-      if ((int)lane != __ffs(peers) - 1) continue;
-      if (blk == NONE) {
-        atomicOr(&b.sc->overflow, OVF_WINDOW);
-        continue;
-      }
-      const unsigned long long all = ((unsigned long long)hi << 32) | lo;
-      unsigned long long* word = b.dense + (size_t)blk * 16 + w;
-      const unsigned long long cur = *word;  // test first: a stale L1 line only costs a redundant atomic
-      if ((cur & all) == all) continue;
-      if (cur != 0ull) {
-        atomicOr(word, all);  // result unused: a fire-and-forget reduction
-      } else if (atomicOr(word, all) == 0ull && atomicExch(b.dstamp + blk, p.seq) != p.seq) {
-        const u32 at = atomicAdd(&b.sc->n_touched, 1u);
-        if (at < p.dlist_cap) b.touched[at] = blk;
-      }
+    commit_word(b, pw);
+    if (bits) {
+      issue_word(p, b, key, bits, pw);
+      commit_word(b, pw);
     }
   }
 }
 
-// phase 4, dense flavour: one warp per listed block. The leaf is found — or created: the only place of a dense scan where
-// the map grows — then the block's line of marks is applied to its cells exactly like k_apply_leaves does, and cleared.
-// A block whose leaf cannot be created (pool exhausted: error bit set) keeps its marks; the host grows the pool and runs
-// this kernel again over the same list: blocks that were applied have empty lines and are skipped, so every cell is
-// still updated exactly once ("resume", not "repeat").
+// phase 3b, dense flavour: the bitmap of touched blocks becomes a list (and is cleared for the next scan). One thread
+// per bitmap word, one atomic per warp.
+__global__ void __launch_bounds__(TPB) k_list_blocks(ScanParams p, ScanBuffers b, u32 nwords) {
+  pdl_enter();
+  if (b.sc->overflow | *b.poison) return;
+  const u32 lane = threadIdx.x & 31;
+  for (u32 base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < nwords; base += gridDim.x * blockDim.x) {
+    const u32 i = base + lane;
+    u32 w = i < nwords ? b.dbits[i] : 0u;
+    const u32 cnt = __popc(w);
+    u32 incl = cnt;
+    for (int o = 1; o < 32; o <<= 1) {
+      const u32 v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= (u32)o) incl += v;
+    }
+    const u32 total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0u) continue;
+    u32 at = 0;
+    if (lane == 31) at = atomicAdd(&b.sc->n_touched, total);
+    at = __shfl_sync(0xffffffffu, at, 31) + incl - cnt;
+    if (w) b.dbits[i] = 0u;
+    while (w) {
+      const u32 bit = __ffs(w) - 1u;
+      w &= w - 1u;
+      if (at < p.dlist_cap) b.touched[at] = i * 32u + bit;
+      ++at;
+    }
+  }
+}
+
+// where the leaf of a block probably is: a direct-mapped hint table indexed by a hash of the block's absolute
+// coordinates (4 B per entry: leaf index + 1). A hint is verified against the leaf's own header, so stale or colliding
+// entries only cost the regular look-up.
+constexpr u32 HINT_BITS = 20;
+__device__ __forceinline__ u32 hint_slot(int lx, int ly, int lz) {
+  u32 h = (u32)lx * 0x9E3779B1u ^ (u32)ly * 0x85EBCA77u ^ (u32)lz * 0xC2B2AE3Du;
+  h ^= h >> 15;
+  return h & ((1u << HINT_BITS) - 1u);
+}
+
+// phase 4, dense flavour: one warp per listed block. Its leaf is found through the hint table — or by the regular walk,
+// or created: the only place of a dense scan where the map grows — then the block's line of marks is applied to the
+// leaf's cells exactly like k_apply_leaves does, and the line is cleared. A block whose leaf cannot be created (pool
+// exhausted: error bit set) keeps its marks; the host grows the pool and runs this kernel again over the same list:
+// blocks that were applied have empty lines and are skipped, so every cell is still updated exactly once ("resume",
+// not "repeat").
 __global__ void __launch_bounds__(TPB, APPLY_MIN_BLOCKS) k_apply_dense(GridDev g, ScanParams p, ScanBuffers b, u32 resume) {
   pdl_enter();
   // frozen pipeline (an earlier scan ran short) or a scan that overflowed its scratch: nothing is applied
@@ -838,24 +968,37 @@ __global__ void __launch_bounds__(TPB, APPLY_MIN_BLOCKS) k_apply_dense(GridDev g
   for (; t < n; t += warps) {
     const u32 blk = blk_n;
     blk_n = t + warps < n ? b.touched[t + warps] : NONE;
+    const u32 bx = blk % p.D, by = (blk / p.D) % p.D, bz = blk / (p.D * p.D);
+    const int lx = p.W0x + (int)bx, ly = p.W0y + (int)by, lz = p.W0z + (int)bz;
     u32* line = reinterpret_cast<u32*>(b.dense + (size_t)blk * 16);
     // lane j < 16 holds 32-bit half j of the touched and of the hit mask = the bits of cell row j
-    u32 th = 0, hh = 0;
+    u32 th = 0, hh = 0, ah = 0;
     if (lane < 16) {
       th = line[lane];
       hh = line[16 + lane];
     }
-    if (__ballot_sync(0xffffffffu, (th | hh) != 0u) == 0u) continue;  // applied by an earlier attempt
-    u32 leaf = NONE;
-    if (lane == 0) {
-      const u32 bx = blk % p.D, by = (blk / p.D) % p.D, bz = blk / (p.D * p.D);
-      leaf = leaf_find_or_create(g, (p.W0x + (int)bx) << 3, (p.W0y + (int)by) << 3, (p.W0z + (int)bz) << 3);
+    // the leaf: hint first (verified against the leaf's header, which shares a line with the ON mask)
+    u32* hint = b.dhint + hint_slot(lx, ly, lz);
+    u32 leaf = *hint - 1u;
+    int4 hdr = make_int4(0, 0, 0, 0);
+    if (leaf < g.leaf_cap) {
+      const unsigned char* lp0 = leaf_ptr(g, leaf);
+      hdr = *reinterpret_cast<const int4*>(lp0);
+      if (lane < 16) ah = reinterpret_cast<const u32*>(lp0 + g.off_active)[lane];
     }
-    leaf = __shfl_sync(0xffffffffu, leaf, 0);
-    if (leaf == NONE) continue;  // pool exhausted: the marks stay, the host grows the pool and resumes
+    if (__ballot_sync(0xffffffffu, (th | hh) != 0u) == 0u) continue;  // applied by an earlier attempt
+    if (!(leaf < g.leaf_cap && hdr.x == (lx << 3) && hdr.y == (ly << 3) && hdr.z == (lz << 3) && (hdr.w & 1))) {
+      leaf = NONE;
+      if (lane == 0) {
+        leaf = leaf_find_or_create(g, lx << 3, ly << 3, lz << 3);
+        if (leaf != NONE) *hint = leaf + 1u;
+      }
+      leaf = __shfl_sync(0xffffffffu, leaf, 0);
+      if (leaf == NONE) continue;  // pool exhausted: the marks stay, the host grows the pool and resumes
+      ah = 0;
+      if (lane < 16) ah = reinterpret_cast<const u32*>(leaf_ptr(g, leaf) + g.off_active)[lane];
+    }
     unsigned char* lp = leaf_ptr(g, leaf);
-    u32 ah = 0;
-    if (lane < 16) ah = reinterpret_cast<const u32*>(lp + g.off_active)[lane];
     // lane owns cells it*32 + lane, it = 0..15 (coalesced 128-B rows); bit `it` of mine/on/hit = that cell touched/ON/hit
     u32 mine = 0, on = 0, hit = 0;
 #pragma unroll
@@ -1123,7 +1266,7 @@ __global__ void __launch_bounds__(TPB) k_shard_bucket(ScanParams p, ScanBuffers 
   u32 o = 0;
   if (i < p.n && !*b.poison) {
     const u32 slot = b.slot_of[i];
-    win = slot != NONE && b.table[slot] == ~i;  // not dropped, and the lowest local index of its voxel
+    win = slot != NONE && b.table[slot] == (p.packed ? ~i : i + 1u);  // not dropped, and the lowest local index of its voxel
     if (win) {
       e = b.ep[i];
       o = shard_owner(e.x >> 5, e.y >> 5, e.z >> 5, p.world);
@@ -1162,7 +1305,7 @@ __global__ void __launch_bounds__(TPB) k_shard_dedupe(ScanParams p, ScanBuffers 
     int4 e;
     bool found;
     const u32 received = shard_locate(p, b, i, found, e);
-    if (found) {
+    if (found && p.packed) {
       const u32 mask = shard_table_mask(p, received);
       const unsigned long long key = pack_key(e);
       u32 slot = (u32)hash3(e.x, e.y, e.z) & mask;
@@ -1173,6 +1316,26 @@ __global__ void __launch_bounds__(TPB) k_shard_dedupe(ScanParams p, ScanBuffers 
         slot = (slot + 1) & mask;
       }
       atomicMax(&b.table[slot], ~(u32)e.w);
+      b.slot_of[i] = slot;
+    } else if (found) {
+      // any coordinates (max_range = inf, voxels beyond +-2^20): 16-byte slots {x, y, z, best}, claimed whole by a
+      // 128-bit CAS; best = ~w is never 0, so an all-zero slot is empty
+      const u32 mask = shard_table_mask(p, received);
+      int4* tab = reinterpret_cast<int4*>(b.table);
+      const int4 mine = make_int4(e.x, e.y, e.z, (int)~(u32)e.w);
+      u32 slot = (u32)hash3(e.x, e.y, e.z) & mask;
+      for (;;) {
+        int4 cur = __ldcg(&tab[slot]);
+        if (cur.w == 0) {
+          cur = cas128(&tab[slot], make_int4(0, 0, 0, 0), mine);
+          if (cur.w == 0) break;  // claimed, with this record as the best so far
+        }
+        if (cur.x == e.x && cur.y == e.y && cur.z == e.z) {
+          atomicMax(reinterpret_cast<u32*>(&tab[slot].w), ~(u32)e.w);
+          break;
+        }
+        slot = (slot + 1) & mask;
+      }
       b.slot_of[i] = slot;
     }
     i += stride;
@@ -1352,6 +1515,7 @@ Map::~Map() {
     if (st.classified) cudaEventDestroy(st.classified);
   for (auto& e : x_copied_)
     if (e) cudaEventDestroy(e);
+  if (grown_) cudaEventDestroy(grown_);
   if (h_ring_) cudaFreeHost(h_ring_);
   p2p_close_peers();
   if (mbox_) cudaFree(mbox_);
@@ -1402,6 +1566,7 @@ int Map::init(double resolution) {
   BNX_CUDA(cudaStreamCreateWithFlags(&pre_stream_, cudaStreamNonBlocking));
   for (auto& st : sets_) BNX_CUDA(cudaEventCreateWithFlags(&st.classified, cudaEventDisableTiming));
   for (auto& e : x_copied_) BNX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  BNX_CUDA(cudaEventCreateWithFlags(&grown_, cudaEventDisableTiming));
   buf_.poison = &grid.dev().ctr->error;
   buf_.ring = d_ring_;
   return reserve_scan(0, 16, 1.0);
@@ -1429,7 +1594,7 @@ int Map::reserve_scan(i64 n, i64 stride_bytes, double max_range, i64 table_n) {
     S().sc_clean = S().t1_clean = false;
   }
   BNX_TRY(b_tiles_.reserve(tile_bytes(np, max_range)));
-  BNX_TRY(b_touched_.reserve((size_t)grid.dev().leaf_cap * 4));
+  if (b_touched_.bytes == 0) BNX_TRY(b_touched_.reserve((size_t)grid.dev().leaf_cap * 4));  // grown by the sparse launch path only
   d_sc_ = S().table.as<ScanCounters>();
   buf_.sc = d_sc_;
   buf_.table = reinterpret_cast<u32*>(S().table.as<unsigned char>() + SC_BYTES);
@@ -1485,15 +1650,22 @@ int Map::build_params(i64 n, const double origin[3], double max_range, ScanParam
 // non-zero offset inside the caller's point type, and the base pointer handed in is &points[0].x)
 static size_t cloud_bytes(i64 n, i64 stride_bytes, bool f64) { return n > 0 ? (size_t)(n - 1) * (size_t)stride_bytes + (f64 ? 24u : 12u) : 0u; }
 
-// Dense marking window: every endpoint and every ray cell of a scan lies within max_range of the origin, so
-// when that ball — in 8^3 leaf blocks — is small enough, the per-scan marks go to a dense array addressed by arithmetic
-// (one 128-B line per block) instead of into the leaves. BNX_DENSE=0 forces the leaf-resident ("sparse") marks, which also
-// serve max_range = inf, huge ranges and grids with other inner/leaf bits. The buffers are allocated (and zeroed) once
-// per window size; the apply pass leaves every line it used zeroed again.
+// Dense marking window (EXPERIMENTAL, off by default): every endpoint and every ray cell of a scan lies
+// within max_range of the origin, so when that ball — in 8^3 leaf blocks — is small enough, the per-scan marks can go to
+// a dense array addressed by arithmetic (one 128-B line per block) instead of into the leaves. Bit-exact like the
+// leaf-resident ("sparse") marks, but measured SLOWER on the B200 in all four variants tried (profiles/r2_notes.md), so
+// it only runs when asked for: BNX_DENSE=1 or bnx_map_set_marking(m, 2). The sparse marks serve every scan, including
+// max_range = inf, huge ranges and grids with other inner/leaf bits. The buffers are allocated (and zeroed) once per
+// window size; the apply pass leaves every line it used zeroed again.
+static bool dense_by_default() {
+  static const bool v = [] {
+    const char* e = std::getenv("BNX_DENSE");
+    return e && std::strcmp(e, "1") == 0;
+  }();
+  return v;
+}
 static u32 dense_max_blocks_per_axis() {
   static const u32 v = [] {
-    const char* e = std::getenv("BNX_DENSE");
-    if (e && std::strcmp(e, "0") == 0) return 0u;
     size_t mb = 2048;
     if (const char* m = std::getenv("BNX_DENSE_MAX_MB")) mb = (size_t)std::strtoull(m, nullptr, 10);
     u32 d = 8;
@@ -1504,14 +1676,15 @@ static u32 dense_max_blocks_per_axis() {
 }
 
 int Map::set_marking(int mode) {
-  BNX_REQUIRE(mode == 0 || mode == 1, "set_marking: 0 (automatic) or 1 (sparse)");
+  BNX_REQUIRE(mode >= 0 && mode <= 2, "set_marking: 0 (default), 1 (sparse) or 2 (dense window where the range allows it)");
   BNX_TRY(drain());
-  force_sparse_ = mode == 1;
+  marking_ = mode;
   return BNX_OK;
 }
 
 u32 Map::dense_dim(double max_range) const {
-  const u32 dmax = force_sparse_ ? 0u : dense_max_blocks_per_axis();
+  const bool want_dense = marking_ == 2 || (marking_ == 0 && dense_by_default());
+  const u32 dmax = want_dense ? dense_max_blocks_per_axis() : 0u;
   const GridDev g = grid.dev();
   if (!dmax || g.ib != 2 || g.lb != 3 || !std::isfinite(max_range) || max_range < 0.0) return 0;
   const double reach_d = std::ceil(max_range * grid.inv_resolution) + 3.0;  // |endpoint voxel - origin voxel| stays below this
@@ -1520,25 +1693,36 @@ u32 Map::dense_dim(double max_range) const {
   return D <= dmax ? D : 0;
 }
 
+bool Map::scan_is_dense(const double origin[3], double max_range) const {
+  if (!dense_dim(max_range)) return false;
+  const double reach = std::ceil(max_range * grid.inv_resolution) + 3.0, lim = (double)(1 << 30);
+  for (int k = 0; k < 3; ++k)
+    if (!(std::fabs(std::floor(origin[k] * grid.inv_resolution)) + reach < lim)) return false;
+  return true;
+}
+
 int Map::reserve_dense(ScanParams& p) {
   p.dense = 0;
+  const double o[3] = {p.ox, p.oy, p.oz};
+  if (!scan_is_dense(o, p.max_range)) return BNX_OK;
   const u32 D = dense_dim(p.max_range);
-  if (!D) return BNX_OK;
   const i64 reach = (i64)(std::ceil(p.max_range * p.inv_res) + 3.0);
-  const i64 lim = (1ll << 30);
-  if (std::llabs((i64)p.Ox) + reach >= lim || std::llabs((i64)p.Oy) + reach >= lim || std::llabs((i64)p.Oz) + reach >= lim) return BNX_OK;
   if (D > dense_D_) {
     // (re)allocation: nothing may be in flight (the callers drain first when dense_need() says so)
     const u32 Da = (D + 7u) & ~7u;
     const size_t blocks = (size_t)Da * Da * Da;
     b_dense_.release();
-    b_dstamp_.release();
+    b_dbits_.release();
     b_dlist_.release();
     BNX_TRY(b_dense_.reserve(blocks * 128));
-    BNX_TRY(b_dstamp_.reserve(blocks * 4));
+    BNX_TRY(b_dbits_.reserve(blocks / 8 + 128));
     BNX_TRY(b_dlist_.reserve(blocks * 4));
     BNX_CUDA(cudaMemsetAsync(b_dense_.p, 0, b_dense_.bytes, grid.stream()));
-    BNX_CUDA(cudaMemsetAsync(b_dstamp_.p, 0, b_dstamp_.bytes, grid.stream()));
+    BNX_CUDA(cudaMemsetAsync(b_dbits_.p, 0, b_dbits_.bytes, grid.stream()));
+    if (!b_dhint_.p) {
+      BNX_TRY(b_dhint_.reserve((size_t)4 << HINT_BITS));
+      BNX_CUDA(cudaMemsetAsync(b_dhint_.p, 0, b_dhint_.bytes, grid.stream()));
+    }
     dense_D_ = Da;
   }
   p.dense = 1;
@@ -1570,6 +1754,12 @@ int Map::insert(const void* points, i64 stride_bytes, i64 n, bool f64, const dou
   BNX_TRY(check_insert_args(points, stride_bytes, n, f64, origin, n_pending_));
   BNX_TRY(drain());
   if (!n_pending_ && world_ == 1 && !profiling && sync_via_ring()) {
+    if (where == BNX_DEVICE) {
+      // the synchronous call reads a device buffer in the order of the map's stream (include/bonxai_b200.h): the front
+      // half runs on the internal stream, so that stream waits for what the map's stream has been given so far
+      BNX_CUDA(cudaEventRecord(ev_[0], grid.stream()));
+      BNX_CUDA(cudaStreamWaitEvent(pre_stream_, ev_[0], 0));
+    }
     BNX_TRY(insert_async(points, stride_bytes, n, f64, origin, max_range, where));
     return complete_queue();
   }
@@ -1644,20 +1834,28 @@ int Map::launch_back(cudaStream_t s, ScanParams& p, bool first_attempt) {
   p.touched_cap = (u32)std::min<size_t>(b_touched_.bytes / 4, 0xFFFFFFFFull);
   if (p.dense) {
     buf_.dense = b_dense_.as<unsigned long long>();
-    buf_.dstamp = b_dstamp_.as<u32>();
+    buf_.dbits = b_dbits_.as<u32>();
+    buf_.dhint = b_dhint_.as<u32>();
     buf_.touched = b_dlist_.as<u32>();
     if (n_pending_) launch_scan_kernel(k_resolve<1, true>, blocks_for(n_pending_), TPB, s, g, p, buf_, n_pending_);
     if (n > 0) launch_scan_kernel(k_resolve<0, true>, blocks_for(n), TPB, s, g, p, buf_, (u32)n);
     if (profiling && first_attempt) cudaEventRecord(ev_[3], s);
-    // chunk indices a ray of this window can have: the first (partial) leaf block + one per 8 cells of the reach
-    const u32 jmax = (u32)(std::ceil(p.max_range * p.inv_res) + 3.0) / 8u + 2u;
-    launch_scan_kernel(k_mark_dense, sm_count() * MARKD_MIN_BLOCKS, TPB, s, p, buf_, jmax);
+    // stretches of SEG cells a ray of this window can have
+    const u32 smax = ((u32)(std::ceil(p.max_range * p.inv_res) + 3.0) + SEG - 1u) / SEG;
+    launch_scan_kernel(k_mark_dense, sm_count() * MARKD_MIN_BLOCKS, TPB, s, p, buf_, smax);
     if (profiling && first_attempt) cudaEventRecord(ev_[4], s);
+    const u32 nwords = (p.D * p.D * p.D + 31u) / 32u;
+    launch_scan_kernel(k_list_blocks, std::min<int>(sm_count() * 4, blocks_for(nwords)), TPB, s, p, buf_, nwords);
     launch_scan_kernel(k_apply_dense, sm_count() * APPLY_MIN_BLOCKS, TPB, s, g, p, buf_, 0u);
     BNX_CUDA(cudaGetLastError());
     if (profiling && first_attempt) cudaEventRecord(ev_[5], s);
     buf_.touched = b_touched_.as<u32>();
     return BNX_OK;
+  }
+  if ((size_t)g.leaf_cap * 4 > b_touched_.bytes) {  // pipelined callers have drained before a scan that needs this
+    BNX_TRY(b_touched_.reserve((size_t)g.leaf_cap * 4));
+    buf_.touched = b_touched_.as<u32>();
+    p.touched_cap = (u32)std::min<size_t>(b_touched_.bytes / 4, 0xFFFFFFFFull);
   }
   if (n_pending_) launch_scan_kernel(k_resolve<1, false>, blocks_for(n_pending_), TPB, s, g, p, buf_, n_pending_);
   if (n > 0) launch_scan_kernel(k_resolve<0, false>, blocks_for(n), TPB, s, g, p, buf_, (u32)n);
@@ -1671,34 +1869,24 @@ int Map::launch_back(cudaStream_t s, ScanParams& p, bool first_attempt) {
 }
 
 // a dense scan reported a scratch overflow (a mark outside its window: cannot happen by construction). Nothing was
-// applied; wipe the marks it left so that later scans stay exact, and fail loudly.
-__global__ void __launch_bounds__(TPB) k_clear_dense(ScanBuffers b, u32 n) {
-  const u32 lane = threadIdx.x & 31;
-  const u32 warps = gridDim.x * (TPB / 32);
-  for (u32 t = blockIdx.x * (TPB / 32) + (threadIdx.x >> 5); t < n; t += warps) reinterpret_cast<u32*>(b.dense + (size_t)b.touched[t] * 16)[lane] = 0u;
-}
-
-int Map::dense_internal_error(const ScanCounters& st, const ScanParams& p) {
+// applied; wipe the window so that later scans stay exact, and fail loudly.
+int Map::dense_internal_error(const ScanCounters& st, const ScanParams&) {
   cudaStream_t s = grid.stream();
-  buf_.dense = b_dense_.as<unsigned long long>();
-  buf_.touched = b_dlist_.as<u32>();
-  if (st.n_touched) {
-    note_launch(), k_clear_dense<<<sm_count() * 8, TPB, 0, s>>>(buf_, std::min(st.n_touched, p.dlist_cap));
-    BNX_CUDA(cudaGetLastError());
-    BNX_CUDA(cudaStreamSynchronize(s));
-  }
-  buf_.touched = b_touched_.as<u32>();
+  BNX_CUDA(cudaMemsetAsync(b_dense_.p, 0, b_dense_.bytes, s));
+  BNX_CUDA(cudaMemsetAsync(b_dbits_.p, 0, b_dbits_.bytes, s));
+  BNX_CUDA(cudaStreamSynchronize(s));
   if (st.gc.error) BNX_TRY(grid.recover(st.gc));
   set_error("insert: internal error, a ray cell fell outside the dense marking window (overflow bits " + std::to_string(st.overflow) + ")");
   return BNX_ERR_CUDA;
 }
 
 // dense scans only: the apply pass ran out of leaves / inner nodes / root slots part-way. The pools have been grown;
-// run the pass again over the same list (lines of blocks that were applied are empty) until every block has its leaf.
+// run the pass again over the same list: blocks that were applied have empty lines, the others still hold their marks.
 int Map::resume_apply(cudaStream_t s, ScanParams& p) {
   const GridDev g = grid.dev();
   buf_.dense = b_dense_.as<unsigned long long>();
-  buf_.dstamp = b_dstamp_.as<u32>();
+  buf_.dbits = b_dbits_.as<u32>();
+  buf_.dhint = b_dhint_.as<u32>();
   buf_.touched = b_dlist_.as<u32>();
   buf_.poison = &g.ctr->error;
   note_launch(), k_apply_dense<<<sm_count() * APPLY_MIN_BLOCKS, TPB, 0, s>>>(g, p, buf_, 1u);
@@ -1742,8 +1930,8 @@ int Map::run_scan(const void* d_points, i64 stride_bytes, bool f64, const ScanPa
   const int persistent = sm_count() * 8;
   i64 retries = 0;
   if (p.dense) {
-    // dense marks: only the apply pass can run short (it is the one place where leaves are created); it is RESUMED over
-    // the same list after the pools have grown — blocks that were applied have empty lines
+    // dense marks: only the apply pass can run short (it is the one place where leaves are created); it is RESUMED
+    // after the pools have grown — blocks that were applied have left the bitmap
     BNX_TRY(launch_scan(d_points, stride_bytes, f64, p, true));
     for (;; ++retries) {
       BNX_CUDA(cudaMemcpyAsync(h_status_, d_sc_, sizeof(ScanCounters), cudaMemcpyDeviceToHost, s));
@@ -1855,14 +2043,26 @@ int Map::insert_async(const void* points, i64 stride_bytes, i64 n, bool f64, con
       const u64 ahead = queue_.size() - k;  // scans that may still allocate before we look again
       const u64 leaves_ahead = (u64)r.n_leaves + ahead * max_leaf_growth_, inner_ahead = (u64)r.n_inner + ahead * 64;
       const u64 roots_ahead = (u64)r.n_roots + ahead * 64;
-      if (r.error || leaves_ahead * 2 > g.leaf_cap || inner_ahead * 2 > g.inner_cap || roots_ahead * 2 > (u64)g.root_mask + 1) {
+      // what the scans already queued may still allocate must fit the pools THEY were launched with; one more pipeline
+      // depth of head-room is the trigger for mapping the next step
+      const u64 full = (u64)sets_active_ * max_leaf_growth_, full_inner = (u64)sets_active_ * 64;
+      const bool dense_next = scan_is_dense(origin, max_range);
+      if (r.error || roots_ahead * 2 > (u64)g.root_mask + 1 ||
+          (!dense_next && (leaves_ahead + full > g.leaf_cap || inner_ahead + full_inner > g.inner_cap))) {
+        // the root table is rehashed, or the leaf-sized scratch of the sparse marks re-allocated: nothing may be in flight
         BNX_TRY(drain(false));
-        // grow for what the refilled pipeline may allocate before the next look, not only for what is in use now
-        // (otherwise the same check drains again and again without growing anything)
-        const u64 full = (u64)sets_active_ * max_leaf_growth_;
-        BNX_TRY(grid.ensure_leaf_capacity(((u64)r.n_leaves + full) * 4));
-        BNX_TRY(grid.ensure_inner_capacity(((u64)r.n_inner + (u64)sets_active_ * 64) * 4));
+        BNX_TRY(grid.ensure_leaf_capacity((u64)r.n_leaves + 2 * full + grid.leaf_step(r.n_leaves)));
+        BNX_TRY(grid.ensure_inner_capacity((u64)r.n_inner + 2 * full_inner + grid.inner_step(r.n_inner)));
         if (roots_ahead * 2 > (u64)g.root_mask + 1) BNX_TRY(grid.grow_root_table(((u64)g.root_mask + 1) * 4));
+      } else if (leaves_ahead + full > g.leaf_cap || inner_ahead + full_inner > g.inner_cap) {
+        // dense marks: nothing of a scan's scratch depends on the pool size, and mapping memory behind the pools does not
+        // wait for the kernels in flight (VMM) — grow AHEAD, in the background: the zero fill runs on the copy stream and
+        // only the scans enqueued from now on (which see the larger pool) wait for it
+        BNX_TRY(grid.ensure_leaf_capacity((u64)r.n_leaves + 2 * full + grid.leaf_step(r.n_leaves), copy_stream_));
+        BNX_TRY(grid.ensure_inner_capacity((u64)r.n_inner + 2 * full_inner + grid.inner_step(r.n_inner), copy_stream_));
+        BNX_CUDA(cudaEventRecord(grown_, copy_stream_));
+        BNX_CUDA(cudaStreamWaitEvent(s, grown_, 0));
+        ++grown_ahead_;
       } else if (k > 0) {
         const AsyncRecord& q = h_ring_[queue_[k - 1].p.async_id & (RING - 1)];
         if (q.id == queue_[k - 1].p.async_id && r.n_leaves > q.n_leaves) max_leaf_growth_ = std::max<u64>(max_leaf_growth_, r.n_leaves - q.n_leaves);
@@ -1870,8 +2070,9 @@ int Map::insert_async(const void* points, i64 stride_bytes, i64 n, bool f64, con
       break;
     }
   }
-  // buffers shared by all scans in flight (stream-ordered use) must not be reallocated under them
-  if ((size_t)grid.dev().leaf_cap * 4 > b_touched_.bytes || ((size_t)n + 32) * sizeof(int4) > b_rays_.bytes ||
+  // buffers shared by all scans in flight (stream-ordered use) must not be reallocated under them (the leaf-sized list
+  // belongs to the sparse marks only)
+  if ((!scan_is_dense(origin, max_range) && (size_t)grid.dev().leaf_cap * 4 > b_touched_.bytes) || ((size_t)n + 32) * sizeof(int4) > b_rays_.bytes ||
       tile_bytes((size_t)n + 32, max_range) > b_tiles_.bytes) {
     BNX_TRY(drain(false));
   }
@@ -2026,7 +2227,7 @@ int Map::drain_queue() {
   if (!gc.error) return grid.maintain(gc);
   if (q[done].p.dense) {
     // dense marks: the failed scan's apply pass ran out of pool space part-way (later scans skipped themselves, so its
-    // list and its window are intact): grow, RESUME the pass — applied blocks have empty lines — then replay the rest
+    // window is intact): grow, RESUME the pass — applied blocks have left the bitmap — then replay the rest
     ScanParams fp = q[done].p;
     buf_.sc = d_sc_ = sets_[set_].table.as<ScanCounters>();
     ScanCounters st = *h_status_;
@@ -2213,10 +2414,6 @@ int Map::shard_begin(const void* points, i64 stride_bytes, i64 n, bool f64, u32 
   const double reach = std::ceil(max_range * grid.inv_resolution) + 4.0, lim = (double)(1 << 20) - 1.0;
   p.packed = std::isfinite(max_range) && max_range >= 0.0 && std::fabs((double)p.Ox) + reach < lim &&
              std::fabs((double)p.Oy) + reach < lim && std::fabs((double)p.Oz) + reach < lim;
-  if (!p.packed) {
-    set_error("sharded insert needs a finite max_range and |voxel coordinates| < 2^20");
-    return BNX_ERR_UNSUPPORTED;
-  }
   const u64 tslots = table_slots(cap_records);
   p.hash_mask = (u32)(tslots - 1);
   sp_ = p;
@@ -2239,11 +2436,11 @@ int Map::shard_begin(const void* points, i64 stride_bytes, i64 n, bool f64, u32 
   if (n > 0) {
     const unsigned char* pts = static_cast<const unsigned char*>(d_points);
     if (f64) {
-      launch_classify<true, false>(true, blocks, s, pts, (u32)stride_bytes, p, buf_);
+      launch_classify<true, false>(p.packed, blocks, s, pts, (u32)stride_bytes, p, buf_);
     } else if (stride_bytes == 16 && (reinterpret_cast<uintptr_t>(pts) & 15u) == 0) {
-      launch_classify<false, true>(true, blocks, s, pts, 16u, p, buf_);
+      launch_classify<false, true>(p.packed, blocks, s, pts, 16u, p, buf_);
     } else {
-      launch_classify<false, false>(true, blocks, s, pts, (u32)stride_bytes, p, buf_);
+      launch_classify<false, false>(p.packed, blocks, s, pts, (u32)stride_bytes, p, buf_);
     }
   }
   // always launched: its last block writes the block headers (counts) and, with mailboxes, the arrival stamps
@@ -2283,16 +2480,18 @@ int Map::shard_resolve_mark(const void* recv_records, void* send_leaves, i64 cap
   // receiver-side dedupe table [table u32[t2] | keys u64[t2]]: large enough for the worst case (every record of every
   // rank lands here); the kernels only use — and, pipelined, zero again — the part the arrived records need
   const u64 t1 = table_slots(p.rec_cap), t2 = table_slots(slots);
+  // packed keys: [table u32[t2] | keys u64[t2]] (12 B per slot); any coordinates: int4[t2] (16 B per slot)
   const void* before = b_table2_.p;
-  BNX_TRY(b_table2_.reserve(t2 * 12));
-  if (b_table2_.p != before) t2_clean_ = false;
+  BNX_TRY(b_table2_.reserve(t2 * 16));
+  if (b_table2_.p != before || t2_packed_ != (p.packed != 0u)) t2_clean_ = false;
+  t2_packed_ = p.packed != 0u;
   uint4* table1 = reinterpret_cast<uint4*>(S().table.as<unsigned char>() + SC_BYTES);
   buf_.table = b_table2_.as<u32>();
   buf_.keys = reinterpret_cast<unsigned long long*>(b_table2_.as<unsigned char>() + t2 * 4);
   p.hash_mask = (u32)(t2 - 1);
   const bool lean = shard_async_ && shard_attempt_ == 0;
   if (shard_attempt_ > 0) BNX_CUDA(cudaMemsetAsync(d_sc_, 0, SC_BYTES, s));  // a retry: counters of the failed attempt
-  if (!(lean && t2_clean_)) BNX_CUDA(cudaMemsetAsync(b_table2_.p, 0, t2 * 12, s));
+  if (!(lean && t2_clean_)) BNX_CUDA(cudaMemsetAsync(b_table2_.p, 0, t2 * 16, s));
   t2_clean_ = lean;
   p.clean16 = lean ? 1u : 0u;
   ++shard_attempt_;

@@ -92,7 +92,8 @@ struct ScanBuffers {
   int4* pending;     // queued addHitPoint/addMissPoint endpoints (xyz, type)
   u32* touched2;     // sharded: scratch-grid leaves touched in this scan
   unsigned long long* dense;  // dense window: per block {u64 touched[8]; u64 hit[8]} = one 128-B line, all zero between scans
-  u32* dstamp;       // dense window: per block, serial of the last scan that listed it
+  u32* dbits;        // dense window: one bit per block, set when the block gets its first mark of the scan
+  u32* dhint;        // leaf hint table: hash of absolute block coordinates -> leaf index + 1 (verified on use)
   const int4* recs;  // sharded: received endpoint records, [world][rec_cap], element 0 of a block = {count}
   const u32* gate;   // sharded: all-reduced error flags; the apply kernels skip when any is set (NULL otherwise)
   const u32* my_flags;  // sharded, peer-memory exchange: this rank's mailbox flag area (NULL: exchanges run by the caller)
@@ -116,8 +117,9 @@ class Map {
     use_next_T_ = true;
   }
   void clear_next_transform() { use_next_T_ = false; }
-  // where a scan keeps its per-scan marks: 0 = automatic (the dense window when the range allows it), 1 = always in the
-  // leaves ("sparse", the only flavour for max_range = inf or non-default grid bits)
+  // where a scan keeps its per-scan marks: 1 = in the leaves ("sparse": serves every scan), 2 = in the dense window
+  // around the origin when the range allows it (experimental: exact, but slower as measured), 0 = default (sparse
+  // unless BNX_DENSE=1)
   int set_marking(int mode);
 
   // ---- root-key sharding across processes (one map shard per GPU), as stages: with caller-owned exchange buffers the
@@ -179,13 +181,16 @@ class Map {
 
   ScanBuffers buf_ = {};
   DevBuf b_pts_, b_rays_, b_tiles_, b_touched_, b_touched2_, b_pending_, b_q_xyz_, b_q_out_;
-  DevBuf b_dense_, b_dstamp_, b_dlist_;  // dense marking window (allocated at the first scan that can use it)
-  bool force_sparse_ = false;
+  DevBuf b_dense_, b_dbits_, b_dhint_, b_dlist_;  // dense marking window (allocated at the first scan that can use it)
+  int marking_ = 0;
   u32 dense_D_ = 0;                      // blocks per axis the window buffers are sized (and zeroed) for
   int reserve_dense(ScanParams& p);      // decides p.dense and sizes the window
   int resume_apply(cudaStream_t s, ScanParams& p);
   int dense_internal_error(const ScanCounters& st, const ScanParams& p);
   u32 dense_dim(double max_range) const;  // blocks per axis a scan of this range needs (0: not eligible)
+  bool scan_is_dense(const double origin[3], double max_range) const;
+  cudaEvent_t grown_ = nullptr;  // pools grown ahead of need: the zero fill on the copy stream
+  i64 grown_ahead_ = 0;          // how often that happened (statistics)
   // Scratch written BEFORE a scan touches the map (classify: endpoints, their dedupe table, the counters) exists once
   // per scan in flight: the pipelined insert classifies on its own stream, many scans ahead of the map updates.
   // The synchronous and the sharded paths use set 0.
@@ -241,6 +246,7 @@ class Map {
   u32 shard_async_id_ = 0, shard_attempt_ = 0;
   i64 shard_n_max_ = 0;
   bool t2_clean_ = false;  // pipelined: receiver table known to be zero
+  bool t2_packed_ = true;  // flavour of the receiver table the last scan used
   DevBuf b_table2_;        // receiver-side dedupe table
   void shard_phase_times();
   struct ShardQueued {

@@ -211,10 +211,11 @@ BNX_API int bnx_map_counters(bnx_map_t* m, int64_t out[8]);
 /* _update_count, probabilistic_map.hpp:129 (cycles 1,2,3) */
 BNX_API int bnx_map_update_count(const bnx_map_t* m, int* value);
 /* Where insertPointCloud keeps the per-scan marks of updateFreeCells (probabilistic_map.cpp:77-106: which cells some ray
- * crossed, which are hit endpoints): mode 0 (default) = a dense window of 8^3 blocks around the origin, addressed by
- * arithmetic, whenever max_range is finite and the window fits (BNX_DENSE_MAX_MB, default 2048 MB; needs the default
- * inner/leaf bits); mode 1 = always inside the leaves (the flavour that also serves max_range = inf). Results are
- * identical; the call completes queued scans first. */
+ * crossed, which are hit endpoints): mode 1 = inside the leaves (serves every scan); mode 2 = EXPERIMENTAL: a dense
+ * window of 8^3 blocks around the origin, addressed by arithmetic, whenever max_range is finite and the window fits
+ * (BNX_DENSE_MAX_MB, default 2048 MB; needs the default inner/leaf bits) — bit-identical results, but measured slower on
+ * the B200 (profiles/r2_notes.md); mode 0 (default) = mode 1 unless the environment says BNX_DENSE=1. The call completes
+ * queued scans first. */
 BNX_API int bnx_map_set_marking(bnx_map_t* m, int mode);
 /* device time of the phases of the last insert in microseconds (CUDA events; enabled by
  * bnx_map_set_profiling(m,1)): {h2d, classify, resolve, mark, apply, total, 0, 0} */

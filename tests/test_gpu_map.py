@@ -17,17 +17,17 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 DEFAULT_OPTS = [-405465, 847297, -1992430, 3476099, 0]
 
 
-@pytest.fixture(autouse=True, params=["auto", "sparse"])
+@pytest.fixture(autouse=True, params=["sparse", "dense"])
 def marking(request, monkeypatch):
-    """every test of this file runs twice: with the automatic choice of where a scan keeps its marks (the dense window
-    whenever max_range is finite and small enough) and with the marks forced into the leaves (bnx_map_set_marking)"""
-    if request.param == "sparse":
+    """every test of this file runs twice: with the per-scan marks in the leaves (the default) and with the experimental
+    dense marking window wherever max_range is finite and small enough (bnx_map_set_marking)"""
+    if request.param == "dense":
         from bonxai_b200 import capi
         orig = capi.ProbabilisticMap.__init__
 
         def init(self, *a, **k):
             orig(self, *a, **k)
-            self.set_marking("sparse")
+            self.set_marking("dense")
 
         monkeypatch.setattr(capi.ProbabilisticMap, "__init__", init)
     return request.param
@@ -292,13 +292,14 @@ def test_refused_scan_leaves_the_map_clean(bnx, port):
     bad[5] = [3.0e7, 1.0e7, 0.0]  # 3e8 cells at 0.1 m: more than 2^40 / 70000 chunks of 8 cells
     nxt = rng.normal(0, 2.0, (50000, 3)).astype(np.float32)
     empty = np.zeros((0, 3), np.float32)
-    # synchronous call: the refused scan does not consume an update id
+    # synchronous call: the refused scan changes nothing but consumes its update id, like an empty scan
     gm, om = bnx.ProbabilisticMap(0.1), port.map(0.1)
     gm.insert(good, [0, 0, 0], inf)
     om.insert(good, [0, 0, 0], inf)
     with pytest.raises(bnx.BonxaiError) as err:
         gm.insert(bad, [0, 0, 0], inf)
     assert err.value.status == 5
+    om.insert(empty, [0, 0, 0], 1.0)
     check_scan(gm, om, "right after the refused scan", counters=False)
     for k in range(3):
         gm.insert(nxt, [0.1 * k, 0, 0], 6.0)

@@ -52,6 +52,28 @@ def test_local_shard_group_random_and_stale(bnx, port, exchange):
 
 
 @pytest.mark.parametrize("exchange", ["transpose", "p2p"])
+def test_local_shard_group_infinite_range_and_far_coordinates(bnx, port, exchange):
+    """the ROS node's default call — max_range = +inf (bonxai_ros/src/bonxai_server.cpp:56,177-182) — and voxel
+    coordinates beyond +-2^20 on a sharded map: sender and receiver fall back from the packed 63-bit dedupe keys to the
+    any-coordinate tables (the receiver's slots are claimed with a 128-bit CAS)"""
+    from bonxai_b200.sharded import LocalShardGroup
+    rng = np.random.default_rng(41)
+    g, om = LocalShardGroup(0.1, 3, exchange=exchange), port.map(0.1)
+    inf = float("inf")
+    far = np.float32([3.0e5, -2.5e5, 1.0e5])  # 3e6 voxels from the origin: does not fit 21 bits per axis
+    scans = [(rng.normal(0, 3.0, (6000, 3)).astype(np.float32), np.float32([0, 0, 0]), inf),
+             (rng.normal(0, 3.0, (6000, 3)).astype(np.float32), np.float32([0.3, 0, 0]), 4.0),   # packed again in between
+             ((rng.normal(0, 3.0, (5000, 3)) + far).astype(np.float32), far, 6.0),
+             ((rng.normal(0, 3.0, (5000, 3)) + far).astype(np.float32), far, inf),
+             (rng.normal(0, 3.0, (6000, 3)).astype(np.float32), np.float32([0.1, 0.2, 0]), inf)]
+    scans[0][0][:300] = scans[0][0][0]  # duplicates split across ranks: the lowest global index wins
+    for k, (pts, o, r) in enumerate(scans):
+        g.insert(pts, o, r)
+        om.insert(pts, o, r)
+        assert_same_dump(g.dump(), om.dump(), f"scan {k} range {r}")
+
+
+@pytest.mark.parametrize("exchange", ["transpose", "p2p"])
 def test_local_shard_group_one_owner_gets_everything(bnx, port, exchange):
     """all endpoints and rays inside ONE root (3.2 m cube): a single rank receives the records of every rank, more
     than the receiving kernels are launched for (they loop), the other ranks receive nothing"""
