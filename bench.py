@@ -204,16 +204,25 @@ def run_reference(args):
     # the GPU arm at N > 1 inserts N x denser scans (N x 2048 azimuths) into one sharded map: same scans here.
     # Scans are generated one by one and the timed sample stops after REFERENCE_BUDGET_S of CPU time, so that the
     # arm ends within a few minutes whatever --steps says (one 8 x 131,072-point scan costs the CPU ~0.7 s).
-    az = AZ * max(1, args.gpus)
-    n_pts = BEAMS * az
+    fleet = args.gpus > 1 and args.workload == "fleet"
+    az = AZ * max(1, args.gpus) if not fleet else AZ
+    n_pts = BEAMS * az * (args.gpus if fleet else 1)
     lib, kind = load_cpu_oracle()
     m = lib.map(RES)
     secs, n = 0.0, 0
     for i in range(args.warmup + args.steps):
-        pts, origin = synth.lidar_scan(i, beams=BEAMS, azimuths=az)
-        m.insert(pts, origin, MAX_RANGE)
+        if fleet:  # one step = the scans of all vehicles, inserted one after the other (the reference has no other way)
+            step_s = 0.0
+            for sensor in range(args.gpus):
+                pts, origin = fleet_scan((i, sensor))
+                m.insert(pts, origin, MAX_RANGE)
+                step_s += m.last_insert_seconds()
+        else:
+            pts, origin = synth.lidar_scan(i, beams=BEAMS, azimuths=az)
+            m.insert(pts, origin, MAX_RANGE)
+            step_s = m.last_insert_seconds()
         if i >= args.warmup:
-            secs += m.last_insert_seconds()
+            secs += step_s
             n += 1
             if secs >= REFERENCE_BUDGET_S:
                 break
@@ -222,7 +231,7 @@ def run_reference(args):
         "impl": "reference", "metric": "insertPointCloud points/sec", "value": pts_s, "unit": "points/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "steps_timed": n, "ms_per_step": 1e3 * secs / n, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64+int32", "data": "synthetic",
-        "config": {"workload": WORKLOAD if args.gpus <= 1 else f"lidar64x{az}_seq({n_pts} pts/scan, res 0.1 m, max_range 50 m, 1 m/scan)",
+        "config": {"workload": WORKLOAD if args.gpus <= 1 else sharded_workload_name(args.gpus, args.workload),
                    "points_per_scan": n_pts, "host": "single-threaded reference CPU path"},
         "cpu_baseline": {"value": pts_s, "unit": "points/s", "cores": 1, "kind": kind,
                          "sample": f"scans {args.warmup}..{args.warmup + n - 1} of the same sequence, one map ({n} of the {args.steps} steps: "
@@ -480,6 +489,27 @@ def _full_scan(job):
     return synth.lidar_scan(scan, beams=BEAMS, azimuths=azimuths)
 
 
+FLEET_SPACING = 150.0  # metres between the parallel streets of the fleet workload (> 2 x max_range + margin)
+
+
+def fleet_scan(job):
+    """scan `step` of vehicle `sensor`: the config-#3 generator with its own seed (other buildings), on a street
+    FLEET_SPACING * sensor metres to the side; pcl::PointXYZ layout"""
+    step, sensor = job
+    pts, origin = synth.lidar_scan(step, beams=BEAMS, azimuths=AZ, seed=7 + sensor)
+    shift = np.float32([0.0, FLEET_SPACING * sensor, 0.0])
+    pts = pts.copy()
+    pts[:, :3] += shift
+    return pts, origin + shift
+
+
+def sharded_workload_name(world: int, kind: str) -> str:
+    if kind == "fleet":
+        return (f"fleet of {world} lidar64x2048 vehicles on parallel streets {FLEET_SPACING:.0f} m apart, one scan per vehicle and step "
+                f"({world} x 131072 pts/step, res 0.1 m, max_range 50 m, 1 m/step) into ONE map")
+    return f"lidar64x{AZ * world}_seq({BEAMS * AZ * world} pts/scan = {world} x 131072, res 0.1 m, max_range 50 m, 1 m/scan)"
+
+
 PARITY_SCANS = 8  # scans of the in-run parity check (sharded map == 1-GPU map == CPU oracle, by digest)
 
 
@@ -492,23 +522,33 @@ def run_gpu_sharded(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     K, W = args.steps, args.warmup
     total = W + K
+    fleet = args.workload == "fleet"
     az = AZ * world
-    n_scan = BEAMS * az
+    n_scan = BEAMS * az  # points per step over all ranks (fleet: world scans of 131,072 points)
     lo, hi = [(n_scan * r) // world for r in (rank, rank + 1)]
     import multiprocessing as mp
     procs = min(total, max(1, ((os.cpu_count() or 2) - 1) // world), 16)
-    jobs = [(s, az, lo, hi) for s in range(total)]
     n_parity = min(PARITY_SCANS, total)
+    # the whole steps of the parity check (rank 0 feeds them to a 1-GPU map and to the CPU oracle, scan after scan)
+    if fleet:
+        jobs, fn = [(s, rank) for s in range(total)], fleet_scan
+        full_jobs, full_fn = [(s, v) for s in range(n_parity) for v in range(world)], fleet_scan
+    else:
+        jobs, fn = [(s, az, lo, hi) for s in range(total)], _slice_scan
+        full_jobs, full_fn = [(s, az) for s in range(n_parity)], _full_scan
     full = []
     if procs > 1:
         with mp.get_context("fork").Pool(procs) as pool:
-            slices = pool.map(_slice_scan, jobs, chunksize=max(1, total // (procs * 4)))
-            if rank == 0:  # the whole scans of the parity check (rank 0 feeds them to a 1-GPU map and to the CPU oracle)
-                full = pool.map(_full_scan, [(s, az) for s in range(n_parity)])
+            slices = pool.map(fn, jobs, chunksize=max(1, total // (procs * 4)))
+            if rank == 0:
+                full = pool.map(full_fn, full_jobs)
     else:
-        slices = [_slice_scan(j) for j in jobs]
+        slices = [fn(j) for j in jobs]
         if rank == 0:
-            full = [_full_scan((s, az)) for s in range(n_parity)]
+            full = [full_fn(j) for j in full_jobs]
+    # fleet: the origins of ALL vehicles at every step (the street offsets are exact in float32)
+    origins = [np.array([slices[i][1] + np.float32([0.0, FLEET_SPACING * (v - rank), 0.0]) for v in range(world)], np.float64)
+               for i in range(total)] if fleet else None
 
     import torch
     import torch.distributed as dist
@@ -549,8 +589,14 @@ def run_gpu_sharded(args):
     # ---------------- in-run parity: sharded map == 1-GPU map == CPU oracle after the first scans (digests) ------------
     with _stdout_to_stderr():
         sm = ShardedMap(RES, bootstrap=bootstrap)
+    def put(m, inp, i):
+        if fleet:
+            m.insert_fleet(inp, n_local, 16, n_max, origins[i], MAX_RANGE, use_async=True)
+        else:
+            m.insert(inp, n_local, 16, lo, n_max, slices[i][1], MAX_RANGE, use_async=True)
+
     for i in range(n_parity):
-        sm.insert(capi.DevPtr(dev[i].data_ptr()), n_local, 16, lo, n_max, slices[i][1], MAX_RANGE, use_async=True)
+        put(sm, capi.DevPtr(dev[i].data_ptr()), i)
     sm.sync()
     dig_sharded = sm.digest()  # collective: combined over the ranks
     parity = None
@@ -576,7 +622,7 @@ def run_gpu_sharded(args):
         with _stdout_to_stderr():
             m = ShardedMap(RES, bootstrap=bootstrap)
         for i in range(W):
-            m.insert(inputs[i], n_local, 16, lo, n_max, slices[i][1], MAX_RANGE, use_async=True)
+            put(m, inputs[i], i)
         m.sync()
         st0, t0s = m.stats(), m.totals()
         barrier()
@@ -587,7 +633,7 @@ def run_gpu_sharded(args):
         calls = []
         for i in range(W, total):
             tc = time.perf_counter()
-            m.insert(inputs[i], n_local, 16, lo, n_max, slices[i][1], MAX_RANGE, use_async=True)
+            put(m, inputs[i], i)
             calls.append(time.perf_counter() - tc)
         enq = time.perf_counter() - tw
         e1.record(stream)
@@ -622,7 +668,7 @@ def run_gpu_sharded(args):
     sm.map.set_profiling(True)
     acc, reps = {}, min(20, K)
     for i in range(W, W + reps):
-        sm.insert(dev_inputs[i], n_local, 16, lo, n_max, slices[i][1], MAX_RANGE, use_async=True)
+        put(sm, dev_inputs[i], i)
         sm.sync()
         pt = sm.map.phase_times()
         for k, name in (("classify", "begin"), ("resolve", "resolve_mark"), ("mark", "merge"), ("apply", "apply"), ("total", "total")):
@@ -658,7 +704,7 @@ def run_gpu_sharded(args):
             "metric": "insertPointCloud points/sec", "value": K * n_scan / secs, "unit": "points/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64+int32", "data": "synthetic",
             "value_runs_ms_per_step": [r["ms_max"] / K for r in runs], "value_reported": "min of the runs (max over ranks each)",
-            "config": {"workload": f"lidar64x{az}_seq({n_scan} pts/scan = {world} x 131072, res 0.1 m, max_range 50 m, 1 m/scan)",
+            "config": {"workload": sharded_workload_name(world, args.workload),
                        "points_per_scan": n_scan, "points_per_gpu_per_scan": n_local,
                        "parallelism": f"one map sharded by root key over {world} GPUs, pipelined (no host sync per scan); " + (
                            "per scan two record exchanges + one flag exchange as NVLink peer-memory stores from the producing kernels into the owners' "
@@ -695,6 +741,9 @@ def run_gpu_sharded(args):
 
 
 def main():
+    if os.environ.get("BNX_BENCH_WATCHDOG"):  # debugging aid: dump every thread's Python stack and exit if the run hangs
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["BNX_BENCH_WATCHDOG"]), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)
@@ -703,6 +752,9 @@ def main():
     ap.add_argument("--cpu-scans", type=int, default=60, help="scans timed for the cpu_baseline (about 10-15 s)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-dropin", action="store_true", help="skip the C++ drop-in arm (e2e_dropin / e2e_insert_publish)")
+    ap.add_argument("--workload", default="fleet", choices=["fleet", "dense-scan"],
+                    help="N > 1: 'fleet' = N vehicles, one 131,072-point scan each per step, into one sharded map (work grows with N); "
+                         "'dense-scan' = ONE sensor whose scan is N x denser (round 1's workload: same voxels, more points)")
     ap.add_argument("--mode", default="sharded", choices=["sharded", "replicas"],
                     help="N > 1: one root-key-sharded map (default) or N independent maps")
     args = ap.parse_args()

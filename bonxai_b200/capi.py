@@ -39,7 +39,7 @@ SYMBOLS = [
     "bnx_map_publish_occupied_f32", "bnx_map_insert_transformed_f32", "bnx_map_insert_async_f32", "bnx_map_insert_async_f64", "bnx_map_totals",
     "bnx_map_shard_config", "bnx_map_shard_begin", "bnx_map_shard_resolve_mark", "bnx_map_shard_merge", "bnx_map_shard_finish",
     "bnx_nccl_unique_id", "bnx_map_shard_comm_init", "bnx_map_shard_insert",
-    "bnx_map_shard_p2p_alloc", "bnx_map_shard_p2p_attach", "bnx_map_shard_exchange", "bnx_map_shard_host_init", "bnx_map_shard_stats",
+    "bnx_map_shard_p2p_alloc", "bnx_map_shard_p2p_attach", "bnx_map_shard_exchange", "bnx_map_shard_host_init", "bnx_map_shard_stats", "bnx_map_shard_set_fleet",
 ]
 
 

@@ -377,6 +377,10 @@ int bnx_map_shard_stats(bnx_map_t* h, int64_t out[8]) {
   std::memcpy(out, h->m.shard_stats, sizeof(int64_t) * 8);
   return BNX_OK;
 }
+int bnx_map_shard_set_fleet(bnx_map_t* h, const double* origins) {
+  BNX_HANDLE(h);
+  return h->m.set_fleet(origins);
+}
 int bnx_map_shard_exchange(const bnx_map_t* h, int* kind) {
   BNX_HANDLE(h);
   BNX_REQUIRE(kind != nullptr, "null output");

@@ -294,11 +294,20 @@ struct RayGeom {
   u32 ax, ay, az, m;
   int sx, sy, sz;
   u32 len0, chunks;
+  int Ox, Oy, Oz;  // origin voxel of the ray's sensor
 };
 
-__device__ __forceinline__ RayGeom ray_geom(const ScanParams& p, int ex, int ey, int ez) {
+// update id and origin voxel of sensor `src`: a fleet step (sharded map) inserts the scans of sensors 0..world-1 as if one
+// after the other, so sensor s uses the id the s-th of those inserts would have had (probabilistic_map.cpp:103-105)
+__device__ __forceinline__ u32 scan_c(const ScanParams& p, u32 src) { return p.fleet ? (p.c - 1u + src) % 3u + 1u : p.c; }
+constexpr u32 LEAF_MASK = 0x0FFFFFFFu;  // touched-list entry of a fleet step = leaf | sensor << 28
+
+__device__ __forceinline__ RayGeom ray_geom(const ScanParams& p, int ex, int ey, int ez, u32 src = 0) {
   RayGeom r;
-  const i64 dx = (i64)ex - p.Ox, dy = (i64)ey - p.Oy, dz = (i64)ez - p.Oz;
+  r.Ox = p.fleet ? p.fO[src][0] : p.Ox;
+  r.Oy = p.fleet ? p.fO[src][1] : p.Oy;
+  r.Oz = p.fleet ? p.fO[src][2] : p.Oz;
+  const i64 dx = (i64)ex - r.Ox, dy = (i64)ey - r.Oy, dz = (i64)ez - r.Oz;
   r.ax = (u32)(dx < 0 ? -dx : dx);
   r.ay = (u32)(dy < 0 ? -dy : dy);
   r.az = (u32)(dz < 0 ? -dz : dz);
@@ -306,7 +315,7 @@ __device__ __forceinline__ RayGeom ray_geom(const ScanParams& p, int ex, int ey,
   r.sy = dy < 0 ? -1 : 1;
   r.sz = dz < 0 ? -1 : 1;
   r.m = max(max(r.ax, r.ay), r.az);
-  const int Oa = r.ax == r.m ? p.Ox : (r.ay == r.m ? p.Oy : p.Oz);
+  const int Oa = r.ax == r.m ? r.Ox : (r.ay == r.m ? r.Oy : r.Oz);
   const int sa = r.ax == r.m ? r.sx : (r.ay == r.m ? r.sy : r.sz);
   r.len0 = sa > 0 ? 8u - ((u32)Oa & 7u) : ((u32)Oa & 7u) + 1u;
   r.chunks = r.m == 0u ? 0u : (r.m <= r.len0 ? 1u : 1u + (r.m - r.len0 + 7u) / 8u);
@@ -326,7 +335,7 @@ __device__ __forceinline__ unsigned long long warp_incl_scan(unsigned long long 
 
 // OR `bits` into word w of a per-scan leaf mask (touched or hit); defined with the mark kernel below
 __device__ __forceinline__ void mark_bits(const GridDev& G, u32 leaf, unsigned long long* word, unsigned long long bits, u32 seq, u32* n_list, u32* list,
-                                          u32 cap);
+                                          u32 cap, u32 tag = 0);
 
 // which root does which rank own (map sharding)? Uses the upper hash bits: the root table slot uses the lower.
 __host__ __device__ __forceinline__ u32 shard_owner(int rx, int ry, int rz, u32 world) {
@@ -360,7 +369,7 @@ __device__ __forceinline__ u32 shard_slot_best(const ScanParams& p, const ScanBu
 // the receiving kernels are fully used whatever the split between the senders is.
 // Called by FULL warps: lane s reads the header of block s, a warp scan turns the counts into ranges. Returns R and, for
 // i < R, the record itself.
-__device__ __forceinline__ u32 shard_locate(const ScanParams& p, const ScanBuffers& b, u32 i, bool& found, int4& e) {
+__device__ __forceinline__ u32 shard_locate(const ScanParams& p, const ScanBuffers& b, u32 i, bool& found, int4& e, u32* from = nullptr) {
   const u32 lane = threadIdx.x & 31;
   u32 incl = lane < p.world ? min((u32)__ldcg(&b.recs[(size_t)lane * p.rec_cap]).x, p.rec_cap - 1u) : 0u;
   for (int o = 1; o < 32; o <<= 1) {
@@ -375,6 +384,7 @@ __device__ __forceinline__ u32 shard_locate(const ScanParams& p, const ScanBuffe
     if (!found && i >= base && i < end) {
       found = true;
       e = __ldcg(&b.recs[(size_t)src * p.rec_cap + 1u + (i - base)]);
+      if (from) *from = src;
     }
     base = end;
   }
@@ -420,9 +430,9 @@ __global__ void __launch_bounds__(TPB) k_resolve(GridDev g, ScanParams p, ScanBu
 
   bool is_end = false, winner = false;
   int4 e = make_int4(0, 0, 0, 0);
-  u32 leaf = NONE, ci = 0, m = 0, chunks = 0;
+  u32 leaf = NONE, ci = 0, m = 0, chunks = 0, src = 0;  // src: the rank a record came from = its sensor in a fleet step
   if (MODE == 2) {
-    received = shard_locate(p, b, i, winner, e);
+    received = shard_locate(p, b, i, winner, e, &src);
     if (winner) {
       winner = shard_slot_best(p, b, b.slot_of[i]) == ~(u32)e.w;
       e.w &= 1;
@@ -458,14 +468,14 @@ __global__ void __launch_bounds__(TPB) k_resolve(GridDev g, ScanParams p, ScanBu
         const u64 act = leaf_active(g, leaf)[ci >> 6];
         const u32 raw = reinterpret_cast<const u32*>(leaf_cells(g, leaf))[ci];
         const u32 word = ((act >> (ci & 63)) & 1ull) ? raw : 0u;
-        stale = (word & 0xFu) == p.c;  // probabilistic_map.cpp:34 / :47 — skipped AND no ray is cast
+        stale = (word & 0xFu) == scan_c(p, src);  // probabilistic_map.cpp:34 / :47 — skipped AND no ray is cast
       } else {
         stale = !DENSE;  // sparse: pool exhausted, the scan will be repeated; dense: no leaf = unknown cell = not stale
       }
     }
     if (!stale) {
       is_end = true;
-      const RayGeom rg = ray_geom(p, e.x, e.y, e.z);
+      const RayGeom rg = ray_geom(p, e.x, e.y, e.z, src);
       m = rg.m;  // probabilistic_map.hpp:180; the ray has exactly m cells (end excluded)
       chunks = rg.chunks;
     }
@@ -524,7 +534,7 @@ __global__ void __launch_bounds__(TPB) k_resolve(GridDev g, ScanParams p, ScanBu
     const u32 grp = __match_any_sync(eballot, leaf);
     if ((int)lane == __ffs(grp) - 1 && atomicExch(leaf_stamp(g, leaf), p.seq) != p.seq) {
       const u32 at = atomicAdd(&b.sc->n_touched, 1u);
-      if (at < p.touched_cap) b.touched[at] = leaf;
+      if (at < p.touched_cap) b.touched[at] = p.fleet ? leaf | (src << 28) : leaf;
     }
   }
   if (mine) {
@@ -535,6 +545,7 @@ __global__ void __launch_bounds__(TPB) k_resolve(GridDev g, ScanParams p, ScanBu
       atomicOr(&b.sc->overflow, OVF_CHUNKS);
     } else {
       b.rays[ray] = make_int4(e.x, e.y, e.z, (int)(u32)cb);
+      if (MODE == 2 && p.fleet) b.ray_src[ray] = (unsigned char)src;
       // every 32-chunk tile whose first chunk lies inside this ray learns its owner (the dense mark kernel needs no tiles)
       const u32 t0 = ((u32)cb + 31u) >> 5, t1 = DENSE ? 0u : ((u32)cb + chunks - 1u) >> 5;
       for (u32 t = t0; t <= t1 && !DENSE; ++t) {
@@ -585,7 +596,7 @@ __device__ __forceinline__ u32 walk_chunk(const ScanParams& p, const RayGeom& r,
     pz = (u32)((2ull * k0 * r.az + r.m) / (2ull * r.m));
   }
   E ex = (E)((i64)k0 * r.ax - (i64)px * r.m), ey = (E)((i64)k0 * r.ay - (i64)py * r.m), ez = (E)((i64)k0 * r.az - (i64)pz * r.m);
-  int x = p.Ox + r.sx * (int)px, y = p.Oy + r.sy * (int)py, z = p.Oz + r.sz * (int)pz;
+  int x = r.Ox + r.sx * (int)px, y = r.Oy + r.sy * (int)py, z = r.Oz + r.sz * (int)pz;
   lx0 = x >> 3;
   ly0 = y >> 3;
   lz0 = z >> 3;
@@ -651,15 +662,16 @@ __device__ __forceinline__ u32 mark_leaf(const GridDev& G, u32& inner, bool new_
 // redundant atomic): the leaves around the sensor are hit by every ray. A word seen non-zero can never be the leaf's
 // first touch, so only writers of an (apparently) empty word need the old value back; the thread that really turns
 // a word non-zero stamps the leaf and, if nobody stamped it in this scan yet, appends it to the touched list.
+// tag: sensor << 28 in a fleet step (every leaf is touched by the rays of ONE sensor then), else 0
 __device__ __forceinline__ void mark_bits(const GridDev& G, u32 leaf, unsigned long long* word, unsigned long long bits, u32 seq, u32* n_list, u32* list,
-                                          u32 cap) {
+                                          u32 cap, u32 tag) {
   const unsigned long long cur = *word;
   if ((cur & bits) == bits) return;
   if (cur != 0ull) {
     atomicOr(word, bits);  // result unused: a fire-and-forget reduction
   } else if (atomicOr(word, bits) == 0ull && atomicExch(leaf_stamp(G, leaf), seq) != seq) {
     const u32 at = atomicAdd(n_list, 1u);
-    if (at < cap) list[at] = leaf;
+    if (at < cap) list[at] = leaf | tag;
   }
 }
 
@@ -713,12 +725,13 @@ __global__ void __launch_bounds__(TPB, MARK_MIN_BLOCKS) k_mark(GridDev g, GridDe
     }
     const u32 starts = __reduce_or_sync(0xffffffffu, bit);
     const u32 chunk = c0 + lane;
-    u32 nseg = 0;
+    u32 nseg = 0, tag = 0;
     int lx0 = 0, ly0 = 0, lz0 = 0, sx = 1, sy = 1, sz = 1;
     if (chunk < total) {
       const u32 r = r_first + __popc(starts & ((2u << lane) - 1u));
       const int4 ray = b.rays[r];
-      const RayGeom rg = ray_geom(p, ray.x, ray.y, ray.z);
+      if (SHARD && p.fleet) tag = (u32)b.ray_src[r] << 28;
+      const RayGeom rg = ray_geom(p, ray.x, ray.y, ray.z, tag >> 28);
       u32 k0, k1;
       chunk_range(rg, chunk - (u32)ray.w, k0, k1);
       sx = rg.sx;
@@ -754,10 +767,10 @@ __global__ void __launch_bounds__(TPB, MARK_MIN_BLOCKS) k_mark(GridDev g, GridDe
         }
         if (leaf != NONE) {
           if (!SHARD || own) {
-            mark_bits(g, leaf, reinterpret_cast<unsigned long long*>(leaf_touched(g, leaf)) + w, bits, p.seq, &b.sc->n_touched, b.touched, p.touched_cap);
+            mark_bits(g, leaf, reinterpret_cast<unsigned long long*>(leaf_touched(g, leaf)) + w, bits, p.seq, &b.sc->n_touched, b.touched, p.touched_cap, tag);
           } else {
             mark_bits(gs, leaf, reinterpret_cast<unsigned long long*>(leaf_touched(gs, leaf)) + w, bits, p.seq, &b.sc->n_touched2, b.touched2,
-                      p.touched2_cap);
+                      p.touched2_cap, tag);
           }
         }
       }
@@ -1089,7 +1102,7 @@ __global__ void __launch_bounds__(TPB) k_clear_touched(GridDev g, ScanBuffers b,
   const u32 lane = threadIdx.x & 31;
   const u32 warps = gridDim.x * (TPB / 32);
   for (u32 t = blockIdx.x * (TPB / 32) + (threadIdx.x >> 5); t < n; t += warps) {
-    if (lane < 16) reinterpret_cast<unsigned long long*>(leaf_touched(g, b.touched[t]))[lane] = 0ull;  // touched[8] + hit[8] are contiguous
+    if (lane < 16) reinterpret_cast<unsigned long long*>(leaf_touched(g, b.touched[t] & LEAF_MASK))[lane] = 0ull;  // touched[8] + hit[8] are contiguous
   }
 }
 
@@ -1151,7 +1164,9 @@ __global__ void __launch_bounds__(TPB, APPLY_MIN_BLOCKS) k_apply_leaves(GridDev 
   u32 t = blockIdx.x * (TPB / 32) + (threadIdx.x >> 5);
   u32 leaf_n = t < n ? b.touched[t] : NONE;
   for (; t < n; t += warps) {
-    const u32 leaf = leaf_n;
+    // fleet step: the entry also names the sensor whose rays touched the leaf, i.e. which update id stamps its cells
+    const u32 leaf = p.fleet ? leaf_n & LEAF_MASK : leaf_n;
+    const u32 c = p.fleet ? scan_c(p, leaf_n >> 28) : p.c;
     leaf_n = t + warps < n ? b.touched[t + warps] : NONE;
     unsigned char* lp = leaf_ptr(g, leaf);
     // lane j < 16 holds 32-bit half j of the three masks = the bits of cell row j (cells 32 j .. 32 j + 31)
@@ -1183,11 +1198,11 @@ __global__ void __launch_bounds__(TPB, APPLY_MIN_BLOCKS) k_apply_leaves(GridDev 
         const u32 r = half * 8 + it;
         if ((hit >> r) & 1u) {
           const i32 prob = min(((i32)word[it] >> 4) + p.hit, p.cmax);
-          cells[r * 32 + lane] = ((u32)prob << 4) | p.c;
+          cells[r * 32 + lane] = ((u32)prob << 4) | c;
           ++changed;
-        } else if (((mine >> r) & 1u) && (word[it] & 0xFu) != p.c) {
+        } else if (((mine >> r) & 1u) && (word[it] & 0xFu) != c) {
           const i32 prob = max(((i32)word[it] >> 4) + p.miss, p.cmin);
-          cells[r * 32 + lane] = ((u32)prob << 4) | p.c;
+          cells[r * 32 + lane] = ((u32)prob << 4) | c;
           ++changed;
         }
       }
@@ -1359,8 +1374,9 @@ __global__ void __launch_bounds__(TPB) k_shard_emit(GridDev gs, ScanParams p, Sc
     unsigned long long m = 0;
     int4* block = nullptr;
     if (valid) {
-      const u32 leaf = b.touched2[t];
+      const u32 entry = b.touched2[t], leaf = p.fleet ? entry & LEAF_MASK : entry;
       hdr = *reinterpret_cast<const int4*>(leaf_ptr(gs, leaf));
+      hdr.w = p.fleet ? (int)(entry >> 28) : 0;  // fleet step: the sensor whose rays touched the leaf travels with the record
       unsigned long long* touched = reinterpret_cast<unsigned long long*>(leaf_touched(gs, leaf));
       const u32 o = shard_owner(hdr.x >> 5, hdr.y >> 5, hdr.z >> 5, p.world);
       block = b.px->leaf[o];
@@ -1371,7 +1387,7 @@ __global__ void __launch_bounds__(TPB) k_shard_emit(GridDev gs, ScanParams p, Sc
     at = __shfl_sync(0xffffffffu, at, first);
     if (valid) {
       if (at < cap) {
-        if (sub == 0) block[(size_t)at * 5] = make_int4(hdr.x, hdr.y, hdr.z, 0);
+        if (sub == 0) block[(size_t)at * 5] = make_int4(hdr.x, hdr.y, hdr.z, hdr.w);
         reinterpret_cast<unsigned long long*>(block + (size_t)at * 5 + 1)[sub] = m;
       } else if (sub == 0) {
         atomicOr(&b.sc->overflow, OVF_LEAVES);
@@ -1431,15 +1447,18 @@ __global__ void __launch_bounds__(TPB) k_shard_merge(GridDev g, GridDev gs, Scan
       if (rec == nullptr && t >= base && t < end) rec = recv + ((size_t)src * cap + 1u + (t - base)) * 5;
       base = end;
     }
-    u32 leaf = NONE;
+    u32 leaf = NONE, tag = 0;
     if (rec != nullptr && sub == 0) {
       const int4 hdr = __ldcg(rec);
       leaf = leaf_find_or_create(g, hdr.x, hdr.y, hdr.z);
+      tag = p.fleet ? (u32)hdr.w << 28 : 0u;
     }
     leaf = __shfl_sync(0xffffffffu, leaf, first);
+    tag = __shfl_sync(0xffffffffu, tag, first);
     if (leaf != NONE) {
       const unsigned long long bits = __ldcg(reinterpret_cast<const unsigned long long*>(rec + 1) + sub);
-      if (bits) mark_bits(g, leaf, reinterpret_cast<unsigned long long*>(leaf_touched(g, leaf)) + sub, bits, p.seq, &b.sc->n_touched, b.touched, p.touched_cap);
+      if (bits)
+        mark_bits(g, leaf, reinterpret_cast<unsigned long long*>(leaf_touched(g, leaf)) + sub, bits, p.seq, &b.sc->n_touched, b.touched, p.touched_cap, tag);
     }
   }
   __shared__ bool s_last;
@@ -1501,6 +1520,11 @@ __global__ void __launch_bounds__(TPB) k_query(GridDev g, const i32* __restrict_
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+static bool shard_debug() {
+  static const bool v = std::getenv("BNX_DEBUG") != nullptr;
+  return v;
+}
+
 Map::~Map() {
   if (grid.stream()) cudaStreamSynchronize(grid.stream());
   if (copy_stream_) {
@@ -1673,6 +1697,13 @@ static u32 dense_max_blocks_per_axis() {
     return d;
   }();
   return v;
+}
+
+int Map::set_fleet(const double* origins_world_x3) {
+  BNX_REQUIRE(world_ > 1, "set_fleet: the map is not sharded");
+  fleet_origins_.clear();
+  if (origins_world_x3) fleet_origins_.assign(origins_world_x3, origins_world_x3 + (size_t)world_ * 3);
+  return BNX_OK;
 }
 
 int Map::set_marking(int mode) {
@@ -2348,6 +2379,26 @@ int Map::shard_begin(const void* points, i64 stride_bytes, i64 n, bool f64, u32 
     BNX_REQUIRE(n + 2 <= cap_records, "shard_begin: the mailbox holds fewer endpoint records than this slice has points");
   }
   BNX_REQUIRE(origin && cap_records >= 2, "shard_begin: null argument");
+  // fleet step (Map::set_fleet): consumed here; nested drains below replay other scans with their own origins
+  std::vector<double> fleet;
+  fleet.swap(fleet_origins_);
+  if (!fleet.empty()) {
+    BNX_REQUIRE(std::isfinite(max_range) && max_range >= 0.0, "fleet step: needs a finite max_range");
+    // no leaf may be touched by the rays of two sensors: reach balls apart by more than two leaf blocks
+    const double need = 2.0 * max_range + 40.0 * grid.resolution;
+    for (int a = 0; a < world_; ++a)
+      for (int c = a + 1; c < world_; ++c) {
+        double d2 = 0.0;
+        for (int k = 0; k < 3; ++k) d2 += (fleet[a * 3 + k] - fleet[c * 3 + k]) * (fleet[a * 3 + k] - fleet[c * 3 + k]);
+        if (!(d2 > need * need)) {
+          set_error("fleet step: the reach of sensors " + std::to_string(a) + " and " + std::to_string(c) +
+                    " overlaps; insert their scans one after the other");
+          return BNX_ERR_UNSUPPORTED;
+        }
+      }
+    origin = &fleet[(size_t)rank_ * 3];
+  }
+  sp_fleet_ = fleet;
   BNX_REQUIRE(f64 ? (stride_bytes >= 24 && stride_bytes % 8 == 0) : (stride_bytes >= 12 && stride_bytes % 4 == 0), "shard_begin: bad stride");
   if (!queue_.empty()) BNX_TRY(drain());  // single-GPU pipeline first; the sharded queue is drained collectively
   set_ = 0;
@@ -2414,6 +2465,14 @@ int Map::shard_begin(const void* points, i64 stride_bytes, i64 n, bool f64, u32 
   const double reach = std::ceil(max_range * grid.inv_resolution) + 4.0, lim = (double)(1 << 20) - 1.0;
   p.packed = std::isfinite(max_range) && max_range >= 0.0 && std::fabs((double)p.Ox) + reach < lim &&
              std::fabs((double)p.Oy) + reach < lim && std::fabs((double)p.Oz) + reach < lim;
+  if (!fleet.empty()) {
+    p.fleet = 1;
+    for (int g = 0; g < world_; ++g)
+      for (int k = 0; k < 3; ++k) {
+        p.fO[g][k] = (i32)std::floor(fleet[(size_t)g * 3 + k] * grid.inv_resolution);
+        if (!(std::fabs((double)p.fO[g][k]) + reach < lim)) p.packed = 0;  // the receiver sees the voxels of every sensor
+      }
+  }
   const u64 tslots = table_slots(cap_records);
   p.hash_mask = (u32)(tslots - 1);
   sp_ = p;
@@ -2467,8 +2526,10 @@ int Map::shard_resolve_mark(const void* recv_records, void* send_leaves, i64 cap
   const int persistent = sm_count() * 8;
   BNX_TRY(b_touched_.reserve((size_t)grid.dev().leaf_cap * 4));
   BNX_TRY(b_touched2_.reserve((size_t)scratch_->dev().leaf_cap * 4));
+  BNX_TRY(b_ray_src_.reserve((size_t)slots + 64));
   buf_.touched = b_touched_.as<u32>();
   buf_.touched2 = b_touched2_.as<u32>();
+  buf_.ray_src = b_ray_src_.as<unsigned char>();
   buf_.recs = static_cast<const int4*>(recv_records);
   buf_.gate = nullptr;
   p.seq = ++seq_;
@@ -2585,7 +2646,8 @@ int Map::shard_finish(const void* flags_reduced, int* retry) {
   counters[5] = shard_retries_;
   counters[6] = (i64)(st.ray_chunk >> 40);
   counters[7] = (i64)(st.ray_chunk & CHUNK_FIELD);
-  if (++update_count == 4) update_count = 1;
+  for (int k = 0; k < (sp_.fleet ? world_ : 1); ++k)  // a fleet step stands for world_ inserts (probabilistic_map.cpp:103-105)
+    if (++update_count == 4) update_count = 1;
   ++shard_stats[7];
   note_leaf_fill(st.gate_fill);
   GridCounters sgc;
@@ -2685,6 +2747,7 @@ int Map::p2p_attach(const void* handles, void* const* local_ptrs) {
 // Collective: all ranks call it at the same point of the protocol with the same capacities.
 int Map::p2p_collective_setup(i64 cap_records, i64 cap_leaves) {
   cudaStream_t s = grid.stream();
+  if (shard_debug()) std::fprintf(stderr, "[bnx rank %d] mailbox setup: %lld records, %lld leaves per sender\n", rank_, (long long)cap_records, (long long)cap_leaves);
   unsigned char mine[64];
   BNX_TRY(p2p_alloc(cap_records, cap_leaves, mine, nullptr));
   ++shard_stats[2];
@@ -2838,8 +2901,10 @@ int Map::shard_insert(const void* points, i64 stride_bytes, i64 n, bool f64, u32
       std::memcpy(q.origin, origin, sizeof(q.origin));
       q.max_range = max_range;
       q.where = where;
+      q.fleet = sp_fleet_;
       squeue_.push_back(q);
-      if (++update_count == 4) update_count = 1;
+      for (int k = 0; k < (sp_.fleet ? world_ : 1); ++k)
+        if (++update_count == 4) update_count = 1;
       return BNX_OK;
     }
     int retry = 0;
@@ -2854,6 +2919,7 @@ int Map::shard_insert(const void* points, i64 stride_bytes, i64 n, bool f64, u32
       cap_leaf_ *= 4;
       if (p2p) {
         // the mailboxes are replaced, the received endpoint records with them: start the scan over (nothing was applied)
+        fleet_origins_ = sp_fleet_;
         return shard_insert(points, stride_bytes, n, f64, index_base, n_max, origin, max_range, where, false);
       }
       BNX_TRY(x_send2_.reserve((size_t)world_ * cap_leaf_ * 80));
@@ -2864,6 +2930,7 @@ int Map::shard_insert(const void* points, i64 stride_bytes, i64 n, bool f64, u32
 
 int Map::shard_drain() {
   cudaStream_t s = grid.stream();
+  if (shard_debug()) std::fprintf(stderr, "[bnx rank %d] shard_drain: %zu queued, next id %u\n", rank_, squeue_.size(), async_next_);
   BNX_CUDA(cudaMemcpyAsync(h_status_, d_sc_, sizeof(ScanCounters), cudaMemcpyDeviceToHost, s));
   GridCounters gc;
   BNX_TRY(grid.read_counters(&gc));  // synchronises the stream
@@ -2892,6 +2959,8 @@ int Map::shard_drain() {
     for (int j = 0; j < 4; ++j) totals[j] += counters[j];
   }
   note_leaf_fill(drain_max_fill_);  // the records carry the max over ranks: every rank takes the same decision here
+  if (shard_debug())
+    std::fprintf(stderr, "[bnx rank %d] shard_drain: synced, error %u, done %zu, fill %u, cap_leaf %lld\n", rank_, gc.error, done, drain_max_fill_, (long long)cap_leaf_);
   drain_max_fill_ = 0;
   GridCounters sgc;
   BNX_TRY(scratch_->read_counters(&sgc));
@@ -2928,6 +2997,7 @@ int Map::shard_drain() {
   for (size_t k = done; k < q.size(); ++k) {
     const ShardQueued& e = q[k];
     update_count = e.c;
+    fleet_origins_ = e.fleet;
     BNX_TRY(shard_insert(e.points, e.stride, e.n, e.f64, e.index_base, e.n_max, e.origin, e.max_range, e.where, false));
   }
   update_count = resume;

@@ -46,6 +46,8 @@ struct ScanParams {
   i32 W0x, W0y, W0z;           // dense window: leaf-block coordinates (voxel >> 3) of its corner
   u32 D;                       // dense window: blocks per axis
   u32 dlist_cap;               // dense window: entries of the touched-block list
+  u32 fleet;                   // sharded: 1 = every rank inserts the scan of its OWN sensor in this step (see Map::set_fleet)
+  i32 fO[MAX_PEERS][3];        // fleet: origin voxel of sensor s (the points held by rank s)
   u32 use_transform;           // fused ROS pre-step: drop non-finite points, then T * p in float before classifying
   float T[12];                 // rows 0..2 of the 4x4 sensor->world matrix
 };
@@ -91,6 +93,7 @@ struct ScanBuffers {
   u32* touched;      // leaves first touched in this scan
   int4* pending;     // queued addHitPoint/addMissPoint endpoints (xyz, type)
   u32* touched2;     // sharded: scratch-grid leaves touched in this scan
+  unsigned char* ray_src;  // sharded fleet step: which sensor a ray belongs to
   unsigned long long* dense;  // dense window: per block {u64 touched[8]; u64 hit[8]} = one 128-B line, all zero between scans
   u32* dbits;        // dense window: one bit per block, set when the block gets its first mark of the scan
   u32* dhint;        // leaf hint table: hash of absolute block coordinates -> leaf index + 1 (verified on use)
@@ -117,6 +120,12 @@ class Map {
     use_next_T_ = true;
   }
   void clear_next_transform() { use_next_T_ = false; }
+  // Fleet step of a sharded map: the NEXT sharded insert takes one scan per rank — rank s holds the whole cloud of sensor
+  // s, origins[s] is that sensor's origin — and gives the result of inserting the scans of sensors 0..world-1 one after
+  // the other (each with its own update id), all of them concurrently. Needs sensors whose reach (max_range) does not
+  // overlap: then no cell is touched by two of them and the order cannot matter; otherwise BNX_ERR_UNSUPPORTED (insert
+  // them one by one). origins = nullptr switches back to one scan split over the ranks.
+  int set_fleet(const double* origins_world_x3);
   // where a scan keeps its per-scan marks: 1 = in the leaves ("sparse": serves every scan), 2 = in the dense window
   // around the origin when the range allows it (experimental: exact, but slower as measured), 0 = default (sparse
   // unless BNX_DENSE=1)
@@ -181,7 +190,10 @@ class Map {
 
   ScanBuffers buf_ = {};
   DevBuf b_pts_, b_rays_, b_tiles_, b_touched_, b_touched2_, b_pending_, b_q_xyz_, b_q_out_;
-  DevBuf b_dense_, b_dbits_, b_dhint_, b_dlist_;  // dense marking window (allocated at the first scan that can use it)
+  DevBuf b_dense_, b_dbits_, b_dhint_, b_dlist_;
+  DevBuf b_ray_src_;
+  std::vector<double> fleet_origins_;  // [world][3] of the next sharded insert (empty: one scan split over the ranks)
+  std::vector<double> sp_fleet_;       // ... of the sharded scan in flight  // dense marking window (allocated at the first scan that can use it)
   int marking_ = 0;
   u32 dense_D_ = 0;                      // blocks per axis the window buffers are sized (and zeroed) for
   int reserve_dense(ScanParams& p);      // decides p.dense and sizes the window
@@ -256,6 +268,7 @@ class Map {
     u32 index_base, async_id, c;
     double origin[3], max_range;
     int where;
+    std::vector<double> fleet;  // origins of a fleet step (empty otherwise)
   };
   std::vector<ShardQueued> squeue_;
   int shard_drain();

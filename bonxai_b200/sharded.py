@@ -80,10 +80,13 @@ class _Shard:
         self.map.set_stream(stream)
 
     # ---- the four stages (bnx_map_shard_*)
-    def begin(self, pts, n, stride_bytes, f64, index_base, origin, max_range):
+    def begin(self, pts, n, stride_bytes, f64, index_base, origin, max_range, fleet=None):
         if n + 2 > self.cap_records and not self.p2p:
             self._alloc_records(max(n + 2, self.cap_records * 2))
         o = np.ascontiguousarray(origin, dtype=np.float64)
+        if fleet is not None:  # fleet step: this rank holds the scan of sensor `rank`, origins of all sensors given
+            fo = np.ascontiguousarray(fleet, dtype=np.float64).reshape(self.world, 3)
+            capi._check(self.lib.bnx_map_shard_set_fleet(self.map.h, C.c_void_p(fo.ctypes.data)))
         if isinstance(pts, capi.DevPtr):
             p, where = C.c_void_p(pts.address), capi.BNX_DEVICE
         else:
@@ -186,6 +189,14 @@ class ShardedMap:
             p, where = C.c_void_p(pts_local.ctypes.data), capi.BNX_HOST
         capi._check(self.lib.bnx_map_shard_insert(self.map.h, p, C.c_int64(stride_bytes), C.c_int64(n_local), int(bool(f64)), C.c_uint32(index_base),
                                                   C.c_int64(n_max), C.c_void_p(o.ctypes.data), C.c_double(max_range), where, int(use_async)))
+
+    def insert_fleet(self, pts_local, n_local, stride_bytes, n_max, origins, max_range, f64=False, use_async=False):
+        """fleet step: this rank holds the WHOLE scan of sensor `rank`; origins = (world, 3) origins of all sensors (the
+        same array on every rank); n_max = the largest scan of the step. Result = the scans of sensors 0..world-1
+        inserted one after the other; needs sensors whose reach does not overlap (else BonxaiError UNSUPPORTED)."""
+        fo = np.ascontiguousarray(origins, dtype=np.float64).reshape(self.world, 3)
+        capi._check(self.lib.bnx_map_shard_set_fleet(self.map.h, C.c_void_p(fo.ctypes.data)))
+        self.insert(pts_local, n_local, stride_bytes, self.rank * n_max, n_max, fo[self.rank], max_range, f64=f64, use_async=use_async)
 
     def sync(self):
         """completes the pipelined scans; collective: every rank must call it at the same point"""
@@ -293,6 +304,53 @@ class LocalShardGroup:
                     if retries[0] & (8 << 8):
                         # larger mailboxes replace the old ones, and with them the received endpoint records:
                         # the scan starts over (a failed attempt has changed nothing)
+                        self._regrow_mailboxes(cap_leaves=self.shards[0].cap_leaves * 4)
+                        restart = True
+                else:
+                    for s in self.shards:
+                        s.grow_after(retries[0])
+
+    def insert_fleet(self, scans, max_range):
+        """fleet step: scans = [(points of sensor s, origin of sensor s)] * world, shard s holds scan s. Equal to
+        inserting the scans one after the other (sensor 0 first) when the sensors' reach does not overlap."""
+        assert len(scans) == self.world
+        pts = [np.ascontiguousarray(p) for p, _ in scans]
+        origins = np.array([np.asarray(o, np.float64) for _, o in scans])
+        f64 = pts[0].dtype == np.float64
+        stride = pts[0].shape[1] * pts[0].dtype.itemsize
+        n_max = max(len(p) for p in pts)
+        need = n_max + 2
+        if self.p2p:
+            if need > self.shards[0].cap_records:
+                self._regrow_mailboxes(cap_records=max(need, self.shards[0].cap_records * 2))
+        else:
+            for s in self.shards:
+                if need > s.cap_records:
+                    s._alloc_records(max(need, s.cap_records * 2))
+        while True:
+            for r, s in enumerate(self.shards):
+                s.begin(pts[r], len(pts[r]), stride, f64, r * n_max, origins[r], max_range, fleet=origins)
+            if not self.p2p:
+                self._exchange("send1", "recv1")
+            restart = False
+            while not restart:
+                self.attempts += 1
+                for s in self.shards:
+                    s.resolve_mark()
+                if not self.p2p:
+                    self._exchange("send2", "recv2")
+                for s in self.shards:
+                    s.merge()
+                if not self.p2p:
+                    flags = self.torch.stack([s.flags for s in self.shards]).max(dim=0).values
+                    for s in self.shards:
+                        s.flags.copy_(flags)
+                retries = [s.finish() for s in self.shards]
+                assert len(set(retries)) == 1
+                if not retries[0]:
+                    return
+                if self.p2p:
+                    if retries[0] & (8 << 8):
                         self._regrow_mailboxes(cap_leaves=self.shards[0].cap_leaves * 4)
                         restart = True
                 else:

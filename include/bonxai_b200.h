@@ -282,6 +282,16 @@ BNX_API int bnx_map_shard_insert(bnx_map_t* m, const void* points, int64_t strid
 BNX_API int bnx_map_shard_p2p_alloc(bnx_map_t* m, int64_t cap_records, int64_t cap_leaves, void* ipc_handle64, void** device_ptr);
 BNX_API int bnx_map_shard_p2p_attach(bnx_map_t* m, const void* ipc_handles, void* const* device_ptrs);
 BNX_API int bnx_map_shard_exchange(const bnx_map_t* m, int* kind);
+/* Fleet step: several sensors feeding ONE sharded map. After bnx_map_shard_set_fleet(m, origins) — origins =
+ * [world][3] doubles, the same on every rank — the NEXT bnx_map_shard_insert / bnx_map_shard_begin of every rank takes
+ * the WHOLE scan of sensor `rank` (index_base = rank * n_max, its origin argument is ignored in favour of origins[rank])
+ * and the step gives exactly the map that world consecutive insertPointCloud calls — sensor 0, 1, ... world-1, each
+ * with its own update id (probabilistic_map.cpp:103-105) — would give, with all scans processed concurrently: endpoint
+ * records go to the owners as usual, rays are cast from their own sensor's origin, and every touched leaf carries the
+ * sensor whose update id stamps it. Exactness needs sensors whose reach does not overlap (pairwise distance > 2 *
+ * max_range + 40 voxels: no cell is then visited by two scans, so their order cannot matter); otherwise the insert
+ * returns BNX_ERR_UNSUPPORTED and the scans have to be inserted one after the other. One call arms one step. */
+BNX_API int bnx_map_shard_set_fleet(bnx_map_t* m, const double* origins);
 /* Bootstrap without NCCL (instead of bnx_nccl_unique_id + bnx_map_shard_comm_init): the caller supplies the collective
  * that hands the 64-byte mailbox handles around — allgather(ctx, send, recv, bytes) must gather `bytes` bytes of HOST
  * memory from every rank into recv[world][bytes] and return 0 (any transport: gloo, MPI, a socket). Peer memory is then

@@ -74,6 +74,40 @@ def test_local_shard_group_infinite_range_and_far_coordinates(bnx, port, exchang
 
 
 @pytest.mark.parametrize("exchange", ["transpose", "p2p"])
+@pytest.mark.parametrize("world", [2, 3, 4])
+def test_fleet_step_equals_consecutive_inserts(bnx, port, world, exchange):
+    """fleet step: every rank holds the scan of its OWN sensor; one sharded step must give exactly what inserting the
+    sensors' scans one after the other gives (each with its own update id), over several steps with moving sensors —
+    including the wrap of the update id and stale endpoints (a sensor that stands still re-hits voxels 3 inserts later)"""
+    from bonxai_b200.sharded import LocalShardGroup
+    g, om = LocalShardGroup(0.1, world, exchange=exchange), port.map(0.1)
+    for step in range(5):
+        scans = []
+        for s in range(world):
+            pts, origin = synth.lidar_scan(step if s != 1 else 0, beams=16, azimuths=512, seed=7 + s)
+            shift = np.float32([0.0, 150.0 * s, 0.0])  # streets 150 m apart: reach 2 x 40 m + margin
+            scans.append((np.ascontiguousarray(pts[:, :3] + shift), origin + shift))
+        g.insert_fleet(scans, 40.0)
+        for pts, origin in scans:
+            om.insert(pts, origin, 40.0)
+        assert_same_dump(g.dump(), om.dump(), f"world {world} fleet step {step}")
+    # a single-sensor scan (split over the ranks) after the fleet steps continues the same map and id sequence
+    pts, origin = synth.lidar_scan(9, beams=16, azimuths=512)
+    g.insert(pts, origin, 40.0)
+    om.insert(pts, origin, 40.0)
+    assert_same_dump(g.dump(), om.dump(), "single scan after fleet steps")
+
+
+def test_fleet_step_refuses_overlapping_sensors(bnx):
+    from bonxai_b200.sharded import LocalShardGroup
+    g = LocalShardGroup(0.1, 2, exchange="p2p")
+    pts, origin = synth.lidar_scan(0, beams=16, azimuths=256)
+    with pytest.raises(bnx.BonxaiError) as err:
+        g.insert_fleet([(pts, origin), (pts, origin + np.float32([50.0, 0, 0]))], 40.0)
+    assert err.value.status == 5
+
+
+@pytest.mark.parametrize("exchange", ["transpose", "p2p"])
 def test_local_shard_group_one_owner_gets_everything(bnx, port, exchange):
     """all endpoints and rays inside ONE root (3.2 m cube): a single rank receives the records of every rank, more
     than the receiving kernels are launched for (they loop), the other ranks receive nothing"""
