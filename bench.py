@@ -605,7 +605,7 @@ def run_gpu_sharded(args):
         for pts, origin in full:
             single.insert(pts, origin, MAX_RANGE)
         dig_single = single.digest()
-        del single
+        single.close()
         lib, kind = load_cpu_oracle()
         om = lib.map(RES)
         for pts, origin in full:
@@ -614,6 +614,9 @@ def run_gpu_sharded(args):
         del om
         parity = {"scans": n_parity, "oracle": kind, "sharded_equals_single_gpu": dig_sharded == dig_single,
                   "sharded_equals_oracle": dig_sharded == dig_cpu, "active_cells": dig_sharded[2]}
+    # maps are closed explicitly, at the same point on every rank (left to the garbage collector, one rank would tear its
+    # shard down while another already waits in the next communicator's rendezvous)
+    sm.close()
     del sm
     full = None
 
@@ -654,7 +657,7 @@ def run_gpu_sharded(args):
         r["ms_max"] = reduce([r["ms"]], dist.ReduceOp.MAX)[0]
         runs.append(r)
         if rep == 0:
-            r.pop("map")
+            r.pop("map").close()
     clocks = sampler.stop()
     best = min(runs, key=lambda r: r["ms_max"])
     ms_max = best["ms_max"]
@@ -674,6 +677,7 @@ def run_gpu_sharded(args):
         for k, name in (("classify", "begin"), ("resolve", "resolve_mark"), ("mark", "merge"), ("apply", "apply"), ("total", "total")):
             acc[name] = acc.get(name, 0.0) + pt[k] / reps
     sm.map.set_profiling(False)
+    sm.close()
     del sm
 
     # ---------------- e2e: the same call with pinned HOST buffers, wall clock ----------------
@@ -681,7 +685,7 @@ def run_gpu_sharded(args):
     e2e_runs = []
     for rep in range(2):
         r = one_run(pinned)
-        r.pop("map")
+        r.pop("map").close()
         r["wall_max"] = reduce([r["wall"]], dist.ReduceOp.MAX)[0]
         e2e_runs.append(r)
     e2e_best = min(e2e_runs, key=lambda r: r["wall_max"])

@@ -340,10 +340,16 @@ class ProbabilisticMap:
         _check(self.lib.bnx_map_grid(self.h, C.byref(gh)))
         self._grid = VoxelGrid(resolution, dtype=np.uint32, _handle=gh, _owner=self)
 
-    def __del__(self):
+    def close(self):
+        """destroys the map now (the object and its grid() wrapper reference each other, so without this the device
+        memory is only released when Python's cycle collector gets to it)"""
         if getattr(self, "h", None):
             self.lib.bnx_map_destroy(self.h)
             self.h = None
+            self._grid.h = None
+
+    def __del__(self):
+        self.close()
 
     def grid(self) -> VoxelGrid:
         return self._grid

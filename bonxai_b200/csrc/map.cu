@@ -138,7 +138,7 @@ __device__ __forceinline__ void wait_arrivals(const u32* flags, u32 stride, u32 
 // LAST block writes the record count of every block header and then the arrival stamp into every owner's flag area
 // (release, system scope; each block fenced its own stores before taking its ticket).
 __device__ __forceinline__ void publish_blocks(const PeerBoxes* px, bool leaves, const u32* cnt, u32* done, u32 flag_off, u32 rank, u32 seq, u32 world,
-                                               u32 cap) {
+                                               u32 cap, size_t rec_off = 0) {
   __shared__ bool s_last;
   const bool remote = px->flag[0] != nullptr;
   __syncthreads();  // the block's stores happen before thread 0's fence (cumulative), which happens before its ticket
@@ -157,7 +157,7 @@ __device__ __forceinline__ void publish_blocks(const PeerBoxes* px, bool leaves,
   if (threadIdx.x < world) {
     const u32 o = threadIdx.x;
     const u32 c = min(*reinterpret_cast<const volatile u32*>(cnt + o), cap - 1u);
-    int4* block = leaves ? px->leaf[o] : px->rec[o];
+    int4* block = leaves ? px->leaf[o] : px->rec[o] + rec_off;
     block[0] = make_int4((int)c, 0, 0, 0);
     if (remote) {
       __threadfence_system();
@@ -1296,12 +1296,12 @@ __global__ void __launch_bounds__(TPB) k_shard_bucket(ScanParams p, ScanBuffers 
     base = __shfl_sync(peers, base, leader);
     const u32 at = base + __popc(peers & ((1u << lane) - 1u)) + 1u;
     if (at < cap) {
-      b.px->rec[o][at] = make_int4(e.x, e.y, e.z, (int)(((index_base + i) << 1) | (u32)e.w));
+      (b.px->rec[o] + (size_t)p.par * p.world * cap)[at] = make_int4(e.x, e.y, e.z, (int)(((index_base + i) << 1) | (u32)e.w));
     } else {
       atomicOr(&b.sc->overflow, OVF_RECORDS);
     }
   }
-  publish_blocks(b.px, false, b.sc->cnt1, &b.sc->done1, MBOX_FLAG1, p.rank, p.xseq1, p.world, cap);
+  publish_blocks(b.px, false, b.sc->cnt1, &b.sc->done1, MBOX_FLAG1 + p.par * MAX_PEERS, p.rank, p.xseq1, p.world, cap, (size_t)p.par * p.world * cap);
 }
 
 // exchange 1, receiver: lowest global index per endpoint voxel over the records of all ranks. Pipelined path: also
@@ -1310,7 +1310,7 @@ __global__ void __launch_bounds__(TPB) k_shard_dedupe(ScanParams p, ScanBuffers 
   pdl_enter();
   // peer-memory exchange: the records of every rank must have arrived (the wait happens even when the pipeline is
   // frozen, so that no rank ever runs ahead of an exchange point)
-  wait_arrivals(b.my_flags ? b.my_flags + MBOX_FLAG1 : nullptr, 1, p.world, p.xseq1, const_cast<u32*>(b.poison));
+  wait_arrivals(b.my_flags ? b.my_flags + MBOX_FLAG1 + p.par * MAX_PEERS : nullptr, 1, p.world, p.xseq1, const_cast<u32*>(b.poison));
   if (*b.poison) return;
   const u32 stride = gridDim.x * blockDim.x;
   u32 i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1540,11 +1540,25 @@ Map::~Map() {
   for (auto& e : x_copied_)
     if (e) cudaEventDestroy(e);
   if (grown_) cudaEventDestroy(grown_);
+  for (auto& e : x_merged_)
+    if (e) cudaEventDestroy(e);
+  for (auto& e : x_begun_)
+    if (e) cudaEventDestroy(e);
   if (h_ring_) cudaFreeHost(h_ring_);
   p2p_close_peers();
   if (mbox_) cudaFree(mbox_);
   for (void* old : mbox_retired_) cudaFree(old);
-  if (comm_) nccl_api(nullptr).CommDestroy(static_cast<ncclComm_t>(comm_));
+  // the communicator only bootstraps (or carries the BNX_SHARD_EXCHANGE=nccl exchanges of scans that are complete by now):
+  // it is ABORTED, not destroyed — ncclCommDestroy may wait for the peer ranks, and maps are not destroyed at the same
+  // moment on every rank (a garbage-collected handle in one process must not dead-lock the next collective of another)
+  if (comm_) {
+    const NcclApi& api = nccl_api(nullptr);
+    if (api.CommAbort) {
+      api.CommAbort(static_cast<ncclComm_t>(comm_));
+    } else {
+      api.CommDestroy(static_cast<ncclComm_t>(comm_));
+    }
+  }
   delete scratch_;
   if (h_status_) cudaFreeHost(h_status_);
   for (auto& e : ev_)
@@ -1591,6 +1605,8 @@ int Map::init(double resolution) {
   for (auto& st : sets_) BNX_CUDA(cudaEventCreateWithFlags(&st.classified, cudaEventDisableTiming));
   for (auto& e : x_copied_) BNX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   BNX_CUDA(cudaEventCreateWithFlags(&grown_, cudaEventDisableTiming));
+  for (auto& e : x_merged_) BNX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto& e : x_begun_) BNX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   buf_.poison = &grid.dev().ctr->error;
   buf_.ring = d_ring_;
   return reserve_scan(0, 16, 1.0);
@@ -2401,13 +2417,29 @@ int Map::shard_begin(const void* points, i64 stride_bytes, i64 n, bool f64, u32 
   sp_fleet_ = fleet;
   BNX_REQUIRE(f64 ? (stride_bytes >= 24 && stride_bytes % 8 == 0) : (stride_bytes >= 12 && stride_bytes % 4 == 0), "shard_begin: bad stride");
   if (!queue_.empty()) BNX_TRY(drain());  // single-GPU pipeline first; the sharded queue is drained collectively
-  set_ = 0;
   cudaStream_t s = grid.stream();
   scratch_->set_stream(s);
   const i64 slots = (i64)world_ * cap_records;
+  const bool lean = shard_async_;  // pipelined: the kernels leave tables and counters zeroed for the next scan
+  // pipelined + peer memory: the front half runs on the pre-stream, one scratch set per exchange in flight (see map.hpp)
+  const bool overlap = lean && staged_p2p_;
+  const u32 xnext = xseq1_ + 1;
+  if (overlap && slots > shard_sets_n_) {
+    // all sets are sized together, up front (same decision on every rank: slots = world * mailbox capacity)
+    const u32 keep_id = shard_async_id_;
+    const i64 keep_n_max = shard_n_max_;
+    BNX_TRY(drain());
+    shard_async_ = true;
+    shard_async_id_ = keep_id;
+    shard_n_max_ = keep_n_max;
+    staged_p2p_ = send_records == nullptr;
+    for (set_ = 0; set_ < SHARD_SETS; ++set_) BNX_TRY(reserve_scan(slots, stride_bytes, max_range, cap_records));
+    shard_sets_n_ = slots;
+  }
+  set_ = overlap ? (int)(xnext % (u32)SHARD_SETS) : 0;
+  cudaStream_t fs = overlap ? pre_stream_ : s;
   // sender-side dedupe table: sized from the exchange capacity (>= n + 2), so it does not change from scan to scan
   BNX_TRY(reserve_scan(std::max<i64>(n, slots), stride_bytes, max_range, cap_records));
-  const bool lean = shard_async_;  // pipelined: the kernels leave tables and counters zeroed for the next scan
   const void* d_points = points;
   int stage_slot = -1;
   if (where == BNX_HOST && n > 0) {
@@ -2432,7 +2464,7 @@ int Map::shard_begin(const void* points, i64 stride_bytes, i64 n, bool f64, u32 
       }
       BNX_CUDA(cudaMemcpyAsync(x_stage_[stage_slot].p, points, cloud_bytes(n, stride_bytes, f64), cudaMemcpyHostToDevice, copy_stream_));
       BNX_CUDA(cudaEventRecord(x_copied_[stage_slot], copy_stream_));
-      BNX_CUDA(cudaStreamWaitEvent(s, x_copied_[stage_slot], 0));
+      BNX_CUDA(cudaStreamWaitEvent(fs, x_copied_[stage_slot], 0));
       d_points = x_stage_[stage_slot].p;
     } else {
       BNX_TRY(b_pts_.reserve((size_t)n * stride_bytes));
@@ -2461,6 +2493,7 @@ int Map::shard_begin(const void* points, i64 stride_bytes, i64 n, bool f64, u32 
   p.async_id = NONE;
   p.rec_cap = (u32)cap_records;
   p.xseq1 = ++xseq1_;
+  p.par = staged_p2p_ ? (p.xseq1 & 1u) : 0u;
   p.max_chunks = (u32)std::min<u64>(((1ull << 40) - 1) / (u64)std::max<i64>(slots, 1), 1ull << 28);
   const double reach = std::ceil(max_range * grid.inv_resolution) + 4.0, lim = (double)(1 << 20) - 1.0;
   p.packed = std::isfinite(max_range) && max_range >= 0.0 && std::fabs((double)p.Ox) + reach < lim &&
@@ -2488,23 +2521,33 @@ int Map::shard_begin(const void* points, i64 stride_bytes, i64 n, bool f64, u32 
   } else {
     buf_.my_flags = reinterpret_cast<const u32*>(mbox_);
   }
-  if (!(lean && S().sc_clean && S().t1_clean)) BNX_CUDA(cudaMemsetAsync(d_sc_, 0, SC_BYTES + tslots * 12, s));
+  if (overlap) {
+    // inbox parity and scratch set of exchange x were last used by exchange x - 2 / x - 4: this rank's merge of x - 2 has
+    // seen every rank's exchange-2 stamp, i.e. every owner is done with the inbox; everything older is done a fortiori
+    const u32 prev = p.xseq1 - 2u;
+    if (p.xseq1 >= 3u && x_merged_seq_[prev % SHARD_SETS] == prev) BNX_CUDA(cudaStreamWaitEvent(fs, x_merged_[prev % SHARD_SETS], 0));
+  }
+  if (!(lean && S().sc_clean && S().t1_clean)) BNX_CUDA(cudaMemsetAsync(d_sc_, 0, SC_BYTES + tslots * 12, fs));
   S().sc_clean = S().t1_clean = lean;  // pipelined: the apply epilogue zeroes the counters, k_shard_dedupe this table
   S().clean_slots = 0;
   const int blocks = blocks_for(n);
   if (n > 0) {
     const unsigned char* pts = static_cast<const unsigned char*>(d_points);
     if (f64) {
-      launch_classify<true, false>(p.packed, blocks, s, pts, (u32)stride_bytes, p, buf_);
+      launch_classify<true, false>(p.packed, blocks, fs, pts, (u32)stride_bytes, p, buf_);
     } else if (stride_bytes == 16 && (reinterpret_cast<uintptr_t>(pts) & 15u) == 0) {
-      launch_classify<false, true>(p.packed, blocks, s, pts, 16u, p, buf_);
+      launch_classify<false, true>(p.packed, blocks, fs, pts, 16u, p, buf_);
     } else {
-      launch_classify<false, false>(p.packed, blocks, s, pts, (u32)stride_bytes, p, buf_);
+      launch_classify<false, false>(p.packed, blocks, fs, pts, (u32)stride_bytes, p, buf_);
     }
   }
   // always launched: its last block writes the block headers (counts) and, with mailboxes, the arrival stamps
-  launch_scan_kernel(k_shard_bucket, blocks, TPB, s, p, buf_, index_base);
+  launch_scan_kernel(k_shard_bucket, blocks, TPB, fs, p, buf_, index_base);
   BNX_CUDA(cudaGetLastError());
+  if (overlap) {  // the back half (map's stream) starts once this rank's own front half is complete
+    BNX_CUDA(cudaEventRecord(x_begun_[p.xseq1 % SHARD_SETS], fs));
+    BNX_CUDA(cudaStreamWaitEvent(s, x_begun_[p.xseq1 % SHARD_SETS], 0));
+  }
   if (profiling) cudaEventRecord(ev_[1], s);
   return BNX_OK;
 }
@@ -2513,7 +2556,7 @@ int Map::shard_resolve_mark(const void* recv_records, void* send_leaves, i64 cap
   BNX_REQUIRE(world_ > 1 && scratch_, "shard_resolve_mark: bad argument");
   if (staged_p2p_) {
     BNX_REQUIRE(p2p_ready_, "shard_resolve_mark: no mailboxes attached");
-    recv_records = mbox_ + MBOX_HEADER;
+    recv_records = mbox_ + MBOX_HEADER + (size_t)sp_.par * world_ * mbox_cap_rec_ * 16;
     cap_leaves = mbox_cap_leaf_;
   } else {
     BNX_REQUIRE(recv_records && send_leaves && cap_leaves >= 2, "shard_resolve_mark: bad argument");
@@ -2572,7 +2615,7 @@ int Map::shard_resolve_mark(const void* recv_records, void* send_leaves, i64 cap
 int Map::shard_merge(const void* recv_leaves, void* flags) {
   BNX_REQUIRE(world_ > 1 && scratch_, "shard_merge: bad argument");
   if (staged_p2p_) {
-    recv_leaves = mbox_ + MBOX_HEADER + (size_t)world_ * mbox_cap_rec_ * 16;
+    recv_leaves = mbox_ + MBOX_HEADER + (size_t)world_ * mbox_cap_rec_ * 16 * 2;
   } else {
     BNX_REQUIRE(recv_leaves && flags, "shard_merge: bad argument");
   }
@@ -2580,6 +2623,11 @@ int Map::shard_merge(const void* recv_leaves, void* flags) {
   const GridDev g = grid.dev(), gs = scratch_->dev();
   launch_scan_kernel(k_shard_merge, sm_count() * 8, TPB, s, g, gs, sp_, buf_, static_cast<const int4*>(recv_leaves), sp_.leaf_cap2, static_cast<u32*>(flags));
   BNX_CUDA(cudaGetLastError());
+  x_merged_seq_[sp_.xseq1 % SHARD_SETS] = 0;
+  if (shard_async_ && staged_p2p_) {
+    BNX_CUDA(cudaEventRecord(x_merged_[sp_.xseq1 % SHARD_SETS], s));
+    x_merged_seq_[sp_.xseq1 % SHARD_SETS] = sp_.xseq1;
+  }
   if (profiling) cudaEventRecord(ev_[3], s);
   return BNX_OK;
 }
@@ -2694,7 +2742,7 @@ int Map::p2p_alloc(i64 cap_records, i64 cap_leaves, void* ipc_handle64, void** l
   p2p_close_peers();
   if (mbox_) mbox_retired_.push_back(mbox_);
   mbox_ = nullptr;
-  const size_t bytes = MBOX_HEADER + (size_t)world_ * ((size_t)cap_records * 16 + (size_t)cap_leaves * 80);
+  const size_t bytes = MBOX_HEADER + (size_t)world_ * ((size_t)cap_records * 16 * 2 + (size_t)cap_leaves * 80);  // two endpoint inboxes (parity)
   void* ptr = nullptr;
   BNX_CUDA(cudaMalloc(&ptr, bytes));
   BNX_CUDA(cudaMemset(ptr, 0, MBOX_HEADER));
@@ -2735,7 +2783,7 @@ int Map::p2p_attach(const void* handles, void* const* local_ptrs) {
     unsigned char* base = static_cast<unsigned char*>(peer_base_[o]);
     px_host_.flag[o] = reinterpret_cast<u32*>(base);
     px_host_.rec[o] = reinterpret_cast<int4*>(base + MBOX_HEADER) + (size_t)rank_ * mbox_cap_rec_;
-    px_host_.leaf[o] = reinterpret_cast<int4*>(base + MBOX_HEADER + (size_t)world_ * mbox_cap_rec_ * 16) + (size_t)rank_ * mbox_cap_leaf_ * 5;
+    px_host_.leaf[o] = reinterpret_cast<int4*>(base + MBOX_HEADER + (size_t)world_ * mbox_cap_rec_ * 16 * 2) + (size_t)rank_ * mbox_cap_leaf_ * 5;
   }
   BNX_TRY(upload_boxes());
   BNX_CUDA(cudaStreamSynchronize(grid.stream()));
@@ -2934,8 +2982,12 @@ int Map::shard_drain() {
   BNX_CUDA(cudaMemcpyAsync(h_status_, d_sc_, sizeof(ScanCounters), cudaMemcpyDeviceToHost, s));
   GridCounters gc;
   BNX_TRY(grid.read_counters(&gc));  // synchronises the stream
+  BNX_CUDA(cudaStreamSynchronize(pre_stream_));
   shard_phase_times();
-  if (gc.error) S().sc_clean = S().t1_clean = t2_clean_ = false;  // frozen kernels cleaned nothing
+  if (gc.error) {  // frozen kernels cleaned nothing
+    t2_clean_ = false;
+    for (auto& st : sets_) st.sc_clean = st.t1_clean = false;
+  }
   std::vector<ShardQueued> q;
   q.swap(squeue_);
   size_t done = q.size();

@@ -12,7 +12,7 @@ namespace bnx {
 // consuming kernel spins on its own flags. No collective launch, no staging copy.
 constexpr int MAX_PEERS = 16;
 constexpr size_t MBOX_HEADER = 4096;      // flag area in front of the two inboxes
-constexpr u32 MBOX_FLAG1 = 0;             // u32[MAX_PEERS]  exchange 1: stamp of the scan whose records have arrived
+constexpr u32 MBOX_FLAG1 = 0;             // u32[2][MAX_PEERS]  exchange 1 (one set per inbox parity): stamp of the scan whose records have arrived
 constexpr u32 MBOX_FLAG2 = 64;            // u32[MAX_PEERS]  exchange 2
 constexpr u32 MBOX_FLAGS4 = 128;          // uint4[2][MAX_PEERS] {pool error bits, overflow bits, 0, stamp}, slot = stamp & 1
 struct PeerBoxes {
@@ -37,6 +37,7 @@ struct ScanParams {
   u32 packed;                  // 1: dedupe table uses packed 64-bit keys (all endpoints fit 21 bits per axis)
   u32 rank, world;             // map sharding: this process owns the roots with shard_owner(root) == rank
   u32 rec_cap;                 // sharded: slots per peer block of the endpoint record exchange
+  u32 par;                     // sharded, peer memory: which of the two endpoint inboxes this scan uses (xseq1 & 1)
   u32 leaf_cap2;               // sharded: slots per peer block of the leaf-mask exchange
   u32 touched2_cap;            // sharded: entries of the scratch-grid touched list
   u32 xseq1, xseq2;            // sharded, peer-memory exchange: arrival stamps of this scan's exchange 1 / exchange 2 + flags
@@ -299,6 +300,16 @@ class Map {
   static constexpr size_t SHARD_QUEUE = 64;  // scans between two collective drains
   static constexpr int SHARD_STAGES = (int)SHARD_QUEUE + 2;
   cudaStream_t copy_stream_ = nullptr;
+  // pipelined + peer memory: the front half of scan k+1 (copy, classify, bucket + stores into the owners' inboxes) runs
+  // on the pre-stream while scan k is still marking / merging / applying. Safe because the endpoint inboxes are double
+  // buffered by the parity of the exchange serial, and the front half of exchange x+2 waits (event) for this rank's merge
+  // of exchange x: that merge has seen the exchange-2 stamps of EVERY rank, which they send after they have consumed
+  // inbox x.
+  static constexpr int SHARD_SETS = 4;
+  cudaEvent_t x_merged_[SHARD_SETS] = {};   // merge kernel of exchange x enqueued (x % SHARD_SETS)
+  u32 x_merged_seq_[SHARD_SETS] = {};       // which exchange serial the event belongs to (0: never recorded)
+  cudaEvent_t x_begun_[SHARD_SETS] = {};    // front half of exchange x done
+  i64 shard_sets_n_ = 0;                    // points the SHARD_SETS scratch sets are sized for
   DevBuf x_stage_[SHARD_STAGES];
   cudaEvent_t x_copied_[SHARD_STAGES] = {};
   size_t x_stage_bytes_ = 0;

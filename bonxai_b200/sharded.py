@@ -198,6 +198,10 @@ class ShardedMap:
         capi._check(self.lib.bnx_map_shard_set_fleet(self.map.h, C.c_void_p(fo.ctypes.data)))
         self.insert(pts_local, n_local, stride_bytes, self.rank * n_max, n_max, fo[self.rank], max_range, f64=f64, use_async=use_async)
 
+    def close(self):
+        """releases the shard now, at a point of the program every rank reaches (not whenever the garbage collector runs)"""
+        self.map.close()
+
     def sync(self):
         """completes the pipelined scans; collective: every rank must call it at the same point"""
         self.map.sync()

@@ -69,9 +69,11 @@ def main():
     st = sm.stats()
     if os.environ.get("BNX_EXPECT_REPLAY") == "1":
         assert st["replays"] + st["sync_retries"] > 0, st
+    kind = sm.exchange_kind()
     dist.barrier()
+    sm.close()
     if rank == 0:
-        print("SHARDED_OK", world, sm.exchange_kind(), st)
+        print("SHARDED_OK", world, kind, st)
     dist.destroy_process_group()
 
 
