@@ -674,7 +674,8 @@ def run_gpu_sharded(args):
         put(sm, dev_inputs[i], i)
         sm.sync()
         pt = sm.map.phase_times()
-        for k, name in (("classify", "begin"), ("resolve", "resolve_mark"), ("mark", "merge"), ("apply", "apply"), ("total", "total")):
+        for k, name in (("classify", "begin"), ("resolve", "resolve_mark"), ("mark", "merge"), ("apply", "apply"), ("total", "total"),
+                        ("sub6", "resolve_mark.wait_dedupe_resolve"), ("sub7", "resolve_mark.mark")):
             acc[name] = acc.get(name, 0.0) + pt[k] / reps
     sm.map.set_profiling(False)
     sm.close()
@@ -700,7 +701,8 @@ def run_gpu_sharded(args):
         alg_bytes = 16.0 * n_scan + 8.0 * (U_all / K)  # whole scan, all ranks
         achieved = alg_bytes * K / secs / 1e9
         peak = float(peaks["hbm_gbs"]) * world
-        stage = max(("begin", "resolve_mark", "merge", "apply"), key=lambda k: acc[k])
+        acc["resolve_mark.emit"] = acc["resolve_mark"] - acc["resolve_mark.wait_dedupe_resolve"] - acc["resolve_mark.mark"]
+        stage = max(("begin", "resolve_mark.wait_dedupe_resolve", "resolve_mark.mark", "resolve_mark.emit", "merge", "apply"), key=lambda k: acc[k])
         digests_agree = len({tuple(r["digest"]) for r in runs + e2e_runs}) == 1
         parity["runs_agree"] = digests_agree
         parity_ok = bool(parity["sharded_equals_single_gpu"] and parity["sharded_equals_oracle"] and digests_agree)

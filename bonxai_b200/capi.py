@@ -496,4 +496,4 @@ class ProbabilisticMap:
     def phase_times(self):
         a = (C.c_double * 8)()
         _check(self.lib.bnx_map_phase_times(self.h, a))
-        return dict(h2d=a[0], classify=a[1], resolve=a[2], mark=a[3], apply=a[4], total=a[5])
+        return dict(h2d=a[0], classify=a[1], resolve=a[2], mark=a[3], apply=a[4], total=a[5], sub6=a[6], sub7=a[7])

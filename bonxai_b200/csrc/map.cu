@@ -334,8 +334,8 @@ __device__ __forceinline__ unsigned long long warp_incl_scan(unsigned long long 
 }
 
 // OR `bits` into word w of a per-scan leaf mask (touched or hit); defined with the mark kernel below
-__device__ __forceinline__ void mark_bits(const GridDev& G, u32 leaf, unsigned long long* word, unsigned long long bits, u32 seq, u32* n_list, u32* list,
-                                          u32 cap, u32 tag = 0);
+__device__ __forceinline__ bool mark_bits(const GridDev& G, u32 leaf, unsigned long long* word, unsigned long long bits, u32 seq);
+__device__ __forceinline__ void list_leaves(bool mine, u32 entry, u32* n_list, u32* list, u32 cap);
 
 // which root does which rank own (map sharding)? Uses the upper hash bits: the root table slot uses the lower.
 __host__ __device__ __forceinline__ u32 shard_owner(int rx, int ry, int rz, u32 world) {
@@ -523,6 +523,7 @@ __global__ void __launch_bounds__(TPB) k_resolve(GridDev g, ScanParams p, ScanBu
       if ((int)lane == __ffs(grp) - 1) atomicOr(b.dbits + (blk >> 5), 1u << (blk & 31u));
     }
   }
+  bool list_me = false;
   if (!DENSE && is_end && !PENDING) {
     // addHitPoint / addMissPoint (probabilistic_map.cpp:30-54) deferred to the apply pass: a hit endpoint sets its bit in
     // the leaf's HIT mask; a miss endpoint gets exactly the update of a ray cell (max(p + miss, clamp_min), stamp), so
@@ -532,11 +533,9 @@ __global__ void __launch_bounds__(TPB) k_resolve(GridDev g, ScanParams p, ScanBu
     // is touched here for the first time in this scan, so ONE lane per distinct leaf of the warp installs the stamp and
     // lists the leaf (the words themselves need no test and no return value).
     const u32 grp = __match_any_sync(eballot, leaf);
-    if ((int)lane == __ffs(grp) - 1 && atomicExch(leaf_stamp(g, leaf), p.seq) != p.seq) {
-      const u32 at = atomicAdd(&b.sc->n_touched, 1u);
-      if (at < p.touched_cap) b.touched[at] = p.fleet ? leaf | (src << 28) : leaf;
-    }
+    list_me = (int)lane == __ffs(grp) - 1 && atomicExch(leaf_stamp(g, leaf), p.seq) != p.seq;
   }
+  if (!DENSE && !PENDING) list_leaves(list_me, p.fleet ? leaf | (src << 28) : leaf, &b.sc->n_touched, b.touched, p.touched_cap);
   if (mine) {
     const unsigned long long at = s_base + s_warp[warp] + (incl - mine);
     const u32 ray = (u32)(at >> 40);
@@ -662,17 +661,28 @@ __device__ __forceinline__ u32 mark_leaf(const GridDev& G, u32& inner, bool new_
 // redundant atomic): the leaves around the sensor are hit by every ray. A word seen non-zero can never be the leaf's
 // first touch, so only writers of an (apparently) empty word need the old value back; the thread that really turns
 // a word non-zero stamps the leaf and, if nobody stamped it in this scan yet, appends it to the touched list.
-// tag: sensor << 28 in a fleet step (every leaf is touched by the rays of ONE sensor then), else 0
-__device__ __forceinline__ void mark_bits(const GridDev& G, u32 leaf, unsigned long long* word, unsigned long long bits, u32 seq, u32* n_list, u32* list,
-                                          u32 cap, u32 tag) {
+// Returns true for the ONE thread of the scan that must append the leaf to the touched list (list_leaves).
+__device__ __forceinline__ bool mark_bits(const GridDev& G, u32 leaf, unsigned long long* word, unsigned long long bits, u32 seq) {
   const unsigned long long cur = *word;
-  if ((cur & bits) == bits) return;
+  if ((cur & bits) == bits) return false;
   if (cur != 0ull) {
     atomicOr(word, bits);  // result unused: a fire-and-forget reduction
-  } else if (atomicOr(word, bits) == 0ull && atomicExch(leaf_stamp(G, leaf), seq) != seq) {
-    const u32 at = atomicAdd(n_list, 1u);
-    if (at < cap) list[at] = leaf | tag;
+    return false;
   }
+  return atomicOr(word, bits) == 0ull && atomicExch(leaf_stamp(G, leaf), seq) != seq;
+}
+// Appends `entry` for every lane with mine == true; called by CONVERGED warps. The slots of the warp come from ONE atomic
+// on the list counter: tens of thousands of returning atomics per scan on that single address serialise in L2.
+// entry = leaf, or leaf | sensor << 28 in a fleet step (every leaf is touched by the rays of ONE sensor then).
+__device__ __forceinline__ void list_leaves(bool mine, u32 entry, u32* n_list, u32* list, u32 cap) {
+  const u32 m = __ballot_sync(0xffffffffu, mine);
+  if (m == 0u) return;
+  const u32 lane = threadIdx.x & 31;
+  const int leader = __ffs(m) - 1;
+  u32 at = 0;
+  if ((int)lane == leader) at = atomicAdd(n_list, (u32)__popc(m));
+  at = __shfl_sync(0xffffffffu, at, leader) + __popc(m & ((1u << lane) - 1u));
+  if (mine && at < cap) list[at] = entry;
 }
 
 // SHARD: cells whose root this rank does not own are marked in the scratch grid gs (same code, other pools);
@@ -747,6 +757,7 @@ __global__ void __launch_bounds__(TPB, MARK_MIN_BLOCKS) k_mark(GridDev g, GridDe
     int rrx = 0, rry = 0, rrz = 0;
     bool have_root = false, own = true;
     for (u32 sgi = 0; sgi < nmax; ++sgi) {
+      bool list_own = false, list_scratch = false;
       if (sgi < nseg) {
         const u32 key = s_key[sgi][threadIdx.x];
         const unsigned long long bits = s_bits[sgi][threadIdx.x];
@@ -767,13 +778,14 @@ __global__ void __launch_bounds__(TPB, MARK_MIN_BLOCKS) k_mark(GridDev g, GridDe
         }
         if (leaf != NONE) {
           if (!SHARD || own) {
-            mark_bits(g, leaf, reinterpret_cast<unsigned long long*>(leaf_touched(g, leaf)) + w, bits, p.seq, &b.sc->n_touched, b.touched, p.touched_cap, tag);
+            list_own = mark_bits(g, leaf, reinterpret_cast<unsigned long long*>(leaf_touched(g, leaf)) + w, bits, p.seq);
           } else {
-            mark_bits(gs, leaf, reinterpret_cast<unsigned long long*>(leaf_touched(gs, leaf)) + w, bits, p.seq, &b.sc->n_touched2, b.touched2,
-                      p.touched2_cap, tag);
+            list_scratch = mark_bits(gs, leaf, reinterpret_cast<unsigned long long*>(leaf_touched(gs, leaf)) + w, bits, p.seq);
           }
         }
       }
+      list_leaves(list_own, leaf | tag, &b.sc->n_touched, b.touched, p.touched_cap);
+      if (SHARD) list_leaves(list_scratch, leaf | tag, &b.sc->n_touched2, b.touched2, p.touched2_cap);
     }
   }
 }
@@ -1287,14 +1299,26 @@ __global__ void __launch_bounds__(TPB) k_shard_bucket(ScanParams p, ScanBuffers 
       o = shard_owner(e.x >> 5, e.y >> 5, e.z >> 5, p.world);
     }
   }
+  // slots: warp-aggregated into shared-memory counters, then ONE global atomic per owner and block (the per-owner counters
+  // are a handful of addresses: tens of thousands of returning atomics on them serialise in L2)
+  __shared__ u32 s_cnt[MAX_PEERS], s_base[MAX_PEERS];
+  if (threadIdx.x < MAX_PEERS) s_cnt[threadIdx.x] = 0u;
+  __syncthreads();
   const u32 act = __ballot_sync(0xffffffffu, win);
+  u32 local = 0;
   if (win) {
     const u32 peers = __match_any_sync(act, o);
     const int leader = __ffs(peers) - 1;
     u32 base = 0;
-    if ((int)lane == leader) base = atomicAdd(&b.sc->cnt1[o], (u32)__popc(peers));
+    if ((int)lane == leader) base = atomicAdd(&s_cnt[o], (u32)__popc(peers));
     base = __shfl_sync(peers, base, leader);
-    const u32 at = base + __popc(peers & ((1u << lane) - 1u)) + 1u;
+    local = base + __popc(peers & ((1u << lane) - 1u));
+  }
+  __syncthreads();
+  if (threadIdx.x < p.world && s_cnt[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(&b.sc->cnt1[threadIdx.x], s_cnt[threadIdx.x]);
+  __syncthreads();
+  if (win) {
+    const u32 at = s_base[o] + local + 1u;
     if (at < cap) {
       (b.px->rec[o] + (size_t)p.par * p.world * cap)[at] = make_int4(e.x, e.y, e.z, (int)(((index_base + i) << 1) | (u32)e.w));
     } else {
@@ -1365,27 +1389,34 @@ __global__ void __launch_bounds__(TPB) k_shard_emit(GridDev gs, ScanParams p, Sc
   const u32 n = min(b.sc->n_touched2, p.touched2_cap);
   const u32 cap = p.leaf_cap2;
   const u32 lane = threadIdx.x & 31, sub = lane & 7u, first = lane & 24u;
-  const u32 groups = gridDim.x * (TPB / 8);
-  for (u32 t0 = (blockIdx.x * (TPB / 32) + (threadIdx.x >> 5)) * 4u; t0 < n; t0 += groups) {  // warp-uniform trip count
-    const u32 t = t0 + (lane >> 3);
+  constexpr u32 PER_BLOCK = TPB / 8;  // leaves per block and round
+  __shared__ u32 s_cnt[MAX_PEERS], s_base[MAX_PEERS];
+  for (u32 tb = blockIdx.x * PER_BLOCK; tb < n; tb += gridDim.x * PER_BLOCK) {  // block-uniform trip count
+    if (threadIdx.x < MAX_PEERS) s_cnt[threadIdx.x] = 0u;
+    __syncthreads();
+    const u32 t = tb + (threadIdx.x >> 3);
     const bool valid = t < n;
-    u32 at = 0;
+    u32 local = 0, o = 0;
     int4 hdr = make_int4(0, 0, 0, 0);
     unsigned long long m = 0;
-    int4* block = nullptr;
     if (valid) {
       const u32 entry = b.touched2[t], leaf = p.fleet ? entry & LEAF_MASK : entry;
       hdr = *reinterpret_cast<const int4*>(leaf_ptr(gs, leaf));
       hdr.w = p.fleet ? (int)(entry >> 28) : 0;  // fleet step: the sensor whose rays touched the leaf travels with the record
       unsigned long long* touched = reinterpret_cast<unsigned long long*>(leaf_touched(gs, leaf));
-      const u32 o = shard_owner(hdr.x >> 5, hdr.y >> 5, hdr.z >> 5, p.world);
-      block = b.px->leaf[o];
-      if (sub == 0) at = atomicAdd(&b.sc->cnt2[o], 1u) + 1u;
+      o = shard_owner(hdr.x >> 5, hdr.y >> 5, hdr.z >> 5, p.world);
+      if (sub == 0) local = atomicAdd(&s_cnt[o], 1u);  // slot inside this block's share: shared-memory atomic
       m = touched[sub];
       touched[sub] = 0ull;
     }
-    at = __shfl_sync(0xffffffffu, at, first);
+    __syncthreads();
+    // ONE global atomic per owner and block (tens of thousands of returning atomics on `world` addresses serialise in L2)
+    if (threadIdx.x < p.world && s_cnt[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(&b.sc->cnt2[threadIdx.x], s_cnt[threadIdx.x]);
+    __syncthreads();
+    local = __shfl_sync(0xffffffffu, local, first);
     if (valid) {
+      const u32 at = s_base[o] + local + 1u;
+      int4* block = b.px->leaf[o];
       if (at < cap) {
         if (sub == 0) block[(size_t)at * 5] = make_int4(hdr.x, hdr.y, hdr.z, hdr.w);
         reinterpret_cast<unsigned long long*>(block + (size_t)at * 5 + 1)[sub] = m;
@@ -1393,6 +1424,7 @@ __global__ void __launch_bounds__(TPB) k_shard_emit(GridDev gs, ScanParams p, Sc
         atomicOr(&b.sc->overflow, OVF_LEAVES);
       }
     }
+    __syncthreads();
   }
   publish_blocks(b.px, true, b.sc->cnt2, &b.sc->done2, MBOX_FLAG2, p.rank, p.xseq2, p.world, cap);
 }
@@ -1455,11 +1487,12 @@ __global__ void __launch_bounds__(TPB) k_shard_merge(GridDev g, GridDev gs, Scan
     }
     leaf = __shfl_sync(0xffffffffu, leaf, first);
     tag = __shfl_sync(0xffffffffu, tag, first);
+    bool list_it = false;
     if (leaf != NONE) {
       const unsigned long long bits = __ldcg(reinterpret_cast<const unsigned long long*>(rec + 1) + sub);
-      if (bits)
-        mark_bits(g, leaf, reinterpret_cast<unsigned long long*>(leaf_touched(g, leaf)) + sub, bits, p.seq, &b.sc->n_touched, b.touched, p.touched_cap, tag);
+      if (bits) list_it = mark_bits(g, leaf, reinterpret_cast<unsigned long long*>(leaf_touched(g, leaf)) + sub, bits, p.seq);
     }
+    list_leaves(list_it, leaf | tag, &b.sc->n_touched, b.touched, p.touched_cap);
   }
   __shared__ bool s_last;
   __syncthreads();
@@ -1634,7 +1667,7 @@ int Map::reserve_scan(i64 n, i64 stride_bytes, double max_range, i64 table_n) {
     S().sc_clean = S().t1_clean = false;
   }
   BNX_TRY(b_tiles_.reserve(tile_bytes(np, max_range)));
-  if (b_touched_.bytes == 0) BNX_TRY(b_touched_.reserve((size_t)grid.dev().leaf_cap * 4));  // grown by the sparse launch path only
+  if (b_touched_.bytes == 0) BNX_TRY(b_touched_.reserve((size_t)grid.dev().leaf_cap * 8));  // 2 x the pool; grown by the sparse launch path only
   d_sc_ = S().table.as<ScanCounters>();
   buf_.sc = d_sc_;
   buf_.table = reinterpret_cast<u32*>(S().table.as<unsigned char>() + SC_BYTES);
@@ -1900,7 +1933,7 @@ int Map::launch_back(cudaStream_t s, ScanParams& p, bool first_attempt) {
     return BNX_OK;
   }
   if ((size_t)g.leaf_cap * 4 > b_touched_.bytes) {  // pipelined callers have drained before a scan that needs this
-    BNX_TRY(b_touched_.reserve((size_t)g.leaf_cap * 4));
+    BNX_TRY(b_touched_.reserve((size_t)g.leaf_cap * 8));
     buf_.touched = b_touched_.as<u32>();
     p.touched_cap = (u32)std::min<size_t>(b_touched_.bytes / 4, 0xFFFFFFFFull);
   }
@@ -2093,20 +2126,25 @@ int Map::insert_async(const void* points, i64 stride_bytes, i64 n, bool f64, con
       // what the scans already queued may still allocate must fit the pools THEY were launched with; one more pipeline
       // depth of head-room is the trigger for mapping the next step
       const u64 full = (u64)sets_active_ * max_leaf_growth_, full_inner = (u64)sets_active_ * 64;
-      const bool dense_next = scan_is_dense(origin, max_range);
-      if (r.error || roots_ahead * 2 > (u64)g.root_mask + 1 ||
-          (!dense_next && (leaves_ahead + full > g.leaf_cap || inner_ahead + full_inner > g.inner_cap))) {
-        // the root table is rehashed, or the leaf-sized scratch of the sparse marks re-allocated: nothing may be in flight
+      const bool short_of_pool = leaves_ahead + full > g.leaf_cap || inner_ahead + full_inner > g.inner_cap;
+      const u64 want_leaves = (u64)r.n_leaves + 2 * full + grid.leaf_step(r.n_leaves);
+      const u64 want_inner = (u64)r.n_inner + 2 * full_inner + grid.inner_step(r.n_inner);
+      // the touched-leaf list of the sparse marks holds one entry per leaf of the pool: it is allocated for twice the pool,
+      // so the pool can grow behind running scans until it has doubled
+      const bool list_fits = scan_is_dense(origin, max_range) || (want_leaves + want_leaves / 8) * 4 <= b_touched_.bytes;
+      if (r.error || roots_ahead * 2 > (u64)g.root_mask + 1 || (short_of_pool && !list_fits)) {
+        // the root table is rehashed, or the leaf-sized list re-allocated: nothing may be in flight
         BNX_TRY(drain(false));
-        BNX_TRY(grid.ensure_leaf_capacity((u64)r.n_leaves + 2 * full + grid.leaf_step(r.n_leaves)));
-        BNX_TRY(grid.ensure_inner_capacity((u64)r.n_inner + 2 * full_inner + grid.inner_step(r.n_inner)));
+        BNX_TRY(grid.ensure_leaf_capacity(want_leaves));
+        BNX_TRY(grid.ensure_inner_capacity(want_inner));
         if (roots_ahead * 2 > (u64)g.root_mask + 1) BNX_TRY(grid.grow_root_table(((u64)g.root_mask + 1) * 4));
-      } else if (leaves_ahead + full > g.leaf_cap || inner_ahead + full_inner > g.inner_cap) {
-        // dense marks: nothing of a scan's scratch depends on the pool size, and mapping memory behind the pools does not
-        // wait for the kernels in flight (VMM) — grow AHEAD, in the background: the zero fill runs on the copy stream and
-        // only the scans enqueued from now on (which see the larger pool) wait for it
-        BNX_TRY(grid.ensure_leaf_capacity((u64)r.n_leaves + 2 * full + grid.leaf_step(r.n_leaves), copy_stream_));
-        BNX_TRY(grid.ensure_inner_capacity((u64)r.n_inner + 2 * full_inner + grid.inner_step(r.n_inner), copy_stream_));
+        BNX_TRY(b_touched_.reserve((size_t)grid.dev().leaf_cap * 8));
+      } else if (short_of_pool) {
+        // mapping memory behind the pools does not wait for the kernels in flight (VMM) — grow AHEAD, in the background:
+        // the zero fill runs on the copy stream and only the scans enqueued from now on (which see the larger pool) wait
+        // for it
+        BNX_TRY(grid.ensure_leaf_capacity(want_leaves, copy_stream_));
+        BNX_TRY(grid.ensure_inner_capacity(want_inner, copy_stream_));
         BNX_CUDA(cudaEventRecord(grown_, copy_stream_));
         BNX_CUDA(cudaStreamWaitEvent(s, grown_, 0));
         ++grown_ahead_;
@@ -2605,7 +2643,9 @@ int Map::shard_resolve_mark(const void* recv_records, void* send_leaves, i64 cap
   const int rblocks = blocks_for(std::min<i64>(slots, 2 * (i64)p.rec_cap));
   launch_scan_kernel(k_shard_dedupe, rblocks, TPB, s, p, buf_, slots, table1, lean ? (u32)(t1 * 12 / 16) : 0u);
   launch_scan_kernel(k_resolve<2, false>, rblocks, TPB, s, g, p, buf_, slots);
+  if (profiling) cudaEventRecord(ev_[6], s);
   launch_scan_kernel(k_mark<true>, sm_count() * MARK_MIN_BLOCKS, TPB, s, g, gs, p, buf_);
+  if (profiling) cudaEventRecord(ev_[7], s);
   launch_scan_kernel(k_shard_emit, persistent, TPB, s, gs, p, buf_);
   BNX_CUDA(cudaGetLastError());
   if (profiling) cudaEventRecord(ev_[2], s);
@@ -2719,6 +2759,10 @@ void Map::shard_phase_times() {
   }
   cudaEventElapsedTime(&ms, ev_[0], ev_[4]);
   phase_us[5] = ms * 1e3;
+  // inside resolve_mark: [6] = wait(exchange 1) + dedupe + resolve, [7] = mark (the rest of the stage is the emit kernel)
+  if (cudaEventElapsedTime(&ms, ev_[1], ev_[6]) == cudaSuccess) phase_us[6] = ms * 1e3;
+  if (cudaEventElapsedTime(&ms, ev_[6], ev_[7]) == cudaSuccess) phase_us[7] = ms * 1e3;
+  cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2949,6 +2993,7 @@ int Map::shard_insert(const void* points, i64 stride_bytes, i64 n, bool f64, u32
       std::memcpy(q.origin, origin, sizeof(q.origin));
       q.max_range = max_range;
       q.where = where;
+      q.set = set_;
       q.fleet = sp_fleet_;
       squeue_.push_back(q);
       for (int k = 0; k < (sp_.fleet ? world_ : 1); ++k)
@@ -2979,10 +3024,18 @@ int Map::shard_insert(const void* points, i64 stride_bytes, i64 n, bool f64, u32
 int Map::shard_drain() {
   cudaStream_t s = grid.stream();
   if (shard_debug()) std::fprintf(stderr, "[bnx rank %d] shard_drain: %zu queued, next id %u\n", rank_, squeue_.size(), async_next_);
-  BNX_CUDA(cudaMemcpyAsync(h_status_, d_sc_, sizeof(ScanCounters), cudaMemcpyDeviceToHost, s));
   GridCounters gc;
   BNX_TRY(grid.read_counters(&gc));  // synchronises the stream
   BNX_CUDA(cudaStreamSynchronize(pre_stream_));
+  {
+    // the counters of the scan that froze the pipeline are in ITS scratch set (a healthy queue: the newest scan's)
+    const void* sc = d_sc_;
+    if (gc.error)
+      for (const ShardQueued& e : squeue_)
+        if (e.async_id == gc.failed_id) sc = sets_[e.set].table.p;
+    BNX_CUDA(cudaMemcpyAsync(h_status_, sc, sizeof(ScanCounters), cudaMemcpyDeviceToHost, s));
+    BNX_CUDA(cudaStreamSynchronize(s));
+  }
   shard_phase_times();
   if (gc.error) {  // frozen kernels cleaned nothing
     t2_clean_ = false;

@@ -225,7 +225,7 @@ class Map {
   float next_T_[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
   bool use_next_T_ = false;
   u32 seq_ = 0;  // scan serial number (leaf stamps)
-  cudaEvent_t ev_[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // profiling
+  cudaEvent_t ev_[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // profiling ([6], [7]: inside the sharded resolve_mark stage)
 
   // ---- pipelined insert
   static constexpr u32 RING = 1024;
@@ -269,6 +269,7 @@ class Map {
     u32 index_base, async_id, c;
     double origin[3], max_range;
     int where;
+    int set = 0;                // scratch set the scan's front half used
     std::vector<double> fleet;  // origins of a fleet step (empty otherwise)
   };
   std::vector<ShardQueued> squeue_;

@@ -53,8 +53,12 @@ def main():
     pool = mp.get_context("fork").Pool(procs)  # fork before CUDA
     batch = args.check
 
+    n_oracle = min(args.oracle_steps, args.steps)
+
     def gen(first):
-        jobs = [(s, v) for s in range(first, min(first + batch, args.steps)) for v in mine]
+        # the first batch ends where the oracle's steps end, so that checkpoint 0 can be compared with the CPU reference
+        last = n_oracle if first == 0 and n_oracle else min(first + batch, args.steps)
+        jobs = [(s, v) for s in range(first, last) for v in mine]
         return pool.map_async(vehicle_scan, jobs, chunksize=max(1, len(jobs) // (procs * 4)))
 
     pending = gen(0)
@@ -135,8 +139,12 @@ def main():
             for p, o in oracle_scans:
                 om.insert(p, o, MAX_RANGE)
                 single.insert(p, o, MAX_RANGE)
-            oracle_digest = {"steps": len(oracle_scans) // vehicles, "oracle": kind, "digest_oracle": list(map(hex, om.digest()[:2])),
-                             "digest_single_gpu": list(map(hex, single.digest()[:2])), "active_cells": om.digest()[2]}
+            od, sd = om.digest(), single.digest()
+            oracle_digest = {"steps": len(oracle_scans) // vehicles, "oracle": kind, "digest_oracle": list(map(hex, od[:2])),
+                             "digest_single_gpu": list(map(hex, sd[:2])), "active_cells": od[2],
+                             "this_run_equals_oracle": checkpoints[0]["steps"] == len(oracle_scans) // vehicles and
+                                                       checkpoints[0]["digest"] == list(map(hex, od[:2])) and checkpoints[0]["active_cells"] == od[2],
+                             "single_gpu_equals_oracle": sd == od}
             single.close()
             del om
     pool.terminate()
