@@ -601,7 +601,9 @@ Grid::~Grid() {
 int Grid::init(double voxel_size, int ib, int lb, int cbytes) {
   // VoxelGrid ctor, bonxai.hpp:389-402
   BNX_REQUIRE(ib >= 1 && lb >= 1, "The minimum value of the inner_bits and leaf_bits should be 1");
-  BNX_REQUIRE(lb <= 4 && ib <= 5, "leaf_bits <= 4 and inner_bits <= 5 are supported");
+  BNX_REQUIRE(lb <= 4 && ib <= 5,
+              "leaf_bits <= 4 and inner_bits <= 5 are supported (the reference accepts any value >= 1, bonxai.hpp:138, but its own "
+              "heap-backed Mask double-frees on destruction for leaf_bits >= 4, so larger leaves are untested upstream as well)");
   BNX_REQUIRE(cbytes >= 1 && cbytes <= 64, "cell_bytes must be in 1..64");
   BNX_REQUIRE(voxel_size > 0.0, "voxel_size must be positive");
   int ndev = 0;

@@ -1151,9 +1151,42 @@ __device__ __forceinline__ void read_gate(const ScanParams& p, const ScanBuffers
   fill = s_gate[2];
 }
 
+// ---- bulk-copy engine (TMA, 1-D): global -> shared, completion counted on an mbarrier
+__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, u32 count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, u32 bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, u32 bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+               "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, u32 parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
 // One warp per listed leaf: hit endpoints (addHitPoint, probabilistic_map.cpp:30-41) and the union of all rays + miss
 // endpoints (clearPoint / addMissPoint, :43-54,81-89). Hit endpoints are never stale (resolve filtered them) and win
 // over ray cells, like the reference where they are stamped before any ray is cast.
+//
+// TMA = true (default grid layout: 8^3 leaves of 4-byte cells): the chain list entry -> masks -> cell rows of a leaf is
+// taken off the warp's critical path by the bulk-copy engine. Every warp keeps three leaves in flight: the 192 bytes of
+// masks (ON, touched, hit: contiguous in the leaf) of leaf i + 2 and the needed 128-byte cell rows of leaf i + 1 land in
+// shared memory (cp.async.bulk, completion counted on mbarriers) while leaf i is updated. Only rows that hold a touched
+// cell which is already ON are fetched (the same bytes as the register flavour); results go back with plain coalesced
+// stores.
+template <bool TMA>
 __global__ void __launch_bounds__(TPB, APPLY_MIN_BLOCKS) k_apply_leaves(GridDev g, ScanParams p, ScanBuffers b) {
   pdl_enter();
   // last kernel of the scan: the host reads counters + grid counters with one copy
@@ -1170,12 +1203,107 @@ __global__ void __launch_bounds__(TPB, APPLY_MIN_BLOCKS) k_apply_leaves(GridDev 
   const u32 lane = threadIdx.x & 31;
   const u32 warps = gridDim.x * (TPB / 32);
   u32 changed = 0;
-  // Kept at 32 registers so that all sm_count * 8 blocks are resident in ONE wave (64 warps per SM): the kernel is a chain
-  // of dependent loads per leaf (list entry -> masks -> cells), so what hides the latency is the number of leaves in
-  // flight, not work per thread. Only the list entry of the warp's next leaf is prefetched.
+  if (TMA) {
+    // shared memory per warp: masks of 3 leaves (192 B each), cell rows of 2 leaves (16 x 128 B each), 5 mbarriers
+    __shared__ __align__(128) unsigned char s_rows[TPB / 32][2][2048];
+    __shared__ __align__(16) u32 s_masks[TPB / 32][3][48];
+    __shared__ __align__(8) unsigned long long s_bar[TPB / 32][5];
+    const u32 wib = threadIdx.x >> 5;
+    unsigned long long* mbar = s_bar[wib];       // [0..2]: masks of leaf i % 3
+    unsigned long long* rbar = s_bar[wib] + 3;   // [0..1]: rows of leaf i % 2
+    if (lane == 0) {
+      for (int k = 0; k < 5; ++k) mbar_init(&s_bar[wib][k], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    const u32 t0 = blockIdx.x * (TPB / 32) + wib;
+    const u32 mine_n = t0 < n ? (n - t0 + warps - 1u) / warps : 0u;  // leaves of this warp: t0 + i * warps
+    auto entry_of = [&](u32 i) { return i < mine_n ? b.touched[t0 + i * warps] : NONE; };
+    auto issue_masks = [&](u32 i, u32 entry) {  // 192 B: ON @64, touched @128, hit @192 of the leaf
+      if (lane == 0) {
+        const unsigned char* lp = leaf_ptr(g, p.fleet ? entry & LEAF_MASK : entry);
+        mbar_expect_tx(&mbar[i % 3u], 192u);
+        bulk_g2s(s_masks[wib][i % 3u], lp + 64, 192u, &mbar[i % 3u]);
+      }
+    };
+    auto issue_rows = [&](u32 i, u32 entry) {  // lane r < 16: row r if it holds a touched cell that is ON
+      const u32* mk = s_masks[wib][i % 3u];
+      const bool need = lane < 16 && ((mk[16 + lane] | mk[32 + lane]) & mk[lane]) != 0u;
+      const u32 rows = __ballot_sync(0xffffffffu, need);
+      if (lane == 0) mbar_expect_tx(&rbar[i & 1u], 128u * (u32)__popc(rows));
+      __syncwarp();
+      if (need) {
+        const unsigned char* lp = leaf_ptr(g, p.fleet ? entry & LEAF_MASK : entry);
+        bulk_g2s(s_rows[wib][i & 1u] + lane * 128u, lp + 256 + lane * 128u, 128u, &rbar[i & 1u]);
+      }
+    };
+    u32 e0 = entry_of(0), e1 = entry_of(1), e2 = entry_of(2);
+    if (mine_n > 0) issue_masks(0, e0);
+    if (mine_n > 1) issue_masks(1, e1);
+    if (mine_n > 0) {
+      mbar_wait(&mbar[0], 0);
+      issue_rows(0, e0);
+    }
+    for (u32 i = 0; i < mine_n; ++i) {
+      const u32 e3 = entry_of(i + 3);  // list entries run three leaves ahead
+      if (i + 2 < mine_n) issue_masks(i + 2, e2);
+      if (i + 1 < mine_n) {
+        mbar_wait(&mbar[(i + 1) % 3u], ((i + 1) / 3u) & 1u);
+        issue_rows(i + 1, e1);
+      }
+      mbar_wait(&rbar[i & 1u], (i >> 1) & 1u);
+      const u32 leaf = p.fleet ? e0 & LEAF_MASK : e0;
+      const u32 c = p.fleet ? scan_c(p, e0 >> 28) : p.c;
+      unsigned char* lp = leaf_ptr(g, leaf);
+      const u32* mk = s_masks[wib][i % 3u];
+      u32 th = 0, hh = 0, ah = 0;
+      if (lane < 16) {
+        ah = mk[lane];
+        th = mk[16 + lane];
+        hh = mk[32 + lane];
+      }
+      u32 mine = 0, on = 0, hit = 0;
+#pragma unroll
+      for (u32 j = 0; j < 16; ++j) {
+        const u32 t32 = __shfl_sync(0xffffffffu, th, j), a32 = __shfl_sync(0xffffffffu, ah, j), h32 = __shfl_sync(0xffffffffu, hh, j);
+        mine |= ((t32 >> lane) & 1u) << j;
+        on |= ((a32 >> lane) & 1u) << j;
+        hit |= ((h32 >> lane) & 1u) << j;
+      }
+      mine |= hit;
+      const u32* srow = reinterpret_cast<const u32*>(s_rows[wib][i & 1u]);
+      u32* cells = reinterpret_cast<u32*>(lp + g.off_cells);
+#pragma unroll
+      for (u32 r = 0; r < 16; ++r) {
+        if (!((mine >> r) & 1u)) continue;
+        const u32 word = ((on >> r) & 1u) ? srow[r * 32 + lane] : 0u;
+        if ((hit >> r) & 1u) {
+          const i32 prob = min(((i32)word >> 4) + p.hit, p.cmax);
+          cells[r * 32 + lane] = ((u32)prob << 4) | c;
+          ++changed;
+        } else if ((word & 0xFu) != c) {
+          const i32 prob = max(((i32)word >> 4) + p.miss, p.cmin);
+          cells[r * 32 + lane] = ((u32)prob << 4) | c;
+          ++changed;
+        }
+      }
+      if (lane < 16 && (th | hh)) {
+        reinterpret_cast<u32*>(lp + g.off_active)[lane] = ah | th | hh;
+        reinterpret_cast<u32*>(lp + g.off_touched)[lane] = 0u;
+        reinterpret_cast<u32*>(lp + g.off_hit)[lane] = 0u;
+      }
+      __syncwarp();  // every lane is done with the buffers of leaf i before the engine may overwrite them
+      e0 = e1;
+      e1 = e2;
+      e2 = e3;
+    }
+  }
+  // Register flavour (any grid layout). Kept at 32 registers so that all blocks are resident in ONE wave: the kernel is a
+  // chain of dependent loads per leaf (list entry -> masks -> cells), so what hides the latency is the number of leaves
+  // in flight, not work per thread. Only the list entry of the warp's next leaf is prefetched.
   u32 t = blockIdx.x * (TPB / 32) + (threadIdx.x >> 5);
-  u32 leaf_n = t < n ? b.touched[t] : NONE;
-  for (; t < n; t += warps) {
+  u32 leaf_n = t < n && !TMA ? b.touched[t] : NONE;
+  for (; !TMA && t < n; t += warps) {
     // fleet step: the entry also names the sensor whose rays touched the leaf, i.e. which update id stamps its cells
     const u32 leaf = p.fleet ? leaf_n & LEAF_MASK : leaf_n;
     const u32 c = p.fleet ? scan_c(p, leaf_n >> 28) : p.c;
@@ -1553,6 +1681,18 @@ __global__ void __launch_bounds__(TPB) k_query(GridDev g, const i32* __restrict_
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+// BNX_APPLY_TMA=1: the apply pass keeps three leaves per warp in flight through the bulk-copy engine (cp.async.bulk +
+// mbarrier) instead of register-held loads. Bit-exact, measured 1.2 us SLOWER per scan on the B200 (16.9 vs 15.7 us:
+// a 192-byte and a few 128-byte bulk copies per leaf have a higher latency than the LDGs they replace, and three leaves
+// per warp do not cover it; profiles/r2_notes.md), so the register flavour stays the default.
+static bool apply_tma() {
+  static const bool v = [] {
+    const char* e = std::getenv("BNX_APPLY_TMA");
+    return e && std::strcmp(e, "1") == 0;
+  }();
+  return v;
+}
+
 static bool shard_debug() {
   static const bool v = std::getenv("BNX_DEBUG") != nullptr;
   return v;
@@ -1942,7 +2082,7 @@ int Map::launch_back(cudaStream_t s, ScanParams& p, bool first_attempt) {
   if (profiling && first_attempt) cudaEventRecord(ev_[3], s);
   launch_scan_kernel(k_mark<false>, sm_count() * MARK_MIN_BLOCKS, TPB, s, g, g, p, buf_);
   if (profiling && first_attempt) cudaEventRecord(ev_[4], s);
-  launch_scan_kernel(k_apply_leaves, sm_count() * APPLY_MIN_BLOCKS, TPB, s, g, p, buf_);
+  launch_scan_kernel(apply_tma() ? k_apply_leaves<true> : k_apply_leaves<false>, sm_count() * APPLY_MIN_BLOCKS, TPB, s, g, p, buf_);
   BNX_CUDA(cudaGetLastError());
   if (profiling && first_attempt) cudaEventRecord(ev_[5], s);
   return BNX_OK;
@@ -2683,7 +2823,7 @@ int Map::shard_finish(const void* flags_reduced, int* retry) {
   const int persistent = sm_count() * 8;
   const GridDev g = grid.dev();
   buf_.gate = static_cast<const u32*>(flags_reduced);
-  launch_scan_kernel(k_apply_leaves, sm_count() * APPLY_MIN_BLOCKS, TPB, s, g, sp_, buf_);
+  launch_scan_kernel(apply_tma() ? k_apply_leaves<true> : k_apply_leaves<false>, sm_count() * APPLY_MIN_BLOCKS, TPB, s, g, sp_, buf_);
   BNX_CUDA(cudaGetLastError());
   if (profiling) cudaEventRecord(ev_[4], s);
   BNX_CUDA(cudaMemcpyAsync(h_status_, d_sc_, sizeof(ScanCounters), cudaMemcpyDeviceToHost, s));
@@ -2976,7 +3116,7 @@ int Map::shard_insert(const void* points, i64 stride_bytes, i64 n, bool f64, u32
     if (!p2p) BNX_NCCL(api, api.AllReduce(flags, flags, 4, ncclUint32, ncclMax, static_cast<ncclComm_t>(comm_), s));
     if (async) {
       buf_.gate = p2p ? reinterpret_cast<const u32*>(mbox_) + MBOX_FLAGS4 : flags;
-      launch_scan_kernel(k_apply_leaves, sm_count() * APPLY_MIN_BLOCKS, TPB, s, grid.dev(), sp_, buf_);
+      launch_scan_kernel(apply_tma() ? k_apply_leaves<true> : k_apply_leaves<false>, sm_count() * APPLY_MIN_BLOCKS, TPB, s, grid.dev(), sp_, buf_);
       BNX_CUDA(cudaGetLastError());
       if (profiling) cudaEventRecord(ev_[4], s);
       buf_.gate = nullptr;

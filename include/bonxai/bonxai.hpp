@@ -108,6 +108,27 @@ class VoxelGrid {
     return (size_t)b;
   }
   void releaseUnusedMemory() { detail::check(bnx_grid_release_unused(handle_)); }
+
+  // Node-object API of the reference (bonxai.hpp:156-161 rootMap, :233-243 lastInnerGrid / lastLeafGrid / getLeafGrid,
+  // :572-586 allocateLeafGrid): it hands out host pointers to std::unordered_map / Grid<> nodes. The nodes of this grid
+  // live in device pools, so the members exist only to turn "no member named rootMap" into a message that says what to
+  // use instead; they fire when (and only when) a caller instantiates them.
+  template <class Dummy = void>
+  void rootMap() const {
+    static_assert(sizeof(Dummy) == 0, "bonxai_b200: rootMap() exposes host node objects; the nodes live in device pools. "
+                                      "Use forEachCell / bnx_grid_dump (cells), bnx_grid_stats (node counts) or Serialize().");
+  }
+  template <class Dummy = void>
+  void lastInnerGrid() const {
+    static_assert(sizeof(Dummy) == 0, "bonxai_b200: Accessor::lastInnerGrid()/lastLeafGrid()/getLeafGrid() return host node pointers; "
+                                      "use the batched accessor calls (getValues / setValues / isCellsOn) instead.");
+  }
+  template <class Dummy = void>
+  void allocateLeafGrid() const {
+    static_assert(sizeof(Dummy) == 0, "bonxai_b200: leaves are allocated by the device-side pools (bump allocator + free list); "
+                                      "there is no host-side LeafGrid to allocate.");
+  }
+
   [[nodiscard]] size_t activeCellsCount() const {
     int64_t n = 0;
     detail::check(bnx_grid_active_count(handle_, &n));
