@@ -731,12 +731,13 @@ int Grid::recover(const GridCounters& seen) {
   return BNX_OK;
 }
 
-int Grid::maintain(const GridCounters& seen) {
-  if ((u64)seen.n_roots * 2 > root_slots_) BNX_TRY(grow_root_table(root_slots_ * 4));
+int Grid::maintain(const GridCounters& seen, u64 extra_leaves, u64 extra_inner) {
+  // root table: under 50 % load now, and still under ~75 % if as many roots arrive again as there are inner nodes of head-room asked for
+  while (((u64)seen.n_roots + extra_inner) * 4 > root_slots_ * 3 || (u64)seen.n_roots * 2 > root_slots_) BNX_TRY(grow_root_table(root_slots_ * 4));
   // keep half a growth step of each pool free so that the next batch rarely needs the retry path
   const u64 ls = leaf_step(seen.n_leaves), is = inner_step(seen.n_inner);
-  if ((u64)seen.n_leaves + ls / 2 > dev_.leaf_cap) BNX_TRY(ensure_leaf_capacity((u64)seen.n_leaves + ls));
-  if ((u64)seen.n_inner + is / 2 > dev_.inner_cap) BNX_TRY(ensure_inner_capacity((u64)seen.n_inner + is));
+  if ((u64)seen.n_leaves + ls / 2 + extra_leaves > dev_.leaf_cap) BNX_TRY(ensure_leaf_capacity((u64)seen.n_leaves + ls + extra_leaves));
+  if ((u64)seen.n_inner + is / 2 + extra_inner > dev_.inner_cap) BNX_TRY(ensure_inner_capacity((u64)seen.n_inner + is + extra_inner));
   return BNX_OK;
 }
 

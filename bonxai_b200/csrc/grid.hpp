@@ -88,7 +88,9 @@ class Grid {
   // after a kernel reported ERR_* bits: clamp counters, grow the failing pools, clear the bits
   int recover(const GridCounters& seen);
   // proactive growth at quiet points (root table load factor, pool head-room)
-  int maintain(const GridCounters& seen);
+  // extra_leaves / extra_inner: head-room the caller knows it needs before the next quiet point (e.g. what the last
+  // window of a pipelined run allocated), on top of half a growth step
+  int maintain(const GridCounters& seen, u64 extra_leaves = 0, u64 extra_inner = 0);
   // zero_stream: where the new memory is zero-filled (default: the grid's stream). Mapping more memory behind the pools
   // does not wait for running kernels (VMM), so a caller may grow AHEAD of need on a side stream while scans run and
   // make its work stream wait for the fill.

@@ -3210,8 +3210,17 @@ int Map::shard_drain() {
   GridCounters sgc;
   BNX_TRY(scratch_->read_counters(&sgc));
   if (!gc.error) {
-    BNX_TRY(scratch_->maintain(sgc));
-    return grid.maintain(gc);
+    // head-room until the next collective drain: three times what the window that just ended allocated (a fleet step adds
+    // the leaves of `world` scans; the scratch grid mirrors most of the foreign map), so that a queued scan running short —
+    // a frozen pipeline and a synchronous replay on every rank — stays the exception
+    const u64 w_leaves = gc.n_leaves > drain_prev_[0] ? gc.n_leaves - drain_prev_[0] : 0, w_inner = gc.n_inner > drain_prev_[1] ? gc.n_inner - drain_prev_[1] : 0;
+    const u64 s_leaves = sgc.n_leaves > drain_prev_[2] ? sgc.n_leaves - drain_prev_[2] : 0, s_inner = sgc.n_inner > drain_prev_[3] ? sgc.n_inner - drain_prev_[3] : 0;
+    drain_prev_[0] = gc.n_leaves;
+    drain_prev_[1] = gc.n_inner;
+    drain_prev_[2] = sgc.n_leaves;
+    drain_prev_[3] = sgc.n_inner;
+    BNX_TRY(scratch_->maintain(sgc, 3 * s_leaves, 3 * s_inner));
+    return grid.maintain(gc, 3 * w_leaves, 3 * w_inner);
   }
   ++shard_stats[1];
   if (gc.error & ERR_PEER) {

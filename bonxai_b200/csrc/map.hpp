@@ -278,6 +278,7 @@ class Map {
   void* comm_ = nullptr;  // ncclComm_t
   AllGatherFn host_gather_ = nullptr;  // caller-supplied bootstrap (instead of NCCL)
   void* host_gather_ctx_ = nullptr;
+  u64 drain_prev_[4] = {0, 0, 0, 0};  // leaves / inner nodes of the map and of the scratch grid at the previous drain
   u32 drain_max_fill_ = 0;  // largest leaf-inbox fill (max over ranks, so equal on every rank) since the last drain
   DevBuf x_send1_, x_recv1_, x_send2_, x_recv2_, x_flags_, x_handles_;
   i64 cap_rec_ = 0, cap_leaf_ = 1 << 16;  // 80-B leaf records per sender block; doubled at a collective drain when half full

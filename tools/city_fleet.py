@@ -61,10 +61,16 @@ def main():
         jobs = [(s, v) for s in range(first, last) for v in mine]
         return pool.map_async(vehicle_scan, jobs, chunksize=max(1, len(jobs) // (procs * 4)))
 
-    pending = gen(0)
+    # all scans are generated BEFORE anything is timed: generator processes that run next to the timed windows take the
+    # cores the enqueueing threads need (one rank that is late to enqueue stalls every rank at the next exchange)
+    batches, first = [], 0
+    while first < args.steps:
+        batches.append(gen(first).get())
+        first += len(batches[-1]) // len(mine)
     oracle_jobs = [(s, v) for s in range(min(args.oracle_steps, args.steps)) for v in range(vehicles)] if rank == 0 else []
     oracle_scans = pool.map(vehicle_scan, oracle_jobs) if oracle_jobs else []
 
+    pool.terminate()
     import torch
     from bonxai_b200 import capi
     torch.cuda.set_device(local % torch.cuda.device_count())
@@ -99,10 +105,8 @@ def main():
     oracle_digest = None
     t_wall = time.perf_counter()
     while done < args.steps:
-        scans = pending.get()
+        scans = batches.pop(0)
         nsteps = len(scans) // len(mine)
-        if done + nsteps < args.steps:
-            pending = gen(done + nsteps)
         dev = [torch.from_numpy(p).cuda() for p, _ in scans]
         torch.cuda.synchronize()
         if world > 1:
@@ -147,7 +151,6 @@ def main():
                              "single_gpu_equals_oracle": sd == od}
             single.close()
             del om
-    pool.terminate()
     tt = gm.totals()
     N_all, U_all, V_all = allsum([tt["N"], tt["U"], tt["V"] + (tt["N"] if world > 1 else 0)])
     stats = sm.stats() if world > 1 else None
