@@ -2592,7 +2592,6 @@ int Map::shard_begin(const void* points, i64 stride_bytes, i64 n, bool f64, u32 
       }
     origin = &fleet[(size_t)rank_ * 3];
   }
-  sp_fleet_ = fleet;
   BNX_REQUIRE(f64 ? (stride_bytes >= 24 && stride_bytes % 8 == 0) : (stride_bytes >= 12 && stride_bytes % 4 == 0), "shard_begin: bad stride");
   if (!queue_.empty()) BNX_TRY(drain());  // single-GPU pipeline first; the sharded queue is drained collectively
   cudaStream_t s = grid.stream();
@@ -2687,6 +2686,7 @@ int Map::shard_begin(const void* points, i64 stride_bytes, i64 n, bool f64, u32 
   const u64 tslots = table_slots(cap_records);
   p.hash_mask = (u32)(tslots - 1);
   sp_ = p;
+  sp_fleet_ = fleet;  // (set here: the nested drains above run other scans through this function)
   shard_retries_ = 0;
   shard_attempt_ = 0;
   if (profiling) cudaEventRecord(ev_[0], s);
@@ -3073,6 +3073,10 @@ int Map::shard_insert(const void* points, i64 stride_bytes, i64 n, bool f64, u32
                       int where, bool async) {
   BNX_REQUIRE((comm_ != nullptr || host_gather_ != nullptr) && world_ > 1, "shard_insert: call shard_comm_init / shard_host_init first");
   BNX_REQUIRE(n_max >= n, "shard_insert: n_max must be the largest slice of the scan over all ranks");
+  // the fleet origins armed for THIS scan are set aside first: the drains below may replay queued scans, which arm (and
+  // consume) their own
+  std::vector<double> armed;
+  armed.swap(fleet_origins_);
   const NcclApi& api = nccl_api(nullptr);
   cudaStream_t s = grid.stream();
   if (!async) BNX_TRY(drain());
@@ -3106,6 +3110,7 @@ int Map::shard_insert(const void* points, i64 stride_bytes, i64 n, bool f64, u32
   shard_async_ = async;
   shard_async_id_ = my_async;
   shard_n_max_ = n_max;
+  fleet_origins_.swap(armed);
   BNX_TRY(shard_begin(points, stride_bytes, n, f64, index_base, origin, max_range, p2p ? nullptr : x_send1_.p, cap_rec_, where));
   sp_.async_id = my_async;
   if (!p2p) BNX_TRY(all_to_all(x_send1_.p, x_recv1_.p, (size_t)cap_rec_ * 16));

@@ -32,6 +32,36 @@ def main():
     if rank == 0:
         import oracle
         om = oracle.load("port").map(0.1)
+    if mode == "fleet":
+        # 80 pipelined FLEET steps without a sync in between: the queue fills (64), so the library drains inside an insert
+        # whose fleet origins are already armed; with tiny pools and 1 MB growth steps that drain finds a frozen pipeline and
+        # replays queued steps (each with its own origins) before the armed step runs
+        keep, steps = [], 80
+        for step in range(steps):
+            scans = []
+            for v in range(world):
+                pts, origin = synth.lidar_scan(step, beams=16, azimuths=256, seed=7 + v)
+                shift = np.float32([0.0, 150.0 * v, 0.0])
+                scans.append((np.ascontiguousarray(pts[:, :3] + shift), origin + shift))
+            mine = torch.from_numpy(scans[rank][0]).cuda()
+            keep.append(mine)
+            sm.insert_fleet(capi.DevPtr(mine.data_ptr()), len(scans[rank][0]), 12, len(scans[rank][0]), np.array([o for _, o in scans]), 40.0,
+                            use_async=True)
+            if rank == 0:
+                for pts, origin in scans:
+                    om.insert(pts, origin, 40.0)
+        sm.sync()
+        dig = sm.digest()
+        st = sm.stats()
+        if rank == 0:
+            assert dig == capi.digest_of_dump(*om.dump()), "fleet pipeline with replays: sharded map differs from the oracle"
+            assert st["replays"] > 0, st
+        dist.barrier()
+        sm.close()
+        if rank == 0:
+            print("SHARDED_OK", world, "fleet", st)
+        dist.destroy_process_group()
+        return
     keep = []
     for scan in range(6 if mode == "async" else 3):
         pts, origin = synth.lidar_scan(scan * 2, beams=32, azimuths=1024)

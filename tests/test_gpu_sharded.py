@@ -155,6 +155,16 @@ def test_processes_sharing_one_gpu(bnx, mode, tiny, world):
     assert r.returncode == 0 and "SHARDED_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
+def test_fleet_pipeline_replays_inside_a_queue_drain(bnx):
+    """regression (round 2, 8-GPU city run): a pipelined fleet step whose insert call first drains a full queue, and that
+    drain replays frozen steps, must keep ITS armed origins — 2 processes on GPU 0, 80 queued fleet steps, tiny pools"""
+    env = dict(os.environ, BNX_SHARD_TEST_MODE="fleet", BNX_SHARD_BOOTSTRAP="host", BNX_SHARD_EXCHANGE="p2p", BNX_PEER_TIMEOUT_MS="120000",
+               BNX_INIT_LEAF_MB="1", BNX_INIT_INNER_MB="0", BNX_GROW_MB="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29629", os.path.join(ROOT, "tests", "sharded_worker.py")], capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0 and "SHARDED_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
 @pytest.mark.parametrize("exchange", ["p2p", "nccl"])
 @pytest.mark.parametrize("mode,tiny", [("sync", False), ("async", False), ("async", True)])
 def test_nccl_two_ranks(bnx, mode, tiny, exchange):
