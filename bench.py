@@ -47,11 +47,11 @@ def load_peaks():
 
 def ncu_traffic(phase: str):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the phase's kernel, from the committed ncu --set full
-    capture of the current kernels (profiles/r1_ncu_summary_v4.json); None if that file has no entry."""
+    capture of the current kernels (profiles/r2_ncu_summary.json, tools/r2_call20.sh); None if that file has no entry."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_ncu_summary_v4.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_ncu_summary.json")) as f:
             k = json.load(f)["kernels"]
-        name = {"classify": "k_classify<0, 1, 1>", "resolve": "k_resolve<0>", "mark": "k_mark<0>", "apply": "k_apply_leaves"}[phase]
+        name = {"classify": "k_classify<0, 1, 1>", "resolve": "k_resolve<0, 0>", "mark": "k_mark<0>", "apply": "k_apply_leaves<0>"}[phase]
         e = k[name]
         scale = {"Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Gbyte": 1e9}
         tot = 0.0

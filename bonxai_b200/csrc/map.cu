@@ -2290,6 +2290,10 @@ int Map::insert_async(const void* points, i64 stride_bytes, i64 n, bool f64, con
         ++grown_ahead_;
       } else if (k > 0) {
         const AsyncRecord& q = h_ring_[queue_[k - 1].p.async_id & (RING - 1)];
+        // per-scan leaf growth: the largest recent value (decays by 2 % per look, floor 2048): the first scans of a map
+        // create far more leaves than the steady state, and a head-room estimate that never forgets them asks for
+        // gigabytes of free pool for ever (city run: a growth step on almost every insert)
+        max_leaf_growth_ = std::max<u64>(2048, max_leaf_growth_ - max_leaf_growth_ / 50);
         if (q.id == queue_[k - 1].p.async_id && r.n_leaves > q.n_leaves) max_leaf_growth_ = std::max<u64>(max_leaf_growth_, r.n_leaves - q.n_leaves);
       }
       break;
