@@ -4,7 +4,10 @@ It restates, in numpy, what the CUDA stages do on each rank — classify + local
 records to the owner of their root), owner-side lowest-global-index / stale verdict, ray casting by the endpoint's
 owner, exchange 2 (ray cells to the owner of *their* root), endpoint apply before ray apply — so that the
 protocol itself (who decides what, in which order, with which two exchanges) is checked against the CPU oracle
-without a GPU. Run by tests/test_shard_protocol_cpu.py with world_size 2 and 3.
+without a GPU; then FLEET steps (every rank inserts the scan of its own sensor): the sender of an endpoint
+record names its sensor, rays start at that sensor's origin, every touched cell is stamped with the update id the
+sensor's scan would have had in a sequence of consecutive inserts. Run by tests/test_shard_protocol_cpu.py with
+world_size 2 and 3.
 
 Two flavours of the exchanges (BNX_MODEL_EXCHANGE):
   gather    an all_gather_object of the per-destination buckets (gloo has no all_to_all)
@@ -137,19 +140,32 @@ def exchange(buckets, kind=0):
         for b in buckets:
             if isinstance(b, tuple):  # endpoint records: (cells (n,3), prio (n,))
                 packed.append(np.concatenate([b[0].astype(np.int64), b[1].astype(np.int64)[:, None]], axis=1))
-            else:                     # ray cells (n,3)
-                packed.append(np.concatenate([b.astype(np.int64), np.zeros((len(b), 1), np.int64)], axis=1))
+            else:                     # ray cells (n,3) or, in a fleet step, (n,4): cell + sensor
+                b = np.asarray(b).reshape(len(b), -1)
+                pad = np.zeros((len(b), 4 - b.shape[1]), np.int64)
+                packed.append(np.concatenate([b.astype(np.int64), pad], axis=1))
         got = MBOX.exchange(kind, packed)
         if isinstance(buckets[0], tuple):
             return [(g[:, :3].astype(np.int32), g[:, 3]) for g in got]
-        return [g[:, :3].astype(np.int32) for g in got]
+        width = max([np.asarray(b).reshape(len(b), -1).shape[1] for b in buckets if len(b)] + [3])
+        return [g[:, :width].astype(np.int32) for g in got]
     gathered = [None] * world
     dist.all_gather_object(gathered, buckets)
     return [gathered[src][rank] for src in range(world)]
 
 
-def sharded_insert(shard: dict, c: int, pts_local, index_base, origin, max_range, res):
-    world = dist.get_world_size()
+def scan_c(c: int, sensor: int) -> int:
+    """update id of the sensor-th consecutive insert starting at id c (probabilistic_map.cpp:103-105)"""
+    return (c - 1 + sensor) % 3 + 1
+
+
+def sharded_insert(shard: dict, c: int, pts_local, index_base, origin, max_range, res, fleet=None):
+    """fleet = None: one scan, this rank holds the points [index_base, ...) of it. fleet = origins of ALL sensors: a fleet
+    step, this rank holds the whole scan of sensor `rank`; the sender of an endpoint record (= the inbox block it arrives
+    in) names its sensor, whose origin the ray starts at and whose update id stamps everything the scan touches."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    if fleet is not None:
+        origin = fleet[rank]
     # ---- stage A: classify my slice, keep the lowest LOCAL index per voxel, send to the root's owner
     cells, miss = classify(pts_local, origin, max_range, res)
     _, first = np.unique(cells, axis=0, return_index=True)
@@ -160,39 +176,45 @@ def sharded_insert(shard: dict, c: int, pts_local, index_base, origin, max_range
     # ---- stage B (owner): lowest GLOBAL index wins, stale test against MY shard, rays only for fresh endpoints
     ecells = np.concatenate([g[0] for g in got])
     eprio = np.concatenate([g[1] for g in got])
+    esrc = np.concatenate([np.full(len(g[1]), src, np.int64) for src, g in enumerate(got)])  # which rank sent it = its sensor
     order = np.argsort(eprio, kind="stable")
-    ecells, eprio = ecells[order], eprio[order]
+    ecells, eprio, esrc = ecells[order], eprio[order], esrc[order]
     _, keep = np.unique(ecells, axis=0, return_index=True)
-    O = np.floor(origin.astype(np.float64) * (1.0 / res)).astype(np.int64)
+    origins = fleet if fleet is not None else [origin] * world
+    Os = [np.floor(np.asarray(o, np.float64) * (1.0 / res)).astype(np.int64) for o in origins]
     endpoints, out_cells = [], [[] for _ in range(world)]
     for i in sorted(keep):
         key = tuple(int(v) for v in ecells[i])
-        if (shard.get(key, 0) & 0xF) == c:
+        sensor = int(esrc[i]) if fleet is not None else 0
+        ci = scan_c(c, sensor)
+        if (shard.get(key, 0) & 0xF) == ci:
             continue  # stale update_id: skipped AND no ray is cast
-        endpoints.append((key, int(eprio[i]) & 1))
-        rc = ray_cells(O, ecells[i])
+        endpoints.append((key, int(eprio[i]) & 1, ci))
+        rc = ray_cells(Os[sensor], ecells[i])
         if len(rc):
             ro = owner_of(rc, world)
+            tagged = np.concatenate([rc, np.full((len(rc), 1), sensor, np.int32)], axis=1)  # the sensor travels with the cell
             for o in range(world):
-                out_cells[o].append(rc[ro == o])
-    send = [np.unique(np.concatenate(b), axis=0) if b else np.zeros((0, 3), np.int32) for b in out_cells]
+                out_cells[o].append(tagged[ro == o])
+    send = [np.unique(np.concatenate(b), axis=0) if b else np.zeros((0, 4), np.int32) for b in out_cells]
     got = exchange(send, 1)
-    # ---- stage C (owner): endpoints first, then every ray cell whose id is not the current one
-    for key, is_miss in endpoints:
+    # ---- stage C (owner): endpoints first, then every ray cell whose id is not its scan's
+    for key, is_miss, ci in endpoints:
         w = shard.get(key, 0)
         p = (w >> 4) if w < 2**31 else ((w - 2**32) >> 4)
         p = max(p + MISS, CMIN) if is_miss else min(p + HIT, CMAX)
-        shard[key] = ((p << 4) | c) & 0xFFFFFFFF
+        shard[key] = ((p << 4) | ci) & 0xFFFFFFFF
     for block in got:
         for cell in block:
             key = (int(cell[0]), int(cell[1]), int(cell[2]))
+            ci = scan_c(c, int(cell[3]))
             w = shard.get(key, 0)
-            if (w & 0xF) != c:
+            if (w & 0xF) != ci:
                 p = (w >> 4) if w < 2**31 else ((w - 2**32) >> 4)
-                shard[key] = ((max(p + MISS, CMIN) << 4) | c) & 0xFFFFFFFF
+                shard[key] = ((max(p + MISS, CMIN) << 4) | ci) & 0xFFFFFFFF
     if MBOX is not None:
         assert MBOX.flags(0) == 0  # every rank has consumed both inboxes of this scan: they may be overwritten now
-    return 1 if c == 3 else c + 1
+    return scan_c(c, world if fleet is not None else 1)
 
 
 def main():
@@ -221,6 +243,28 @@ def main():
             xyz, words = om.dump()
             want = {tuple(int(v) for v in x): int(w) for x, w in zip(xyz, words)}
             assert union == want, f"scan {k}: sharded model differs from the oracle ({len(union)} vs {len(want)} cells)"
+    # ---- fleet steps: every rank holds the scan of its OWN sensor (parallel streets, reach not overlapping); the result
+    # must equal the sensors' scans inserted one after the other, each with its own update id. Sensor 1 stands still,
+    # so its endpoints turn stale when the id sequence comes round.
+    for step in range(4):
+        scans = []
+        for v in range(world):
+            pts, origin = synth.lidar_scan(step if v != 1 else 0, beams=8, azimuths=96, seed=7 + v)
+            shift = np.float32([0.0, 40.0 * v, 0.0])  # max_range 12 m: streets 40 m apart never share a cell
+            scans.append((np.ascontiguousarray(pts[:, :3] + shift), origin + shift))
+        c = sharded_insert(shard, c, scans[rank][0], rank * len(scans[0][0]), None, max_range, res, fleet=[o for _, o in scans])
+        gathered = [None] * world
+        dist.all_gather_object(gathered, shard)
+        if rank == 0:
+            for pts, origin in scans:
+                om.insert(pts, origin, max_range)
+            union = {}
+            for g in gathered:
+                assert not (set(g) & set(union)), "shards overlap"
+                union.update(g)
+            xyz, words = om.dump()
+            want = {tuple(int(v) for v in x): int(w) for x, w in zip(xyz, words)}
+            assert union == want, f"fleet step {step}: sharded model differs from the oracle ({len(union)} vs {len(want)} cells)"
     dist.barrier()
     if MBOX is not None:
         MBOX.close()
