@@ -165,18 +165,28 @@ def test_fleet_pipeline_replays_inside_a_queue_drain(bnx):
     assert r.returncode == 0 and "SHARDED_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
-@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
-@pytest.mark.parametrize("mode,tiny", [("sync", False), ("async", False), ("async", True)])
-def test_nccl_two_ranks(bnx, mode, tiny, exchange):
-    """the native driver (bnx_map_shard_insert) on 2 GPUs, one process each, with the peer-memory exchange (CUDA IPC
-    mailboxes over NVLink) and with NCCL collectives: synchronous, pipelined, and pipelined with pools so small that a
-    queued scan runs short and all ranks freeze + replay"""
-    import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
-    env = dict(os.environ, BNX_SHARD_TEST_MODE=mode, BNX_SHARD_EXCHANGE=exchange)
-    if tiny:
-        env.update(BNX_INIT_LEAF_MB="2", BNX_INIT_INNER_MB="0")
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29611", os.path.join(ROOT, "tests", "sharded_worker.py")], capture_output=True, text=True, timeout=900, env=env)
-    assert r.returncode == 0 and "SHARDED_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+def _gpus() -> int:
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:  # noqa: BLE001
+        return 0
+
+
+# NCCL refuses two ranks on one device, so these cases only EXIST on a box with >= 2 GPUs (they are collected there and
+# absent elsewhere, instead of showing up as six skips); on a 1-GPU box the same driver, kernels and protocol run as
+# test_processes_sharing_one_gpu (handles through a host callback instead of ncclAllGather).
+if _gpus() >= 2:
+
+    @pytest.mark.parametrize("exchange", ["p2p", "nccl"])
+    @pytest.mark.parametrize("mode,tiny", [("sync", False), ("async", False), ("async", True)])
+    def test_nccl_two_ranks(bnx, mode, tiny, exchange):
+        """the native driver (bnx_map_shard_insert) on 2 GPUs, one process each, with the peer-memory exchange (CUDA IPC
+        mailboxes over NVLink, handles through ncclAllGather) and with NCCL collectives: synchronous, pipelined, and pipelined
+        with pools so small that a queued scan runs short and all ranks freeze + replay"""
+        env = dict(os.environ, BNX_SHARD_TEST_MODE=mode, BNX_SHARD_EXCHANGE=exchange)
+        if tiny:
+            env.update(BNX_INIT_LEAF_MB="2", BNX_INIT_INNER_MB="0")
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                            "--master-port", "29611", os.path.join(ROOT, "tests", "sharded_worker.py")], capture_output=True, text=True, timeout=900, env=env)
+        assert r.returncode == 0 and "SHARDED_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
