@@ -448,7 +448,7 @@ def run_gpu(args):
             line["parity"] = {"scans": n_cpu, "oracle": kind, "active_cells": dig_gpu[2], "gpu_digest_equals_oracle": dig_gpu == dig_cpu,
                               "passes_agree": bool(digests_agree)}
             if not args.no_dropin:
-                dd = run_dropin(scans, W)
+                dd = run_dropin(scans[:W + min(K, 100)], W)  # bounded: at most 100 timed scans per mode
                 line["e2e_dropin"] = {
                     "call": "Bonxai::ProbabilisticMap::insertPointCloud(std::vector<PointXYZ>, origin, max_range) through include/ (C++), "
                             "synchronous per scan, separate process",
