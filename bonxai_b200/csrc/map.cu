@@ -2393,7 +2393,8 @@ int Map::complete_queue() {
   done_upto_ = 0;
   // pool head-room for the next scans, from the record (no device read); growing synchronises, but only when it grows
   const GridDev g = grid.dev();
-  if ((u64)gc.n_roots * 2 > (u64)g.root_mask + 1 || (u64)gc.n_leaves * 2 > g.leaf_cap || (u64)gc.n_inner * 2 > g.inner_cap) {
+  if ((u64)gc.n_roots * 2 > (u64)g.root_mask + 1 || (u64)gc.n_leaves + grid.leaf_step(gc.n_leaves) / 2 > g.leaf_cap ||
+      (u64)gc.n_inner + grid.inner_step(gc.n_inner) / 2 > g.inner_cap) {  // the thresholds of Grid::maintain
     BNX_CUDA(cudaStreamSynchronize(s));
     BNX_CUDA(cudaStreamSynchronize(pre_stream_));
     return grid.maintain(gc);
