@@ -91,3 +91,24 @@ def test_host_ray_iterator_matches_oracle(port, tmp_path):
         out = subprocess.run([str(exe), *map(str, a + b)], capture_output=True, text=True, check=True).stdout
         got = np.array([[int(t) for t in l.split()] for l in out.splitlines()], np.int32).reshape(-1, 3)
         assert np.array_equal(got, port.compute_ray(a, b))
+
+
+def test_dropin_bench_tool_compiles(tmp_path):
+    """tools/cpp/dropin_bench.cpp (the caller bench.py times for e2e_dropin / e2e_insert_publish) builds against include/"""
+    exe = tmp_path / "dropin_bench"
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tools/cpp/dropin_bench.cpp"),
+                        "-L", os.path.join(ROOT, "bonxai_b200"), "-lbonxai_b200", "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+
+
+def test_node_object_api_fails_to_compile_with_a_message(tmp_path):
+    """rootMap() & co hand out host node objects upstream (bonxai.hpp:156-161,233-243); here a caller that uses them gets a
+    compile-time message naming the replacement instead of 'no member named rootMap'"""
+    src = tmp_path / "uses_rootmap.cpp"
+    src.write_text('#include "bonxai/bonxai.hpp"\nint main() { Bonxai::VoxelGrid<int> g(0.1); g.rootMap(); return 0; }\n')
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)], capture_output=True, text=True)
+    assert r.returncode != 0 and "the nodes live in device pools" in r.stderr, r.stderr[-2000:]
+    ok = tmp_path / "plain.cpp"
+    ok.write_text('#include "bonxai/bonxai.hpp"\nint main() { Bonxai::VoxelGrid<int> g(0.1); return (int)g.activeCellsCount(); }\n')
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(ok)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
