@@ -238,7 +238,8 @@ BNX_API int bnx_map_phase_times(bnx_map_t* m, double out_us[8]);
  *                       shard_resolve_mark with the same recv_records (bits 8.. say which exchange buffer to grow)
  *
  * All buffers are device memory on the map's stream. The union of the shards equals the unsharded map bit for
- * bit. Needs a finite max_range; addHitPoint/addMissPoint queues are not supported on a sharded map.
+ * bit. max_range may be +inf and voxel coordinates arbitrary (the dedupe tables then hold full keys instead of the
+ * packed 63-bit ones); addHitPoint/addMissPoint queues are not supported on a sharded map.
  * ---------------------------------------------------------------------------------------------- */
 BNX_API int bnx_map_shard_config(bnx_map_t* m, int rank, int world);
 BNX_API int bnx_map_shard_begin(bnx_map_t* m, const void* points, int64_t stride_bytes, int64_t n, int is_f64,
