@@ -54,7 +54,24 @@ def workloads():
     w["rand_f64"] = _rand_scans(2, 0.037, 4, 2000, 1.0, float("inf"), np.float64)
     w["lidar_0_2"] = (0.1, [(*synth.lidar_scan(s), 50.0) for s in range(3)])
     w["depth_small"] = (0.01, [(*synth.depth_scan(s, width=320, height=200), 5.0) for s in range(2)])
+    w["fleet_3x4"] = (0.1, [(pts, origin, 40.0) for step in fleet_steps() for pts, origin in step])
     return w
+
+
+def fleet_steps(world: int = 3, steps: int = 4):
+    """[[(points, origin) of sensor 0..world-1] for every step]: three vehicles on parallel streets 150 m apart (reach 40 m:
+    no cell is shared), sensor 1 standing still. Inserted one after the other — sensor 0, 1, 2, then the next step — this
+    is the sequence a FLEET step of a sharded map must reproduce (bnx_map_shard_set_fleet); the golden digests after
+    every insert come from the unmodified reference."""
+    out = []
+    for step in range(steps):
+        scans = []
+        for s in range(world):
+            pts, origin = synth.lidar_scan(step if s != 1 else 0, beams=16, azimuths=512, seed=7 + s)
+            shift = np.float32([0.0, 150.0 * s, 0.0])
+            scans.append((np.ascontiguousarray(pts[:, :3] + shift), origin + shift))
+        out.append(scans)
+    return out
 
 
 def run(make_map, name_filter=None):

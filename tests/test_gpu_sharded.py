@@ -98,6 +98,22 @@ def test_fleet_step_equals_consecutive_inserts(bnx, port, world, exchange):
     assert_same_dump(g.dump(), om.dump(), "single scan after fleet steps")
 
 
+@pytest.mark.parametrize("exchange", ["transpose", "p2p"])
+def test_fleet_steps_match_the_reference_golden(bnx, exchange):
+    """the golden fleet sequence (tests/golden/workloads.py::fleet_steps): digests produced by the UNMODIFIED reference
+    inserting the vehicles' scans one after the other; a sharded map must show the digest of 'after the last vehicle of
+    step k' after its k-th fleet step"""
+    import json
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import workloads as W
+    from bonxai_b200.sharded import LocalShardGroup
+    golden = json.load(open(os.path.join(ROOT, "tests", "golden", "map_golden.json")))["digests"]["fleet_3x4"]
+    g = LocalShardGroup(0.1, 3, exchange=exchange)
+    for k, scans in enumerate(W.fleet_steps()):
+        g.insert_fleet(scans, 40.0)
+        assert W.digest(*g.dump(sort=False)) == golden[3 * k + 2], f"fleet step {k}"
+
+
 def test_fleet_step_refuses_overlapping_sensors(bnx):
     from bonxai_b200.sharded import LocalShardGroup
     g = LocalShardGroup(0.1, 2, exchange="p2p")
