@@ -314,7 +314,7 @@ def run_gpu(args):
     # Python thread on a shared VM core, and one descheduling of ~10 ms is 1/3 of the whole timed region.
     sampler = ClockSampler(local_rank)
     sampler.start()
-    value_runs, launches, enqueue_us, tt = [], 0, 0.0, None
+    value_runs, launches, enqueue_us, tt, pool = [], 0, 0.0, None, None
     run_digests = [sync_digest]
     for rep in range(2 if world == 1 else 1):
         m = capi.ProbabilisticMap(RES)
@@ -339,6 +339,12 @@ def run_gpu(args):
         assert m.active_count() == active, "pipelined and synchronous passes disagree"
         tt = m.totals()
         run_digests.append(m.digest())
+        try:  # pool usage at the end of the run: bytes mapped behind the leaf / inner pools vs bytes of live leaves
+            gst = m.grid().stats()
+            pool = {"leaves_live": int(gst["leaves"]), "leaf_bytes_live": int(gst["leaves"]) * 2304, "mapped_bytes": int(gst["mapped_bytes"]),
+                    "mapped_over_live": gst["mapped_bytes"] / max(1, gst["leaves"] * 2304)}
+        except Exception as e:  # noqa: BLE001
+            pool = {"error": repr(e)}
         del m
         settle()
     clocks = sampler.stop()
@@ -430,6 +436,7 @@ def run_gpu(args):
             "e2e": {"value": world * K * N_PTS / e2e_s, "unit": "points/s", "h2d_bytes_per_step": N_PTS * 16, "d2h_bytes_per_step": 64,
                     "ms_per_step": 1e3 * e2e_s / K, "runs_ms_per_step": [1e3 * r / K for r in e2e_runs], "reported": "min of the runs"},
             "gpu_launches": int(launches_all),
+            "pool": pool,
             "host_enqueue_us_per_scan": {"device_buffers": enqueue_us, "host_buffers": enqueue_e2e_us},
             "clocks": clocks,
         }
