@@ -134,6 +134,30 @@ def nccl_library_path():
     return "libnccl.so.2"
 
 
+GATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64)  # bnx_allgather_fn (include/bonxai_b200.h)
+
+
+def host_allgather_callback(group=None):
+    """the bnx_allgather_fn a host program hands to bnx_map_shard_host_init, here over torch.distributed (any backend that
+    moves CPU tensors, e.g. gloo): gathers `nbytes` bytes of host memory from every rank into recv[world][nbytes]"""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+
+    def gather(ctx, send, recv, nbytes):
+        try:
+            mine = torch.frombuffer(bytearray(C.string_at(send, nbytes)), dtype=torch.uint8)
+            parts = [torch.empty(nbytes, dtype=torch.uint8) for _ in range(world)]
+            dist.all_gather(parts, mine, group=group)
+            C.memmove(recv, b"".join(bytes(p.tolist()) for p in parts), nbytes * world)
+            return 0
+        except Exception as e:  # noqa: BLE001
+            print("bootstrap all-gather failed:", repr(e), file=sys.stderr)
+            return 1
+
+    return GATHER_FN(gather)
+
+
 class ShardedMap:
     """one rank of a map sharded over torch.distributed ranks (one process per GPU). torch.distributed is only used to
     hand the NCCL unique id around; the per-scan exchanges are issued by the library itself (bnx_map_shard_insert)."""
@@ -151,20 +175,7 @@ class ShardedMap:
         self.lib = self.map.lib
         self.map.set_stream(torch.cuda.current_stream().cuda_stream)
         if bootstrap == "host":
-            world = self.world
-
-            def gather(ctx, send, recv, nbytes):
-                try:
-                    mine = torch.frombuffer(bytearray(C.string_at(send, nbytes)), dtype=torch.uint8)
-                    parts = [torch.empty(nbytes, dtype=torch.uint8) for _ in range(world)]
-                    dist.all_gather(parts, mine, group=group)
-                    C.memmove(recv, b"".join(bytes(p.tolist()) for p in parts), nbytes * world)
-                    return 0
-                except Exception as e:  # noqa: BLE001
-                    print("bootstrap all-gather failed:", repr(e), file=sys.stderr)
-                    return 1
-
-            self._gather_cb = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64)(gather)  # keep alive
+            self._gather_cb = host_allgather_callback(group)  # keep alive as long as the map
             capi._check(self.lib.bnx_map_shard_host_init(self.map.h, self.rank, self.world, self._gather_cb, None))
             return
         path = nccl_library_path().encode()

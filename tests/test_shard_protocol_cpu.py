@@ -27,3 +27,13 @@ def test_split_points_covers_every_index_once():
             parts = split_points(n, world)
             assert parts[0][0] == 0 and parts[-1][1] == n and all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
             assert max(h - l for l, h in parts) - min(h - l for l, h in parts) <= 1
+
+
+@pytest.mark.parametrize("world,port", [(2, 29721), (3, 29722)])
+def test_host_bootstrap_callback_over_gloo(world, port):
+    """the caller-supplied all-gather of bnx_map_shard_host_init (mailbox handles without NCCL), called through its C
+    function pointer by 2 and 3 gloo processes"""
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), os.path.join(ROOT, "tests", "bootstrap_worker.py")], capture_output=True, text=True, timeout=300,
+                       env=dict(os.environ, OMP_NUM_THREADS="1"))
+    assert r.returncode == 0 and f"BOOTSTRAP_OK {world}" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
