@@ -95,6 +95,35 @@ def test_port_vs_reference_live_maps(port, ref):
         assert np.array_equal(pm.get_voxels(0), rm.get_voxels(0)) and np.array_equal(pm.get_voxels(2), rm.get_voxels(2))
 
 
+def test_port_vs_reference_edge_inputs(port, ref):
+    """inputs that sit on the corners of the algorithm (bonxai_map/src/probabilistic_map.cpp:79-141 and
+    bonxai_core/include/bonxai/grid_coord.hpp posToCoord): points exactly on voxel faces (floor of x / res), negative
+    coordinates next to zero, rays of length zero, points further than max_range (clamped to the range sphere and cast as
+    misses), the same endpoint many times, voxel coordinates beyond +-2^20, a scan of one point and an empty scan"""
+    rng = np.random.default_rng(23)
+    res = 0.125  # exactly representable: k * res lands on voxel faces in both float widths
+    lattice = (rng.integers(-40, 40, (1500, 3)) * res)
+    near_zero = rng.choice([-res, -1e-7, -0.0, 0.0, 1e-7, res], (600, 3))
+    far = np.float64([4.0e5, -3.0e5, 2.5e5])  # ~3.2e6 voxels out
+    scans = [(lattice, np.zeros(3), 3.0),
+             (lattice.astype(np.float32), np.float32([res, res, res]), 1.0),       # origin on a voxel corner, mostly clamped
+             (near_zero, np.float64([0.0, 0.0, 0.0]), float("inf")),                # includes zero-length rays
+             (np.repeat(lattice[:7], 200, axis=0), np.float64([0.3, -0.2, 0.1]), 2.0),
+             (lattice + far, far, 2.5),
+             ((lattice + far).astype(np.float32), far.astype(np.float32), float("inf")),
+             (lattice[:1], np.float64([1.0, 1.0, 1.0]), 10.0),
+             (lattice[:0], np.zeros(3), 10.0),
+             (lattice, np.zeros(3), 0.0)]                                           # range 0: every point clamps onto the origin
+    pm, rm = port.map(res), ref.map(res)
+    for k, (pts, origin, rmax) in enumerate(scans):
+        pts = np.ascontiguousarray(pts)
+        pm.insert(pts, origin, rmax)
+        rm.insert(pts, origin, rmax)
+        assert_same_dump(pm.dump(), rm.dump(), f"edge scan {k}")
+    assert pm.active_count() > 20000 and len(pm.get_voxels(0)) > 500  # the comparison is not vacuous
+    assert np.array_equal(pm.get_voxels(0), rm.get_voxels(0)) and np.array_equal(pm.get_voxels(1), rm.get_voxels(1))
+
+
 def test_port_counters_match_dump_diff(port, ref):
     """U (cells whose word changed) counted natively by the port == dump diff measured on the reference"""
     from bonxai_b200 import synth
